@@ -1,0 +1,11 @@
+"""`import MAS_library as MASL` resolving to the B200-native implementation.
+
+Put this directory (dropin/) on PYTHONPATH ahead of the Pylians3 install; see INTEGRATION.md."""
+import os as _os
+import sys as _sys
+
+_root = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+if _root not in _sys.path:
+    _sys.path.insert(0, _root)
+from pylians3_b200.MAS_library import *  # noqa: E402,F401,F403
+from pylians3_b200.MAS_library import MA  # noqa: E402,F401

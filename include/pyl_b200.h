@@ -1,0 +1,177 @@
+/* pyl_b200.h -- C ABI of the B200-native density-field / power-spectrum hot path.
+ *
+ * This is the drop-in boundary for the path
+ *     MAS_library.MA -> FFT3Dr_f -> Pk_library.Pk / XPk
+ * of Pylians3.  Every entry point is `extern "C"`, takes plain pointers and sizes, returns
+ * an int status (0 = PYL_OK, negative = error; never throws, never exits) and is ordered
+ * on the CUDA stream it is given.  No torch types appear here.
+ *
+ * Reference interfaces replaced (paths relative to the Pylians3 tree):
+ *   library/MAS_library/MAS_c.h:3-10          void NGP|CIC|TSC|PCS(FLOAT *pos, FLOAT *number,
+ *                                             FLOAT *W, long particles, int dims, int axes,
+ *                                             FLOAT BoxSize, int threads)
+ *   library/MAS_library/MAS_library.pyx:72-80 MA()'s dispatch to NGP/CIC/TSC/PCS(+W)
+ *   library/Pk_library/Pk_library.pyx:117-130 FFT3Dr_f(a, threads)
+ *   library/Pk_library/Pk_library.pyx:311-378 Pk.__init__ hot loop   (no native ABI exists)
+ *   library/Pk_library/Pk_library.pyx:623-732 XPk.__init__ hot loop  (no native ABI exists)
+ *
+ * Ownership: all device pointers are BORROWED.  The device-pointer entry points never
+ * allocate: scratch memory is passed in (`ws`, sized by the matching *_workspace_bytes
+ * query).  Only the host-pointer convenience entry points (section 4) own a grow-only
+ * device arena.
+ */
+#ifndef PYL_B200_H
+#define PYL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cudaStream_t without dragging cuda_runtime.h into C / Cython / cgo consumers */
+typedef struct CUstream_st *pyl_stream_t;
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define PYL_OK 0
+#define PYL_ERR_ARG (-1)       /* bad argument (NULL pointer, unknown scheme, bad axes ...) */
+#define PYL_ERR_CUDA (-2)      /* a CUDA runtime call or kernel launch failed               */
+#define PYL_ERR_CUFFT (-3)     /* a cuFFT call failed                                       */
+#define PYL_ERR_WORKSPACE (-4) /* workspace missing or smaller than *_workspace_bytes()     */
+#define PYL_ERR_DOMAIN (-5)    /* slab deposit: a particle's stencil left the local planes  */
+
+const char *pyl_error_string(int status);
+/* detail of the last failure on the calling thread ("" if none) */
+const char *pyl_last_error(void);
+/* "pyl_b200 <version> sm_100a" */
+const char *pyl_version(void);
+
+/* ---- 1. mass assignment ------------------------------------------------------------ */
+/* scheme ids; the MAS window exponent of Pk_library.pyx:72-78 is (id + 1) */
+#define PYL_MAS_NGP 0
+#define PYL_MAS_CIC 1
+#define PYL_MAS_TSC 2
+#define PYL_MAS_PCS 3
+
+/* deposit algorithms */
+#define PYL_MODE_AUTO (-1)         /* pick by particle density and scheme                  */
+#define PYL_MODE_ATOMIC 0          /* one red.global.add.f32 per stencil cell              */
+#define PYL_MODE_TILED 1           /* bucket by tile, accumulate in shared memory, flush   */
+#define PYL_MODE_DETERMINISTIC 2   /* as TILED, fixed summation order: bit-reproducible    */
+
+/* Scratch bytes pyl_deposit needs for this problem (0 for PYL_MODE_ATOMIC). */
+size_t pyl_deposit_workspace_bytes(int mas, int64_t particles, int dims, int axes, int mode);
+
+/* number[dims^axes] (float32, C order, DEVICE) += deposit of `particles` particles.
+ *   pos : DEVICE float32 [particles][axes], C-contiguous, 0 <= pos <= BoxSize
+ *   W   : DEVICE float32 [particles] or NULL
+ *   axes: 3, or 2 (plane; like the reference each particle then lands 1/2/3/4 times, i.e.
+ *         the plane is 1x/2x/3x/4x the 2D deposit -- MAS_library.pyx:84-110 divides after)
+ * Arithmetic follows MAS_library.pyx:123-166,273-292,369-404,463-497 (+W variants): the
+ * cell coordinate is the ROUNDED float32 product pos*(dims/BoxSize).
+ * Replaces MAS_c.h:3-10 / MAS_library.pyx:72-80. */
+int pyl_deposit(int mas, const float *pos, float *number, const float *W, int64_t particles,
+                int dims, int axes, float BoxSize, int mode, void *ws, size_t ws_bytes,
+                pyl_stream_t stream);
+
+/* Slab variant for one rank of a multi-GPU run (x-slab decomposition).
+ * `number` holds `x_planes` consecutive x-planes of the global grid starting at global
+ * plane `x_origin` (periodic: plane index is taken modulo dims), i.e. the rank's own planes
+ * plus its ghost planes.  A stencil cell whose x-plane falls outside is NOT deposited and is
+ * counted in *dropped (DEVICE int64, may be NULL; the caller checks it is 0). 3D only. */
+int pyl_deposit_slab(int mas, const float *pos, float *number, const float *W,
+                     int64_t particles, int dims, float BoxSize, int x_origin, int x_planes,
+                     int64_t *dropped, pyl_stream_t stream);
+
+/* x[i] /= divisor, IEEE float32 division: the 2D renormalisation `number2 /= 2.0|3.0|4.0`
+ * of MAS_library.pyx:90-107 */
+int pyl_divide_inplace(float *x, int64_t n, float divisor, pyl_stream_t stream);
+/* x[i] *= factor */
+int pyl_scale_inplace(float *x, int64_t n, float factor, pyl_stream_t stream);
+/* x[i] = x[i]*a + b */
+int pyl_affine_inplace(float *x, int64_t n, float a, float b, pyl_stream_t stream);
+/* out[0] = sum_i x[i] accumulated in float64 (DEVICE double; zeroed by the call) */
+int pyl_sum_f64(const float *x, int64_t n, double *out, pyl_stream_t stream);
+/* x[i] = float(double(x[i]) / (sum[0]/count)) - 1 : delta = n/<n> - 1 exactly as the reference's
+ * callers compute it in NumPy (docs/source/construction.rst:50, Pk_snapshot.py:88).  `sum` is a
+ * DEVICE double (e.g. from pyl_sum_f64, all-reduced across ranks), so no host sync is needed. */
+int pyl_overdensity_inplace(float *x, int64_t n, const double *sum, double count, pyl_stream_t stream);
+/* out[i] += in[i] (ghost-plane merge after the halo exchange) */
+int pyl_add_inplace(float *out, const float *in, int64_t n, pyl_stream_t stream);
+
+/* ---- 2. FFT stage (cuFFT; replaces FFT3Dr_f, Pk_library.pyx:117-130) ---------------- */
+/* Unnormalised forward r2c, (dims,dims,dims) float32 -> (dims,dims,dims/2+1) complex64,
+ * C order, out of place; `delta` is not modified.  Plans are cached per (dims, device). */
+size_t pyl_fft_r2c_workspace_bytes(int dims);
+int pyl_fft_r2c(const float *delta, float *delta_k /* interleaved re,im */, int dims, void *ws,
+                size_t ws_bytes, pyl_stream_t stream);
+
+/* Pieces of the slab-decomposed distributed transform:
+ *   stage 1: `nx` local x-planes, batched 2D r2c over (y,z): (nx,dims,dims) -> (nx,dims,nz)
+ *   stage 2: after the all-to-all transpose, 1D c2c along x IN PLACE on (dims, nky, nz)   */
+size_t pyl_fft_slab_workspace_bytes(int dims, int nx, int nky);
+int pyl_fft_slab_yz(const float *slab, float *slab_k, int dims, int nx, void *ws, size_t ws_bytes,
+                    pyl_stream_t stream);
+int pyl_fft_slab_x(float *cols_k, int dims, int nky, void *ws, size_t ws_bytes,
+                   pyl_stream_t stream);
+/* release every cached cuFFT plan of the calling thread's current device */
+int pyl_fft_clear_plans(void);
+
+/* ---- 3. |delta_k|^2 binning (replaces Pk_library.pyx:311-378 and :623-732) ---------- */
+/* Offsets (in 8-byte words) of each accumulator inside the single output buffer.
+ * F fields, X = F(F-1)/2 pairs (i<j lexicographic).  Nm* are uint64 counts, the rest are
+ * float64 RAW sums (no units, DC bin included), exactly the accumulators of the reference
+ * loop before Pk_library.pyx:384 / :735:
+ *   k3D[kmax+1]  Nm3D[kmax+1]  Pk3D[kmax+1][3][F]  PkX3D[kmax+1][3][X]  phase[kmax+1]
+ *   Nm1D[kmax_par+1]  Pk1D[kmax_par+1][F]  PkX1D[kmax_par+1][X]       (k1D = k_par*Nm1D)
+ *   Nm2D[n2d]  Pk2D[n2d][F]  PkX2D[n2d][X],   n2d = (kmax_par+1)*(kmax_per+1)           */
+typedef struct pyl_pk_layout {
+    int32_t dims, fields, xfields, kmax_par, kmax_per, kmax;
+    int64_t n2d;
+    int64_t k3D, Nm3D, Pk3D, PkX3D, phase;
+    int64_t Nm1D, Pk1D, PkX1D;
+    int64_t Nm2D, Pk2D, PkX2D;
+    int64_t total_words; /* size of the output buffer in 8-byte words */
+} pyl_pk_layout_t;
+
+/* frequencies() of Pk_library.pyx:56-61 plus the buffer layout */
+int pyl_pk_layout(int dims, int fields, pyl_pk_layout_t *layout);
+
+size_t pyl_pk_bin_workspace_bytes(int dims, int fields);
+
+/* Bin `fields` (1..PYL_MAX_FIELDS) half-spectra in ONE pass.
+ *   delta_k  : HOST array of `fields` DEVICE pointers, each (dims, nky, dims/2+1) complex64
+ *              holding global ky rows [ky_lo, ky_lo+nky) of the r2c output (single GPU:
+ *              ky_lo = 0, nky = dims).  Not modified (the reference's in-place
+ *              deconvolution, :351-352, is an internal temporary).
+ *   mas_index: HOST array, per field 0..4 = None,NGP,CIC,TSC,PCS (Pk_library.pyx:72-78)
+ *   axis     : line of sight 0|1|2
+ *   want_phase: accumulate Pkphase of field 0 (Pk only; Pk_library.pyx:358,377)
+ *   out      : DEVICE buffer of layout.total_words 8-byte words; zeroed by the call
+ * Applies the Hermitian-duplicate skip rule (:324-327), the float32 window factor (:351)
+ * and the float64 accumulation of the reference. */
+#define PYL_MAX_FIELDS 4
+int pyl_pk_bin(const float *const *delta_k, int fields, const int *mas_index, int dims,
+               int ky_lo, int nky, int axis, int want_phase, void *out, void *ws,
+               size_t ws_bytes, pyl_stream_t stream);
+
+/* ---- 4. host-pointer entry points with the reference's exact C signature ------------ */
+/* Same argument list as MAS_c.h:3-10 (HOST pointers; `threads` is accepted and ignored).
+ * They copy pos/W/number to the GPU, run pyl_deposit, and copy number back; a maintainer
+ * can point MAS_c.pxd at them unchanged.  Return PYL_* status. */
+int pyl_NGP(float *pos, float *number, float *W, long particles, int dims, int axes,
+            float BoxSize, int threads);
+int pyl_CIC(float *pos, float *number, float *W, long particles, int dims, int axes,
+            float BoxSize, int threads);
+int pyl_TSC(float *pos, float *number, float *W, long particles, int dims, int axes,
+            float BoxSize, int threads);
+int pyl_PCS(float *pos, float *number, float *W, long particles, int dims, int axes,
+            float BoxSize, int threads);
+/* free the arena owned by the entry points above */
+int pyl_host_arena_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYL_B200_H */

@@ -1,0 +1,312 @@
+"""Drop-in for the hot-path part of Pylians3's `Pk_library`: `Pk`, `XPk` and their helpers.
+
+Mirrors library/Pk_library/Pk_library.pyx:
+  frequencies :56-61, MAS_function :72-78, MAS_correction :83-84, check_number_modes :87-99,
+  FFT3Dr_f :117-130, class Pk :263-420, class XPk :529-793
+with the same names, positional order, defaults, printed messages and result attributes
+(k3D, Pk, Nmodes3D, Pkphase, k1D, Pk1D, Nmodes1D, kpar, kper, Pk2D, Nmodes2D; XPk adds XPk,
+PkX1D, PkX2D).  The FFT (cuFFT), the MAS-window deconvolution and the |delta_k|^2 binning run
+on the GPU through the C ABI of include/pyl_b200.h; the O(bins) finalisation (units, averages;
+:384-418 and :735-791) stays on the host, vectorised.  There is no CPU path.
+
+`delta` may be a NumPy float32 array (copied host->device) or a torch CUDA float32 tensor
+(zero-copy).  `threads` is accepted and ignored.
+"""
+import ctypes
+import time
+
+import numpy as np
+import torch
+
+from . import _device as D
+from . import _lib as L
+from .errors import reference_exit
+
+__all__ = ["Pk", "XPk", "frequencies", "MAS_function", "MAS_correction", "check_number_modes", "FFT3Dr_f"]
+
+
+# ---- helpers with the reference's names ---------------------------------------------------
+def frequencies(BoxSize, dims):
+    """Pk_library.pyx:56-61."""
+    kF = 2.0 * np.pi / BoxSize
+    middle = dims // 2
+    kN = middle * kF
+    kmax_par = middle
+    kmax_per = int(np.sqrt(middle ** 2 + middle ** 2))
+    kmax = int(np.sqrt(middle ** 2 + middle ** 2 + middle ** 2))
+    return kF, kN, kmax_par, kmax_per, kmax
+
+
+def MAS_function(MAS):
+    """Pk_library.pyx:72-78: exponent of the window; anything unknown (None, 'None') -> 0."""
+    MAS_index = 0
+    if MAS == "NGP":
+        MAS_index = 1
+    if MAS == "CIC":
+        MAS_index = 2
+    if MAS == "TSC":
+        MAS_index = 3
+    if MAS == "PCS":
+        MAS_index = 4
+    return MAS_index
+
+
+def MAS_correction(x, MAS_index):
+    """Pk_library.pyx:83-84."""
+    return 1.0 if x == 0.0 else float(np.power(x / np.sin(x), MAS_index))
+
+
+def check_number_modes(Nmodes, dims):
+    """Pk_library.pyx:87-99: every independent mode must have been counted exactly once."""
+    own_modes = 1 if dims % 2 == 1 else 8
+    repeated_modes = (dims ** 3 - own_modes) // 2
+    indep_modes = repeated_modes + own_modes
+    if int(np.sum(Nmodes)) != indep_modes:
+        reference_exit("WARNING: Not all modes counted",
+                       "Counted  %d independent modes" % (int(np.sum(Nmodes))),
+                       "Expected %d independent modes" % indep_modes)
+
+
+# ---- device stages ------------------------------------------------------------------------
+def _as_delta(delta, dev, name="delta"):
+    if isinstance(delta, torch.Tensor):
+        if delta.ndim != 3:
+            raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % delta.ndim)
+    else:
+        delta = np.asarray(delta) if not isinstance(delta, np.ndarray) else delta
+        if delta.ndim != 3:
+            raise ValueError("Buffer has wrong number of dimensions (expected 3, got %d)" % delta.ndim)
+    t, _ = D.to_device_f32(delta, dev, name)
+    if not (t.shape[0] == t.shape[1] == t.shape[2]):
+        raise ValueError("%s must be a (dims,dims,dims) grid, got %s" % (name, tuple(t.shape)))
+    return t
+
+
+def fft3d_r2c_device(delta_d):
+    """(dims,dims,dims) float32 CUDA tensor -> (dims,dims,dims//2+1) complex64 CUDA tensor (cuFFT)."""
+    lib = L.load()
+    dims = delta_d.shape[0]
+    dev = delta_d.device
+    with torch.cuda.device(dev):
+        out = torch.empty((dims, dims, dims // 2 + 1), dtype=torch.complex64, device=dev)
+        need = lib.pyl_fft_r2c_workspace_bytes(dims)
+        if need == ctypes.c_size_t(-1).value:
+            L.check(-3, "pyl_fft_r2c_workspace_bytes")
+        ws = D.workspace(need, dev, "fft")
+        L.check(lib.pyl_fft_r2c(D.ptr(delta_d), D.ptr(out), dims, D.ptr(ws), need, D.stream_ptr(dev)),
+                "pyl_fft_r2c")
+    return out
+
+
+def FFT3Dr_f(a, threads=1):
+    """Pk_library.pyx:117-130: unnormalised forward r2c of a float32 cube, returned as complex64
+    ndarray (dims,dims,dims//2+1).  Given a CUDA tensor it returns a CUDA tensor."""
+    D.require_cuda()
+    dev = D.pick_device(a)
+    out = fft3d_r2c_device(_as_delta(a, dev, "a"))
+    return out if D.is_cuda_tensor(a) else out.cpu().numpy()
+
+
+def bin_device(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=None):
+    """Run pyl_pk_bin on `len(dk_list)` (<= L.MAX_FIELDS) half-spectra; returns (int64 CUDA tensor
+    holding the raw accumulators, layout)."""
+    lib = L.load()
+    F = len(dk_list)
+    nky = dims if nky is None else nky
+    dev = dk_list[0].device
+    lay = L.pk_layout(dims, F)
+    with torch.cuda.device(dev):
+        out = torch.empty(lay.total_words, dtype=torch.int64, device=dev)
+        need = lib.pyl_pk_bin_workspace_bytes(dims, F)
+        ws = D.workspace(need, dev, "pkbin")
+        ptrs = (ctypes.c_void_p * F)(*[D.ptr(t) for t in dk_list])
+        mi = (ctypes.c_int * F)(*[int(i) for i in mas_index])
+        st = lib.pyl_pk_bin(ptrs, F, mi, dims, ky_lo, nky, axis, 1 if want_phase else 0, D.ptr(out),
+                            D.ptr(ws), need, D.stream_ptr(dev))
+    L.check(st, "pyl_pk_bin")
+    return out, lay
+
+
+def unpack_raw(words, lay):
+    """Split the flat accumulator buffer (host int64 ndarray) into named float64 arrays."""
+    F, X = lay.fields, lay.xfields
+    n3, n1, n2 = lay.kmax + 1, lay.kmax_par + 1, lay.n2d
+    f64 = words.view(np.float64)
+
+    def cnt(off, n):
+        return words[off:off + n].astype(np.float64)
+
+    def dbl(off, *shape):
+        n = int(np.prod(shape))
+        return f64[off:off + n].reshape(shape).copy()
+
+    Nm1D = cnt(lay.Nm1D, n1)
+    return dict(k3D=dbl(lay.k3D, n3), Nm3D=cnt(lay.Nm3D, n3), Pk3D=dbl(lay.Pk3D, n3, 3, F),
+                PkX3D=dbl(lay.PkX3D, n3, 3, X), phase=dbl(lay.phase, n3),
+                Nm1D=Nm1D, k1D=Nm1D * np.arange(n1, dtype=np.float64),     # sum of k_par over the bin
+                Pk1D=dbl(lay.Pk1D, n1, F), PkX1D=dbl(lay.PkX1D, n1, X),
+                Nm2D=cnt(lay.Nm2D, n2), Pk2D=dbl(lay.Pk2D, n2, F), PkX2D=dbl(lay.PkX2D, n2, X))
+
+
+def bin_fields(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=None, reduce_fn=None):
+    """Raw accumulators for ANY number of fields.
+
+    Up to L.MAX_FIELDS fields go through one launch.  More fields are covered by launches over
+    pairs of field blocks (each launch yields the autos of its fields and all their crosses), and
+    the results are scattered into the (.., F) / (.., X) arrays in the reference's pair order.
+    `reduce_fn(int64 cuda tensor, layout)` lets the multi-GPU path all-reduce before the D2H."""
+    F = len(dk_list)
+
+    def run(idx):
+        out, lay = bin_device([dk_list[i] for i in idx], [mas_index[i] for i in idx], dims, axis,
+                              want_phase and len(idx) == 1, ky_lo, nky)
+        if reduce_fn is not None:
+            out = reduce_fn(out, lay)
+        return unpack_raw(out.cpu().numpy(), lay)
+
+    if F <= L.MAX_FIELDS:
+        return run(list(range(F)))
+
+    pair_id = {}
+    for i in range(F):
+        for j in range(i + 1, F):
+            pair_id[(i, j)] = len(pair_id)
+    X = len(pair_id)
+    half = L.MAX_FIELDS // 2
+    blocks = [list(range(b, min(b + half, F))) for b in range(0, F, half)]
+    res, seen_auto, seen_pair = None, set(), set()
+    for bi in range(len(blocks)):
+        for bj in range(bi + 1, len(blocks)) if len(blocks) > 1 else []:
+            idx = blocks[bi] + blocks[bj]
+            r = run(idx)
+            if res is None:
+                res = {k: v for k, v in r.items() if k in ("k3D", "Nm3D", "Nm1D", "k1D", "Nm2D", "phase")}
+                for k in ("Pk3D", "Pk1D", "Pk2D"):
+                    res[k] = np.zeros(r[k].shape[:-1] + (F,))
+                for k in ("PkX3D", "PkX1D", "PkX2D"):
+                    res[k] = np.zeros(r[k].shape[:-1] + (X,))
+            for a, ga in enumerate(idx):
+                if ga not in seen_auto:
+                    seen_auto.add(ga)
+                    for k in ("Pk3D", "Pk1D", "Pk2D"):
+                        res[k][..., ga] = r[k][..., a]
+            lx = 0
+            for a in range(len(idx)):
+                for b in range(a + 1, len(idx)):
+                    g = (idx[a], idx[b])
+                    if g not in seen_pair:
+                        seen_pair.add(g)
+                        for k in ("PkX3D", "PkX1D", "PkX2D"):
+                            res[k][..., pair_id[g]] = r[k][..., lx]
+                    lx += 1
+    return res
+
+
+# ---- host finalisation (vectorised restatement of :384-418 / :735-791) --------------------
+def _kpar_kper(kmax_par, kmax_per, kF):
+    i2 = np.arange((kmax_par + 1) * (kmax_per + 1))
+    k_par = i2 % (kmax_par + 1)
+    k_per = i2 // (kmax_par + 1)
+    return 0.5 * (k_par + k_par + 1) * kF, 0.5 * (k_per + k_per + 1) * kF
+
+
+def _finalize(raw, BoxSize, dims):
+    """Returns dict with the reference's attribute arrays, field/pair axes kept last."""
+    kF, kN, kmax_par, kmax_per, kmax = frequencies(BoxSize, dims)
+    fact = (BoxSize / dims ** 2) ** 3
+    o = {}
+    # 1D: discard the DC bin, give units, perpendicular-area weight
+    Nm1 = raw["Nm1D"][1:]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k1D = (raw["k1D"][1:] / Nm1) * kF
+        kmaxper = np.sqrt(kN ** 2 - k1D ** 2)
+        w1 = (np.pi * kmaxper ** 2 / Nm1)
+        o["Pk1D"] = (raw["Pk1D"][1:] * fact) * w1[:, None] / (2.0 * np.pi) ** 2
+        o["PkX1D"] = (raw["PkX1D"][1:] * fact) * w1[:, None] / (2.0 * np.pi) ** 2
+    o["k1D"], o["Nmodes1D"] = k1D, Nm1
+    # 2D: DC bin kept
+    o["kpar"], o["kper"] = _kpar_kper(kmax_par, kmax_per, kF)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        o["Pk2D"] = raw["Pk2D"] * fact / raw["Nm2D"][:, None]
+        o["PkX2D"] = raw["PkX2D"] * fact / raw["Nm2D"][:, None]
+    o["Nmodes2D"] = raw["Nm2D"]
+    # 3D: check modes, discard the DC bin, (2l+1) factors, units
+    check_number_modes(raw["Nm3D"], dims)
+    Nm3 = raw["Nm3D"][1:]
+    ell = np.array([1.0, 5.0, 9.0])[None, :, None]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        o["k3D"] = (raw["k3D"][1:] / Nm3) * kF
+        o["Pk"] = (raw["Pk3D"][1:] * ell / Nm3[:, None, None]) * fact
+        o["XPk"] = (raw["PkX3D"][1:] * ell / Nm3[:, None, None]) * fact
+        o["Pkphase"] = (raw["phase"][1:] / Nm3) * fact
+    o["Nmodes3D"] = Nm3
+    return o
+
+
+class Pk:
+    """1D, 2D and 3D power spectrum of a density field (Pk_library.pyx:263-420).
+
+    Attributes: k3D, Pk (kmax,3: l=0,2,4), Nmodes3D, Pkphase, k1D, Pk1D, Nmodes1D, kpar, kper,
+    Pk2D, Nmodes2D."""
+
+    def __init__(self, delta, BoxSize, axis=2, MAS="CIC", threads=1, verbose=True):
+        start = time.time()
+        if verbose:
+            print("\nComputing power spectrum of the field...")
+        D.require_cuda()
+        if axis not in (0, 1, 2):
+            raise ValueError("axis must be 0, 1 or 2")
+        dev = D.pick_device(delta)
+        delta_d = _as_delta(delta, dev)
+        dims = delta_d.shape[0]
+        delta_k = fft3d_r2c_device(delta_d)
+        start2 = time.time()
+        raw = bin_fields([delta_k], [MAS_function(MAS)], dims, axis, want_phase=True)
+        if verbose:
+            print("Time to complete loop = %.2f" % (time.time() - start2))
+        o = _finalize(raw, BoxSize, dims)
+        self.k1D, self.Pk1D, self.Nmodes1D = o["k1D"], o["Pk1D"][:, 0], o["Nmodes1D"]
+        self.kpar, self.kper = o["kpar"], o["kper"]
+        self.Pk2D, self.Nmodes2D = o["Pk2D"][:, 0], o["Nmodes2D"]
+        self.k3D, self.Nmodes3D = o["k3D"], o["Nmodes3D"]
+        self.Pk, self.Pkphase = np.ascontiguousarray(o["Pk"][:, :, 0]), o["Pkphase"]
+        if verbose:
+            print("Time taken = %.2f seconds" % (time.time() - start))
+
+
+class XPk:
+    """Auto- and cross-power spectra of several fields (Pk_library.pyx:529-793).
+
+    Attributes: k3D, Nmodes3D, Pk (kmax,3,F), XPk (kmax,3,X), k1D, Nmodes1D, Pk1D (.,F),
+    PkX1D (.,X), kpar, kper, Nmodes2D, Pk2D (.,F), PkX2D (.,X); pairs i<j in lexicographic order."""
+
+    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1):
+        start = time.time()
+        print("\nComputing power spectra of the fields...")
+        D.require_cuda()
+        if axis not in (0, 1, 2):
+            raise ValueError("axis must be 0, 1 or 2")
+        fields = len(delta)
+        dims = len(delta[0])
+        for i in range(1, fields):
+            if len(delta[i]) != dims:
+                reference_exit("Fields have different grid sizes!!!")
+        if MAS is None or len(MAS) != fields:
+            raise TypeError("MAS must be a list with one scheme per field")
+        dev = D.pick_device(*delta)
+        dk = [fft3d_r2c_device(_as_delta(d, dev, "delta[%d]" % i)) for i, d in enumerate(delta)]
+        if D.is_cuda_tensor(delta[0]):
+            torch.cuda.synchronize(dev)
+        print("Time FFTS = %.2f" % (time.time() - start))
+        start2 = time.time()
+        raw = bin_fields(dk, [MAS_function(m) for m in MAS], dims, axis)
+        del dk
+        print("Time loop = %.2f" % (time.time() - start2))
+        o = _finalize(raw, BoxSize, dims)
+        self.k1D, self.Nmodes1D = o["k1D"], o["Nmodes1D"]
+        self.Pk1D, self.PkX1D = o["Pk1D"], o["PkX1D"]
+        self.kpar, self.kper, self.Nmodes2D = o["kpar"], o["kper"], o["Nmodes2D"]
+        self.Pk2D, self.PkX2D = o["Pk2D"], o["PkX2D"]
+        self.k3D, self.Nmodes3D = o["k3D"], o["Nmodes3D"]
+        self.Pk, self.XPk = o["Pk"], o["XPk"]
+        print("Time taken = %.2f seconds" % (time.time() - start))

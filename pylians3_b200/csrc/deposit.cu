@@ -1,0 +1,70 @@
+// C entry points of the mass-assignment stage: argument checks + algorithm selection.
+#include "common.cuh"
+
+namespace pyl {
+int deposit_atomic(int mas, const float *pos, float *number, const float *W, int64_t particles,
+                   int dims, int axes, float BoxSize, bool slab, int x_origin, int x_planes,
+                   int64_t *dropped, cudaStream_t stream);
+size_t deposit_tiled_workspace(int mas, int64_t particles, int dims, int axes, int mode);
+int deposit_tiled(int mas, const float *pos, float *number, const float *W, int64_t particles,
+                  int dims, int axes, float BoxSize, int mode, void *ws, size_t ws_bytes,
+                  cudaStream_t stream);
+bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes);
+}  // namespace pyl
+
+using namespace pyl;
+
+static int resolve_mode(int mas, int64_t particles, int dims, int axes, int mode) {
+    if (mode == PYL_MODE_ATOMIC) return mode;
+    const bool ok = deposit_tiled_supported(mas, particles, dims, axes);
+    if (mode == PYL_MODE_AUTO) return ok ? PYL_MODE_TILED : PYL_MODE_ATOMIC;
+    return ok ? mode : PYL_MODE_ATOMIC;   // TILED / DETERMINISTIC requested but not applicable
+}
+
+extern "C" {
+
+size_t pyl_deposit_workspace_bytes(int mas, int64_t particles, int dims, int axes, int mode) {
+    if (mas < PYL_MAS_NGP || mas > PYL_MAS_PCS || particles <= 0 || dims <= 0) return 0;
+    const int m = resolve_mode(mas, particles, dims, axes, mode);
+    if (m == PYL_MODE_ATOMIC) return 0;
+    return deposit_tiled_workspace(mas, particles, dims, axes, m);
+}
+
+int pyl_deposit(int mas, const float *pos, float *number, const float *W, int64_t particles,
+                int dims, int axes, float BoxSize, int mode, void *ws, size_t ws_bytes,
+                pyl_stream_t stream) {
+    PYL_REQUIRE(mas >= PYL_MAS_NGP && mas <= PYL_MAS_PCS, "pyl_deposit: unknown scheme");
+    PYL_REQUIRE(axes == 2 || axes == 3, "pyl_deposit: axes must be 2 or 3");
+    PYL_REQUIRE(dims > 0, "pyl_deposit: dims must be positive");
+    PYL_REQUIRE(particles >= 0, "pyl_deposit: negative particle count");
+    PYL_REQUIRE(BoxSize > 0.0f, "pyl_deposit: BoxSize must be positive");
+    PYL_REQUIRE(mode >= PYL_MODE_AUTO && mode <= PYL_MODE_DETERMINISTIC, "pyl_deposit: unknown mode");
+    if (particles == 0) return PYL_OK;
+    PYL_REQUIRE(pos != nullptr && number != nullptr, "pyl_deposit: NULL pos/number");
+    const int m = resolve_mode(mas, particles, dims, axes, mode);
+    if (m == PYL_MODE_ATOMIC)
+        return deposit_atomic(mas, pos, number, W, particles, dims, axes, BoxSize, false, 0, dims,
+                              nullptr, as_stream(stream));
+    const size_t need = deposit_tiled_workspace(mas, particles, dims, axes, m);
+    if (ws == nullptr || ws_bytes < need) {
+        set_last_error("pyl_deposit: workspace of %zu bytes required, %zu given", need, ws_bytes);
+        return PYL_ERR_WORKSPACE;
+    }
+    return deposit_tiled(mas, pos, number, W, particles, dims, axes, BoxSize, m, ws, ws_bytes,
+                         as_stream(stream));
+}
+
+int pyl_deposit_slab(int mas, const float *pos, float *number, const float *W,
+                     int64_t particles, int dims, float BoxSize, int x_origin, int x_planes,
+                     int64_t *dropped, pyl_stream_t stream) {
+    PYL_REQUIRE(mas >= PYL_MAS_NGP && mas <= PYL_MAS_PCS, "pyl_deposit_slab: unknown scheme");
+    PYL_REQUIRE(dims > 0 && x_planes > 0 && x_planes <= dims, "pyl_deposit_slab: bad plane window");
+    PYL_REQUIRE(x_origin >= 0 && x_origin < dims, "pyl_deposit_slab: x_origin outside [0,dims)");
+    PYL_REQUIRE(particles >= 0 && BoxSize > 0.0f, "pyl_deposit_slab: bad particles/BoxSize");
+    if (particles == 0) return PYL_OK;
+    PYL_REQUIRE(pos != nullptr && number != nullptr, "pyl_deposit_slab: NULL pos/number");
+    return deposit_atomic(mas, pos, number, W, particles, dims, 3, BoxSize, true, x_origin,
+                          x_planes, dropped, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// K2f: particle-parallel deposit with one red.global.add.f32 per stencil cell.
+//
+// Replaces the reference's serial loops MAS_library.pyx:142-166 (CIC), :288-292 (NGP),
+// :388-404 (TSC), :481-497 (PCS) and their W variants, and the OpenMP C core MAS_c.c:8-266.
+// It is the first kernel of the path (minimum slice), the fallback of the tiled kernel for
+// sparse inputs, and the only kernel used for slab deposits with ghost planes.
+//
+// Layout: pos is [particles][AXES] float32.  Each thread takes FOUR consecutive particles so
+// that positions arrive as aligned float4 loads (3 x float4 = 4 particles in 3D, 2 x float4
+// in 2D) and weights as one float4; a scalar path covers unaligned bases and the tail.
+#include "common.cuh"
+#include "stencil.cuh"
+
+namespace pyl {
+
+struct SlabWindow {
+    int x_origin;   // global plane stored at local plane 0
+    int x_planes;   // number of local planes (== dims for the whole grid)
+};
+
+template <int MAS, int AXES, bool WEIGHTED, bool SLAB>
+__device__ __forceinline__ void deposit_one(const float *p, float wp, float *__restrict__ number,
+                                            int dims, float inv_cell_size, SlabWindow win,
+                                            unsigned long long &dropped) {
+    constexpr int S = StencilWidth<MAS>::value;
+    int idx[3][S];
+    float w[3][S];
+#pragma unroll
+    for (int a = 0; a < AXES; a++)
+        axis_stencil<MAS>(cell_coordinate(p[a], inv_cell_size), dims, idx[a], w[a]);
+
+    if (AXES == 3) {
+#pragma unroll
+        for (int l = 0; l < S; l++) {
+            int plane = idx[0][l];
+            if (SLAB) {
+                plane -= win.x_origin;
+                if (plane < 0) plane += dims;
+                if (plane >= win.x_planes) { dropped += 1; continue; }
+            }
+            const int64_t base_x = (int64_t)plane * dims;
+#pragma unroll
+            for (int m = 0; m < S; m++) {
+                const float wxy = __fmul_rn(w[0][l], w[1][m]);
+                float *row = number + (base_x + idx[1][m]) * dims;
+#pragma unroll
+                for (int n = 0; n < S; n++) {
+                    float v = __fmul_rn(wxy, w[2][n]);
+                    if (WEIGHTED) v = __fmul_rn(v, wp);
+                    atomicAdd(row + idx[2][n], v);   // result unused -> RED.E.ADD.F32
+                }
+            }
+        }
+    } else {
+        // plane: the reference pins the third axis to cell 0 with unit weight and still loops
+        // over its S entries (MAS_library.pyx:138-139), so every cell receives S equal adds.
+#pragma unroll
+        for (int l = 0; l < S; l++) {
+            float *row = number + (int64_t)idx[0][l] * dims;
+#pragma unroll
+            for (int m = 0; m < S; m++) {
+                float v = __fmul_rn(w[0][l], w[1][m]);
+                if (WEIGHTED) v = __fmul_rn(v, wp);
+                atomicAdd(row + idx[1][m], v * (float)S);
+            }
+        }
+    }
+}
+
+template <int MAS, int AXES, bool WEIGHTED, bool SLAB>
+__global__ void __launch_bounds__(256)
+deposit_atomic_kernel(const float *__restrict__ pos, const float *__restrict__ W,
+                      float *__restrict__ number, int64_t particles, int dims,
+                      float inv_cell_size, SlabWindow win, unsigned long long *dropped_out,
+                      int vec_ok) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long dropped = 0;
+    const int64_t groups = vec_ok ? (particles >> 2) : 0;
+
+    for (int64_t g = tid; g < groups; g += stride) {
+        float p[4 * AXES];
+        const float4 *src = reinterpret_cast<const float4 *>(pos + g * 4 * AXES);
+#pragma unroll
+        for (int q = 0; q < AXES; q++) {
+            const float4 v = __ldg(src + q);
+            p[4 * q + 0] = v.x; p[4 * q + 1] = v.y; p[4 * q + 2] = v.z; p[4 * q + 3] = v.w;
+        }
+        float wv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+        if (WEIGHTED) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(W + g * 4));
+            wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            deposit_one<MAS, AXES, WEIGHTED, SLAB>(p + q * AXES, wv[q], number, dims,
+                                                   inv_cell_size, win, dropped);
+    }
+    // scalar tail (or everything, when the base pointers are not 16-byte aligned)
+    for (int64_t i = (groups << 2) + tid; i < particles; i += stride) {
+        float p[AXES];
+#pragma unroll
+        for (int a = 0; a < AXES; a++) p[a] = __ldg(pos + i * AXES + a);
+        const float wp = WEIGHTED ? __ldg(W + i) : 1.0f;
+        deposit_one<MAS, AXES, WEIGHTED, SLAB>(p, wp, number, dims, inv_cell_size, win, dropped);
+    }
+    if (SLAB && dropped_out != nullptr && dropped != 0) atomicAdd(dropped_out, dropped);
+}
+
+template <int MAS, int AXES, bool WEIGHTED, bool SLAB>
+static int launch_atomic(const float *pos, const float *W, float *number, int64_t particles,
+                         int dims, float inv_cell_size, SlabWindow win,
+                         unsigned long long *dropped, cudaStream_t stream) {
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(pos) & 15) == 0) &&
+                       (!WEIGHTED || (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    int64_t blocks = ((particles + 3) / 4 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 32;    // grid-stride beyond 32 CTAs per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    deposit_atomic_kernel<MAS, AXES, WEIGHTED, SLAB><<<(int)blocks, 256, 0, stream>>>(
+        pos, W, number, particles, dims, inv_cell_size, win, dropped, vec_ok);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
+template <int MAS>
+static int dispatch_atomic(const float *pos, const float *W, float *number, int64_t particles,
+                           int dims, int axes, float inv, bool slab, SlabWindow win,
+                           unsigned long long *dropped, cudaStream_t s) {
+    if (slab) {
+        return W ? launch_atomic<MAS, 3, true, true>(pos, W, number, particles, dims, inv, win, dropped, s)
+                 : launch_atomic<MAS, 3, false, true>(pos, W, number, particles, dims, inv, win, dropped, s);
+    }
+    if (axes == 3) {
+        return W ? launch_atomic<MAS, 3, true, false>(pos, W, number, particles, dims, inv, win, dropped, s)
+                 : launch_atomic<MAS, 3, false, false>(pos, W, number, particles, dims, inv, win, dropped, s);
+    }
+    return W ? launch_atomic<MAS, 2, true, false>(pos, W, number, particles, dims, inv, win, dropped, s)
+             : launch_atomic<MAS, 2, false, false>(pos, W, number, particles, dims, inv, win, dropped, s);
+}
+
+// shared with deposit.cu
+int deposit_atomic(int mas, const float *pos, float *number, const float *W, int64_t particles,
+                   int dims, int axes, float BoxSize, bool slab, int x_origin, int x_planes,
+                   int64_t *dropped, cudaStream_t stream) {
+    // inv_cell_size = dims/BoxSize evaluated in float32 like `cdef float inv_cell_size`
+    // (MAS_library.pyx:135); IEEE division on the host, identical to the CPU's.
+    const float inv = (float)dims / BoxSize;
+    SlabWindow win{x_origin, x_planes};
+    unsigned long long *dr = reinterpret_cast<unsigned long long *>(dropped);
+    switch (mas) {
+        case PYL_MAS_NGP: return dispatch_atomic<PYL_MAS_NGP>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream);
+        case PYL_MAS_CIC: return dispatch_atomic<PYL_MAS_CIC>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream);
+        case PYL_MAS_TSC: return dispatch_atomic<PYL_MAS_TSC>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream);
+        case PYL_MAS_PCS: return dispatch_atomic<PYL_MAS_PCS>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream);
+    }
+    set_last_error("deposit: unknown mass-assignment scheme %d", mas);
+    return PYL_ERR_ARG;
+}
+
+}  // namespace pyl

@@ -1,0 +1,504 @@
+// K5/K6: MAS-window deconvolution + |delta_k|^2 binning of the r2c half-spectrum, one read pass.
+//
+// Replaces the serial loops library/Pk_library/Pk_library.pyx:311-378 (Pk) and :623-732 (XPk).
+//
+// Why not "one thread per mode + atomics": each mode feeds ~7 float64 accumulators (3D shell:
+// k, P0, P2, P4, phase; 2D (k_par,k_per) bin; 1D k_par bin) plus three counters.  At the
+// HBM roofline a SM must retire ~3 modes/clock, while red.global issues < 1 lane/clock/SM
+// and shared-memory float64 atomics are CAS loops -- per-mode atomics cap the kernel at a
+// few percent of the roofline.  So the kernel removes the atomics geometrically instead:
+//
+//  * WALK.  A thread owns a column of modes: fixed |k_o| (the "other" in-plane axis) and
+//    fixed kz (lanes run along kz, the contiguous axis, so every warp load is a coalesced
+//    256-byte row segment), and walks |k_w| = s0..s1 along the remaining axis.  Along the
+//    walk k^2 = |k_o|^2 + kz^2 + s^2 grows monotonically, so the shell index, and (because the
+//    walk axis is chosen different from the line of sight) the (k_par,k_per) bin move
+//    monotonically and slowly: the thread keeps the current bin's sums in REGISTERS and only
+//    issues red.global.add.f64 when the bin changes.  The 1D bin (k_par) is constant per
+//    thread and is flushed once.
+//  * FOLD.  The four modes (+-k_o, +-k_w, kz) share |k|, mu^2, k_par, k_per, hence every bin
+//    and Legendre weight and the (even) MAS window: they are loaded together and summed
+//    before anything else happens, so the geometry math and the flushes are paid once per
+//    four modes.  The Hermitian-duplicate rule of the reference (:324-327) is applied per
+//    mode, so counts stay exact.
+//  * Flushes of the small, hot arrays (3D shells, 1D) go to NREP replicas selected by
+//    blockIdx to avoid same-address serialisation in L2; a second tiny kernel folds them.
+//
+// Counts are uint64, everything else float64, exactly as wide as the reference's accumulators.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pyl {
+
+constexpr int PK_BLOCK = 128;
+constexpr int PK_NREP = 8;
+
+template <int F>
+struct PkArgs {
+    const float2 *dk[F];     // (N, nky, nz) complex64 each
+    const double *win[F];    // MAS window per |k| index: (x/sin x)^p, x = pi*k/N, [m+1]
+    int N, m, nz, even;
+    int ky_lo, nky;          // stored ky rows [ky_lo, ky_lo+nky)
+    int walk_y;              // 1: walk along ky, other axis = kx;  0: walk along kx, other = ky
+    int fold_other;          // 1: thread folds +-k_o (needs both rows stored)
+    int n_other;             // fold: m+1 values |k_o|; no fold: stored indices of the other axis
+    int axis;                // line of sight
+    int kmax_par1;           // kmax_par + 1
+    int seg_len, nseg;       // walk range [0, m] cut into nseg segments of seg_len steps
+    long long T;             // threads per segment = n_other * nz
+    unsigned long long *out; // layout base (2D section is accumulated here directly)
+    unsigned long long *rep; // NREP replicas of words [0, rep_words) (3D + 1D sections)
+    long long rep_words;
+    // word offsets (see pyl_pk_layout_t)
+    long long o_k3D, o_Nm3D, o_Pk3D, o_PkX3D, o_phase, o_Nm1D, o_Pk1D, o_PkX1D, o_Nm2D, o_Pk2D, o_PkX2D;
+};
+
+__device__ __forceinline__ int isqrt_fix(int v) {
+    int r = (int)__fsqrt_rn((float)v);
+    if (r * r > v) r--;
+    else if ((r + 1) * (r + 1) <= v) r++;
+    return r;
+}
+
+__device__ __forceinline__ void red_f64(unsigned long long *base, long long word, double v) {
+    atomicAdd(reinterpret_cast<double *>(base + word), v);   // result unused -> RED.E.ADD.F64
+}
+__device__ __forceinline__ void red_u64(unsigned long long *base, long long word, unsigned long long v) {
+    atomicAdd(base + word, v);
+}
+
+// phase^2 of one mode, phase = atan2(re, |delta_k|) (Pk_library.pyx:358).  |delta_k| >= |re|,
+// so phase = sign(re) * atan(1/sqrt(1 + (im/re)^2)), evaluated in float32 (scale-free, no
+// overflow of re^2+im^2); the per-mode relative error ~1e-7 is far inside the 1e-4 bin tolerance.
+__device__ __forceinline__ double phase_sq(float re, float im) {
+    if (re == 0.0f) return 0.0;
+    const float q = __fdividef(im, re);
+    const float t = rsqrtf(fmaf(q, q, 1.0f));
+    const float a = atanf(t);
+    return (double)(a * a);
+}
+
+template <int F, bool PHASE>
+__global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A) {
+    constexpr int X = F * (F - 1) / 2;
+    const int seg = blockIdx.y;
+    const long long t = (long long)blockIdx.x * PK_BLOCK + threadIdx.x;
+    if (t >= A.T) return;
+
+    const int N = A.N, m = A.m, nz = A.nz;
+    const bool even = A.even != 0;
+    const int oi = (int)(t / nz);          // index along the other axis (|k_o| or stored index)
+    const int kz = (int)(t - (long long)oi * nz);
+    const bool zspecial = (kz == 0) || (kz == m && even);
+
+    // ---- the (up to two) rows of the other axis handled by this thread ------------------
+    int o_val[2], o_idx[2];
+    bool o_ok[2];
+    int a_abs;
+    if (A.fold_other) {
+        a_abs = oi;
+        o_val[0] = oi; o_idx[0] = oi; o_ok[0] = true;
+        o_val[1] = -oi; o_idx[1] = N - oi;
+        o_ok[1] = (oi != 0) && !(even && oi == m);
+    } else {
+        const int gi = oi + (A.walk_y ? 0 : A.ky_lo);    // stored index -> global index
+        const int v = (gi > m) ? gi - N : gi;
+        a_abs = v < 0 ? -v : v;
+        o_val[0] = v; o_idx[0] = gi; o_ok[0] = true;
+        o_val[1] = 0; o_idx[1] = 0; o_ok[1] = false;
+    }
+
+    // window factors that do not change along the walk
+    double win_oz[F];
+#pragma unroll
+    for (int f = 0; f < F; f++) win_oz[f] = A.win[f][a_abs] * A.win[f][kz];
+
+    // ---- bin bookkeeping ----------------------------------------------------------------
+    const int s0 = seg * A.seg_len;
+    const int s1 = min(s0 + A.seg_len, m + 1);
+    const int base2 = a_abs * a_abs + kz * kz;
+    // k_par by line of sight; the walk coordinate is x (walk_y==0) or y (walk_y==1)
+    const int walk_axis = A.walk_y ? 1 : 0;
+    const int other_axis = A.walk_y ? 0 : 1;
+    const bool par_is_walk = (A.axis == walk_axis);
+    const int kpar_fixed = (A.axis == other_axis) ? a_abs : kz;     // used when !par_is_walk
+    const int perp_base = par_is_walk ? base2 : (A.axis == other_axis ? kz * kz : a_abs * a_abs);
+
+    int kidx = isqrt_fix(base2 + s0 * s0);
+    int kper = isqrt_fix(perp_base + (par_is_walk ? 0 : s0 * s0));
+    const int mm = m * m;
+
+    int cur3 = -1, cur1 = -1;
+    long long cur2 = -1;
+    unsigned int cnt3 = 0, cnt2 = 0, cnt1 = 0;
+    double ksum = 0.0, ph3 = 0.0;
+    double P3[3][F], P2[F], P1[F];
+    double PX3[3][X > 0 ? X : 1], PX2[X > 0 ? X : 1], PX1[X > 0 ? X : 1];
+#pragma unroll
+    for (int f = 0; f < F; f++) { P3[0][f] = P3[1][f] = P3[2][f] = 0.0; P2[f] = 0.0; P1[f] = 0.0; }
+#pragma unroll
+    for (int x = 0; x < X; x++) { PX3[0][x] = PX3[1][x] = PX3[2][x] = 0.0; PX2[x] = 0.0; PX1[x] = 0.0; }
+
+    unsigned long long *rep = A.rep + (long long)(blockIdx.x % PK_NREP) * A.rep_words;
+
+    auto flush3 = [&]() {
+        if (cnt3 == 0) return;
+        red_u64(rep, A.o_Nm3D + cur3, cnt3);
+        red_f64(rep, A.o_k3D + cur3, ksum);
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+#pragma unroll
+            for (int f = 0; f < F; f++) red_f64(rep, A.o_Pk3D + ((long long)cur3 * 3 + l) * F + f, P3[l][f]);
+#pragma unroll
+            for (int x = 0; x < X; x++) red_f64(rep, A.o_PkX3D + ((long long)cur3 * 3 + l) * X + x, PX3[l][x]);
+        }
+        if (PHASE) red_f64(rep, A.o_phase + cur3, ph3);
+        cnt3 = 0; ksum = 0.0; ph3 = 0.0;
+#pragma unroll
+        for (int f = 0; f < F; f++) P3[0][f] = P3[1][f] = P3[2][f] = 0.0;
+#pragma unroll
+        for (int x = 0; x < X; x++) PX3[0][x] = PX3[1][x] = PX3[2][x] = 0.0;
+    };
+    auto flush2 = [&]() {
+        if (cnt2 == 0) return;
+        red_u64(A.out, A.o_Nm2D + cur2, cnt2);
+#pragma unroll
+        for (int f = 0; f < F; f++) red_f64(A.out, A.o_Pk2D + cur2 * F + f, P2[f]);
+#pragma unroll
+        for (int x = 0; x < X; x++) red_f64(A.out, A.o_PkX2D + cur2 * X + x, PX2[x]);
+        cnt2 = 0;
+#pragma unroll
+        for (int f = 0; f < F; f++) P2[f] = 0.0;
+#pragma unroll
+        for (int x = 0; x < X; x++) PX2[x] = 0.0;
+    };
+    auto flush1 = [&]() {
+        if (cnt1 == 0) return;
+        red_u64(rep, A.o_Nm1D + cur1, cnt1);
+#pragma unroll
+        for (int f = 0; f < F; f++) red_f64(rep, A.o_Pk1D + (long long)cur1 * F + f, P1[f]);
+#pragma unroll
+        for (int x = 0; x < X; x++) red_f64(rep, A.o_PkX1D + (long long)cur1 * X + x, PX1[x]);
+        cnt1 = 0;
+#pragma unroll
+        for (int f = 0; f < F; f++) P1[f] = 0.0;
+#pragma unroll
+        for (int x = 0; x < X; x++) PX1[x] = 0.0;
+    };
+
+    // ---- loads: the 2x2 sign combinations of (other, walk) at walk step s ----------------
+    // slot c = 2*io + iw.  ok[c] carries existence AND the Hermitian-duplicate rule.
+    auto row_of = [&](int o_index, int w_index) -> long long {
+        const int kxx = A.walk_y ? o_index : w_index;
+        const int kyy = A.walk_y ? w_index : o_index;
+        return ((long long)kxx * A.nky + (kyy - A.ky_lo)) * nz + kz;
+    };
+    auto mode_ok = [&](int ov, int wv) -> bool {
+        const int kx = A.walk_y ? ov : wv;
+        const int ky = A.walk_y ? wv : ov;
+        if (zspecial) {
+            if (kx < 0) return false;
+            if ((kx == 0 || (kx == m && even)) && ky < 0) return false;
+        }
+        return true;
+    };
+    auto fetch = [&](int s, float2 (&v)[4][F], unsigned &okmask) {
+        okmask = 0;
+        const bool wneg = (s != 0) && !(even && s == m);
+#pragma unroll
+        for (int io = 0; io < 2; io++) {
+#pragma unroll
+            for (int iw = 0; iw < 2; iw++) {
+                const int c = 2 * io + iw;
+                const int wv = iw ? -s : s;
+                const int widx = iw ? N - s : s;
+                const bool ok = o_ok[io] && (iw == 0 || wneg) && mode_ok(o_val[io], wv);
+                if (ok) {
+                    okmask |= 1u << c;
+                    const long long r = row_of(o_idx[io], widx);
+#pragma unroll
+                    for (int f = 0; f < F; f++) v[c][f] = __ldg(A.dk[f] + r);
+                }
+            }
+        }
+    };
+
+    float2 cur_v[4][F];
+    unsigned cur_ok = 0;
+    if (s0 < s1) fetch(s0, cur_v, cur_ok);
+
+    for (int s = s0; s < s1; s++) {
+        // software prefetch of the next step while this one is reduced
+        float2 nxt_v[4][F];
+        unsigned nxt_ok = 0;
+        if (s + 1 < s1) fetch(s + 1, nxt_v, nxt_ok);
+
+        // ---- geometry of this step (shared by the folded modes) -------------------------
+        const int ss = s * s;
+        const int k2 = base2 + ss;
+        while ((kidx + 1) * (kidx + 1) <= k2) kidx++;
+        if (!par_is_walk) {
+            const int p2 = perp_base + ss;
+            while ((kper + 1) * (kper + 1) <= p2) kper++;
+        }
+        const int kpar = par_is_walk ? s : kpar_fixed;
+        const long long i2 = (long long)A.kmax_par1 * kper + kpar;
+        const int i1 = (k2 <= mm) ? kpar : -1;
+
+        if (kidx != cur3) { flush3(); cur3 = kidx; }
+        if (i2 != cur2) { flush2(); cur2 = i2; }
+        if (i1 != cur1) { flush1(); cur1 = i1; }
+
+        const int mult = __popc(cur_ok);
+        if (mult) {
+            // ---- window-deconvolved power of the folded modes ---------------------------
+            double D[F], DX[X > 0 ? X : 1];
+            double PH = 0.0;
+#pragma unroll
+            for (int f = 0; f < F; f++) D[f] = 0.0;
+#pragma unroll
+            for (int x = 0; x < X; x++) DX[x] = 0.0;
+            float fac[F];
+#pragma unroll
+            for (int f = 0; f < F; f++)   // product in float64, rounded to float32 (:351)
+                fac[f] = __double2float_rn(win_oz[f] * A.win[f][s]);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (cur_ok & (1u << c)) {
+                    double re[F], im[F];
+#pragma unroll
+                    for (int f = 0; f < F; f++) {
+                        const float r32 = __fmul_rn(cur_v[c][f].x, fac[f]);   // complex64*float32 (:352)
+                        const float i32 = __fmul_rn(cur_v[c][f].y, fac[f]);
+                        re[f] = (double)r32;
+                        im[f] = (double)i32;
+                        D[f] += re[f] * re[f] + im[f] * im[f];
+                        if (PHASE && f == 0) PH += phase_sq(r32, i32);
+                    }
+                    int x = 0;
+#pragma unroll
+                    for (int i = 0; i < F; i++)
+#pragma unroll
+                        for (int j = i + 1; j < F; j++) { DX[x] += re[i] * re[j] + im[i] * im[j]; x++; }
+                }
+            }
+
+            // ---- Legendre weights (:347-348, :374-376) ----------------------------------
+            const double k = sqrt((double)k2);
+            const double mu2 = (k2 == 0) ? 0.0 : (double)(kpar * kpar) / (double)k2;
+            const double val1 = (3.0 * mu2 - 1.0) * 0.5;
+            const double val2 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) * 0.125;
+
+            cnt3 += mult; ksum += (double)mult * k;
+            cnt2 += mult;
+            if (PHASE) ph3 += PH;
+#pragma unroll
+            for (int f = 0; f < F; f++) {
+                P3[0][f] += D[f]; P3[1][f] += D[f] * val1; P3[2][f] += D[f] * val2;
+                P2[f] += D[f];
+            }
+#pragma unroll
+            for (int x = 0; x < X; x++) {
+                PX3[0][x] += DX[x]; PX3[1][x] += DX[x] * val1; PX3[2][x] += DX[x] * val2;
+                PX2[x] += DX[x];
+            }
+            if (i1 >= 0) {
+                cnt1 += mult;
+#pragma unroll
+                for (int f = 0; f < F; f++) P1[f] += D[f];
+#pragma unroll
+                for (int x = 0; x < X; x++) PX1[x] += DX[x];
+            }
+        }
+
+        cur_ok = nxt_ok;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int f = 0; f < F; f++) cur_v[c][f] = nxt_v[c][f];
+    }
+    flush3(); flush2(); flush1();
+}
+
+// window table: win[f][i] = (x/sin x)^p, x = pi*i/N  (Pk_library.pyx:83-84; even in k)
+__global__ void pk_window_kernel(double *tab, int fields, int m1, int N, const int4 p4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m1) return;
+    const int p[4] = {p4.x, p4.y, p4.z, p4.w};
+    const double x = (M_PI / (double)N) * (double)i;
+    for (int f = 0; f < fields; f++) {
+        double v = 1.0;
+        if (i != 0 && p[f] != 0) v = pow(x / sin(x), (double)p[f]);
+        tab[(long long)f * m1 + i] = v;
+    }
+}
+
+// out[w] = sum over replicas; words in [c0,c0+nc) and [c1,c1+nc1) are uint64 counts
+__global__ void pk_fold_replicas_kernel(unsigned long long *out, const unsigned long long *rep,
+                                        long long words, int nrep, long long c0, long long nc0,
+                                        long long c1, long long nc1) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    const bool is_count = (w >= c0 && w < c0 + nc0) || (w >= c1 && w < c1 + nc1);
+    if (is_count) {
+        unsigned long long s = 0;
+        for (int r = 0; r < nrep; r++) s += rep[(long long)r * words + w];
+        out[w] = s;
+    } else {
+        double s = 0.0;
+        for (int r = 0; r < nrep; r++) s += __longlong_as_double((long long)rep[(long long)r * words + w]);
+        out[w] = (unsigned long long)__double_as_longlong(s);
+    }
+}
+
+static void fill_layout(int dims, int F, pyl_pk_layout_t *L) {
+    const int m = dims / 2;
+    const int X = F * (F - 1) / 2;
+    L->dims = dims; L->fields = F; L->xfields = X;
+    L->kmax_par = m;
+    L->kmax_per = (int)sqrt((double)m * m + (double)m * m);
+    L->kmax = (int)sqrt(3.0 * (double)m * m);
+    L->n2d = (int64_t)(L->kmax_par + 1) * (L->kmax_per + 1);
+    const int64_t n3 = L->kmax + 1, n1 = L->kmax_par + 1;
+    int64_t w = 0;
+    L->k3D = w; w += n3;
+    L->Nm3D = w; w += n3;
+    L->Pk3D = w; w += n3 * 3 * F;
+    L->PkX3D = w; w += n3 * 3 * X;
+    L->phase = w; w += n3;
+    L->Nm1D = w; w += n1;
+    L->Pk1D = w; w += n1 * F;
+    L->PkX1D = w; w += n1 * X;
+    L->Nm2D = w; w += L->n2d;
+    L->Pk2D = w; w += L->n2d * F;
+    L->PkX2D = w; w += L->n2d * X;
+    L->total_words = w;
+}
+
+static size_t bin_workspace(int dims, int F) {
+    pyl_pk_layout_t L;
+    fill_layout(dims, F, &L);
+    const size_t tab = align_up((size_t)F * (dims / 2 + 1) * sizeof(double), 256);
+    const size_t rep = (size_t)PK_NREP * (size_t)L.Nm2D * 8;
+    return tab + rep;
+}
+
+template <int F>
+static int launch_bin(const float *const *delta_k, const int *mas_index, int dims, int ky_lo,
+                      int nky, int axis, int want_phase, void *out, void *ws, cudaStream_t stream) {
+    pyl_pk_layout_t L;
+    fill_layout(dims, F, &L);
+    const int m = dims / 2, nz = m + 1;
+
+    double *tab = reinterpret_cast<double *>(ws);
+    const size_t tab_bytes = align_up((size_t)F * nz * sizeof(double), 256);
+    unsigned long long *rep =
+        reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(ws) + tab_bytes);
+    const long long rep_words = L.Nm2D;   // the 3D and 1D sections precede the 2D section
+
+    PYL_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)L.total_words * 8, stream));
+    PYL_CUDA_CHECK(cudaMemsetAsync(rep, 0, (size_t)PK_NREP * rep_words * 8, stream));
+
+    int p[4] = {0, 0, 0, 0};
+    for (int f = 0; f < F; f++) p[f] = mas_index[f];
+    pk_window_kernel<<<(nz + 127) / 128, 128, 0, stream>>>(tab, F, nz, dims, make_int4(p[0], p[1], p[2], p[3]));
+    PYL_LAUNCH_CHECK();
+
+    PkArgs<F> A;
+    for (int f = 0; f < F; f++) {
+        A.dk[f] = reinterpret_cast<const float2 *>(delta_k[f]);
+        A.win[f] = tab + (size_t)f * nz;
+    }
+    A.N = dims; A.m = m; A.nz = nz; A.even = (dims % 2 == 0);
+    A.ky_lo = ky_lo; A.nky = nky;
+    const bool whole = (ky_lo == 0 && nky == dims);
+    if (whole) {
+        // fold both in-plane axes; walk along y unless y is the line of sight
+        A.fold_other = 1;
+        A.walk_y = (axis == 1) ? 0 : 1;
+        A.n_other = m + 1;
+    } else {
+        // slab of ky rows (distributed transform): only kx is complete -> walk x, no ky fold
+        A.fold_other = 0;
+        A.walk_y = 0;
+        A.n_other = nky;
+    }
+    A.axis = axis;
+    A.kmax_par1 = L.kmax_par + 1;
+    A.T = (long long)A.n_other * nz;
+
+    // cut the walk so that the grid has a few waves of warps even for small grids
+    const long long warps_per_seg = (A.T + 31) / 32;
+    const long long want_warps = (long long)sm_count() * 64;
+    long long nseg = (want_warps + warps_per_seg - 1) / warps_per_seg;
+    const long long max_seg = (m + 1 + 7) / 8;          // at least 8 steps per segment
+    if (nseg > max_seg) nseg = max_seg;
+    if (nseg < 1) nseg = 1;
+    A.seg_len = (int)((m + 1 + nseg - 1) / nseg);
+    A.nseg = (m + 1 + A.seg_len - 1) / A.seg_len;
+
+    A.out = reinterpret_cast<unsigned long long *>(out);
+    A.rep = rep; A.rep_words = rep_words;
+    A.o_k3D = L.k3D; A.o_Nm3D = L.Nm3D; A.o_Pk3D = L.Pk3D; A.o_PkX3D = L.PkX3D; A.o_phase = L.phase;
+    A.o_Nm1D = L.Nm1D; A.o_Pk1D = L.Pk1D; A.o_PkX1D = L.PkX1D;
+    A.o_Nm2D = L.Nm2D; A.o_Pk2D = L.Pk2D; A.o_PkX2D = L.PkX2D;
+
+    if (A.T > 0) {
+        dim3 grid((unsigned)((A.T + PK_BLOCK - 1) / PK_BLOCK), (unsigned)A.nseg);
+        if (want_phase) pk_bin_walk_kernel<F, true><<<grid, PK_BLOCK, 0, stream>>>(A);
+        else pk_bin_walk_kernel<F, false><<<grid, PK_BLOCK, 0, stream>>>(A);
+        PYL_LAUNCH_CHECK();
+    }
+    pk_fold_replicas_kernel<<<(unsigned)((rep_words + 255) / 256), 256, 0, stream>>>(
+        A.out, rep, rep_words, PK_NREP, L.Nm3D, (long long)L.kmax + 1, L.Nm1D, (long long)L.kmax_par + 1);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
+}  // namespace pyl
+
+using namespace pyl;
+
+extern "C" {
+
+int pyl_pk_layout(int dims, int fields, pyl_pk_layout_t *layout) {
+    PYL_REQUIRE(layout != nullptr, "pyl_pk_layout: layout is NULL");
+    PYL_REQUIRE(dims > 0 && fields >= 1, "pyl_pk_layout: bad dims/fields");
+    fill_layout(dims, fields, layout);
+    return PYL_OK;
+}
+
+size_t pyl_pk_bin_workspace_bytes(int dims, int fields) {
+    if (dims <= 0 || fields < 1 || fields > PYL_MAX_FIELDS) return 0;
+    return bin_workspace(dims, fields);
+}
+
+int pyl_pk_bin(const float *const *delta_k, int fields, const int *mas_index, int dims,
+               int ky_lo, int nky, int axis, int want_phase, void *out, void *ws,
+               size_t ws_bytes, pyl_stream_t stream) {
+    PYL_REQUIRE(fields >= 1 && fields <= PYL_MAX_FIELDS, "pyl_pk_bin: fields must be 1..PYL_MAX_FIELDS");
+    PYL_REQUIRE(dims > 0 && dims <= 8192, "pyl_pk_bin: dims must be in 1..8192");
+    PYL_REQUIRE(axis >= 0 && axis <= 2, "pyl_pk_bin: axis must be 0, 1 or 2");
+    PYL_REQUIRE(delta_k != nullptr && mas_index != nullptr && out != nullptr, "pyl_pk_bin: NULL pointer");
+    PYL_REQUIRE(ky_lo >= 0 && nky >= 0 && ky_lo + nky <= dims, "pyl_pk_bin: bad ky window");
+    for (int f = 0; f < fields; f++) {
+        PYL_REQUIRE(delta_k[f] != nullptr || nky == 0, "pyl_pk_bin: NULL field pointer");
+        PYL_REQUIRE(mas_index[f] >= 0 && mas_index[f] <= 4, "pyl_pk_bin: mas_index must be 0..4");
+    }
+    PYL_REQUIRE(!want_phase || fields == 1, "pyl_pk_bin: phase is accumulated for a single field only");
+    const size_t need = bin_workspace(dims, fields);
+    if (ws == nullptr || ws_bytes < need) {
+        set_last_error("pyl_pk_bin: workspace of %zu bytes required, %zu given", need, ws_bytes);
+        return PYL_ERR_WORKSPACE;
+    }
+    cudaStream_t s = as_stream(stream);
+    switch (fields) {
+        case 1: return launch_bin<1>(delta_k, mas_index, dims, ky_lo, nky, axis, want_phase, out, ws, s);
+        case 2: return launch_bin<2>(delta_k, mas_index, dims, ky_lo, nky, axis, 0, out, ws, s);
+        case 3: return launch_bin<3>(delta_k, mas_index, dims, ky_lo, nky, axis, 0, out, ws, s);
+        default: return launch_bin<4>(delta_k, mas_index, dims, ky_lo, nky, axis, 0, out, ws, s);
+    }
+}
+
+}  // extern "C"

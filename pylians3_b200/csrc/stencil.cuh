@@ -1,0 +1,103 @@
+// Per-axis mass-assignment stencils (device), arithmetic restated from the reference:
+//   NGP  library/MAS_library/MAS_library.pyx:290-291
+//   CIC  library/MAS_library/MAS_library.pyx:152-157
+//   TSC  library/MAS_library/MAS_library.pyx:392-399
+//   PCS  library/MAS_library/MAS_library.pyx:485-492
+// Every operation that fixes the reference's result is spelled with an explicit-rounding
+// intrinsic so nvcc cannot contract it into an FMA: the cell coordinate `dist` is the ROUNDED
+// float32 product pos*inv_cell_size (an exact product moves CIC weights
+// by up to 3e-2 at dims=1024).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pyl {
+
+template <int MAS> struct StencilWidth { static constexpr int value = MAS + 1; };  // 1,2,3,4
+
+// periodic wrap into [0, dims).  Inputs inside the documented domain 0 <= pos <= BoxSize only
+// ever need one conditional add/subtract; anything else (the reference would index out of
+// bounds there) is folded back with a true modulo so we never write outside the grid.
+__device__ __forceinline__ int wrap_index(int i, int dims) {
+    if (i >= dims) i -= dims;
+    else if (i < 0) i += dims;
+    if ((unsigned)i >= (unsigned)dims) {
+        i %= dims;
+        if (i < 0) i += dims;
+    }
+    return i;
+}
+
+__device__ __forceinline__ float cell_coordinate(float pos, float inv_cell_size) {
+    return __fmul_rn(pos, inv_cell_size);
+}
+
+// idx[j] : wrapped cell index along this axis, w[j] : its weight, j < StencilWidth<MAS>
+template <int MAS>
+__device__ __forceinline__ void axis_stencil(float dist, int dims, int *idx, float *w);
+
+template <>
+__device__ __forceinline__ void axis_stencil<PYL_MAS_NGP>(float dist, int dims, int *idx, float *w) {
+    // <int>(pos*inv + 0.5): the 0.5 is a double in the reference, so the add is done in f64
+    const int i = __double2int_rz(__dadd_rn((double)dist, 0.5));
+    idx[0] = wrap_index(i, dims);
+    w[0] = 1.0f;
+}
+
+template <>
+__device__ __forceinline__ void axis_stencil<PYL_MAS_CIC>(float dist, int dims, int *idx, float *w) {
+    const int i = __float2int_rz(dist);
+    const float u = __fsub_rn(dist, (float)i);
+    const float d = __fsub_rn(1.0f, u);
+    idx[0] = wrap_index(i, dims);
+    idx[1] = (idx[0] + 1 == dims) ? 0 : idx[0] + 1;
+    w[0] = d;
+    w[1] = u;
+}
+
+template <>
+__device__ __forceinline__ void axis_stencil<PYL_MAS_TSC>(float dist, int dims, int *idx, float *w) {
+    const int minimum = __double2int_rd(__dadd_rn((double)dist, -1.5));
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int c = minimum + j + 1;
+        idx[j] = wrap_index(c, dims);
+        const float diff = fabsf(__fsub_rn((float)c, dist));
+        float v;
+        if (diff < 0.5f) {
+            v = __double2float_rn(__dsub_rn(0.75, (double)__fmul_rn(diff, diff)));
+        } else if (diff < 1.5f) {
+            const double t = __dsub_rn(1.5, (double)diff);
+            v = __double2float_rn(__dmul_rn(__dmul_rn(0.5, t), t));
+        } else {
+            v = 0.0f;
+        }
+        w[j] = v;
+    }
+}
+
+template <>
+__device__ __forceinline__ void axis_stencil<PYL_MAS_PCS>(float dist, int dims, int *idx, float *w) {
+    const int minimum = __double2int_rd(__dadd_rn((double)dist, -2.0));
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int c = minimum + j + 1;
+        idx[j] = wrap_index(c, dims);
+        const float diff = fabsf(__fsub_rn((float)c, dist));
+        const double x = (double)diff;
+        float v;
+        if (diff < 1.0f) {
+            // (4 - 6x^2 + 3x^3)/6, left-to-right like the reference's double expression
+            const double a = __dsub_rn(4.0, __dmul_rn(__dmul_rn(6.0, x), x));
+            const double b = __dmul_rn(__dmul_rn(__dmul_rn(3.0, x), x), x);
+            v = __double2float_rn(__ddiv_rn(__dadd_rn(a, b), 6.0));
+        } else if (diff < 2.0f) {
+            const double t = __dsub_rn(2.0, x);
+            v = __double2float_rn(__ddiv_rn(__dmul_rn(__dmul_rn(t, t), t), 6.0));
+        } else {
+            v = 0.0f;
+        }
+        w[j] = v;
+    }
+}
+
+}  // namespace pyl
