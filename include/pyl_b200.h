@@ -46,6 +46,8 @@ const char *pyl_error_string(int status);
 const char *pyl_last_error(void);
 /* "pyl_b200 <version> sm_100a" */
 const char *pyl_version(void);
+/* number of kernels of THIS library launched by the process so far (cuFFT's are not counted) */
+unsigned long long pyl_kernel_launches(void);
 
 /* ---- 1. mass assignment ------------------------------------------------------------ */
 /* scheme ids; the MAS window exponent of Pk_library.pyx:72-78 is (id + 1) */

@@ -44,7 +44,7 @@ def _cythonize(pyx, c_out, include):
     os.makedirs(os.path.dirname(c_out), exist_ok=True)
     cmd = [sys.executable, "-m", "cython", "-3", "-X", "legacy_implicit_noexcept=True",
            "-I", include, "-o", c_out, pyx]
-    subprocess.check_call(cmd)
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 
 
 def _compile(sources, so_out, include_dirs, extra=()):

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Tiny driver for ncu captures of one stage (kept small so ncu replays stay cheap).
+
+    python profiles/run_stage.py deposit CIC auto 512 [reps]
+    python profiles/run_stage.py pk 512 [axis] [reps]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, synth, overdensity_  # noqa: E402
+
+BOX = 1000.0
+what = sys.argv[1]
+dev = torch.device("cuda", 0)
+if what == "deposit":
+    mas, mode, N = sys.argv[2], sys.argv[3], int(sys.argv[4])
+    reps = int(sys.argv[5]) if len(sys.argv) > 5 else 2
+    kind = sys.argv[6] if len(sys.argv) > 6 else "uniform"
+    pos = synth.uniform_device(N ** 3, BOX, 1, dev) if kind == "uniform" else synth.zeldovich_device(N, BOX, 1, dev)
+    grid = torch.zeros((N, N, N), dtype=torch.float32, device=dev)
+    for _ in range(reps):
+        MASL.MA(pos, grid, BOX, mas, mode=mode)
+    torch.cuda.synchronize()
+    print("sum/N^3 =", float(grid.sum(dtype=torch.float64)) / N ** 3 / reps)
+else:
+    N = int(sys.argv[2])
+    axis = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+    pos = synth.uniform_device(N ** 3, BOX, 1, dev)
+    grid = torch.zeros((N, N, N), dtype=torch.float32, device=dev)
+    MASL.MA(pos, grid, BOX, "CIC")
+    del pos
+    overdensity_(grid)
+    for _ in range(reps):
+        pk = PKL.Pk(grid, BOX, axis, "CIC", verbose=False)
+    print("Pk0[:3] =", pk.Pk[:3, 0])

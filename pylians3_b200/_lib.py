@@ -38,6 +38,7 @@ PROTOTYPES = {
     "pyl_error_string": (ctypes.c_char_p, [_i]),
     "pyl_last_error": (ctypes.c_char_p, []),
     "pyl_version": (ctypes.c_char_p, []),
+    "pyl_kernel_launches": (ctypes.c_ulonglong, []),
     "pyl_deposit_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i]),
     "pyl_deposit": (_i, [_i, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, _sz, _vp]),
     "pyl_deposit_slab": (_i, [_i, _vp, _vp, _vp, _i64, _i, _f, _i, _i, _vp, _vp]),

@@ -1,11 +1,15 @@
 // Error reporting, version string and small elementwise / reduction utilities.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace pyl {
 
 static thread_local char g_err[512] = "";
+
+unsigned long long launches();
 
 void set_last_error(const char *fmt, ...) {
     va_list ap;
@@ -13,6 +17,10 @@ void set_last_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
     static int cached[64] = {0};
@@ -143,6 +151,8 @@ const char *pyl_error_string(int status) {
 const char *pyl_last_error(void) { return g_err; }
 
 const char *pyl_version(void) { return "pyl_b200 0.1.0 sm_100a"; }
+
+unsigned long long pyl_kernel_launches(void) { return pyl::launches(); }
 
 int pyl_affine_inplace(float *x, int64_t n, float a, float b, pyl_stream_t stream) {
     PYL_REQUIRE(x != nullptr || n == 0, "pyl_affine_inplace: x is NULL");

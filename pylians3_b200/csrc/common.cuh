@@ -21,7 +21,14 @@ void set_last_error(const char *fmt, ...);
         }                                                                                 \
     } while (0)
 
-#define PYL_LAUNCH_CHECK() PYL_CUDA_CHECK(cudaGetLastError())
+// every kernel launch of this library is followed by PYL_LAUNCH_CHECK(), which also feeds the
+// launch counter read by pyl_kernel_launches() (bench.py reports it as "gpu_launches")
+void count_launch();
+#define PYL_LAUNCH_CHECK()                                                                \
+    do {                                                                                  \
+        pyl::count_launch();                                                              \
+        PYL_CUDA_CHECK(cudaGetLastError());                                               \
+    } while (0)
 
 #define PYL_REQUIRE(cond, msg)                                                            \
     do {                                                                                  \

@@ -39,6 +39,7 @@ int pyl_deposit(int mas, const float *pos, float *number, const float *W, int64_
     PYL_REQUIRE(particles >= 0, "pyl_deposit: negative particle count");
     PYL_REQUIRE(BoxSize > 0.0f, "pyl_deposit: BoxSize must be positive");
     PYL_REQUIRE(mode >= PYL_MODE_AUTO && mode <= PYL_MODE_DETERMINISTIC, "pyl_deposit: unknown mode");
+    PYL_REQUIRE(mode != PYL_MODE_DETERMINISTIC, "pyl_deposit: PYL_MODE_DETERMINISTIC is not implemented yet");
     if (particles == 0) return PYL_OK;
     PYL_REQUIRE(pos != nullptr && number != nullptr, "pyl_deposit: NULL pos/number");
     const int m = resolve_mode(mas, particles, dims, axes, mode);

@@ -1,15 +1,468 @@
-// Tiled deposit (bucket by tile -> shared-memory accumulation -> coalesced flush).
-// Placeholder until the tiled kernels land: reports "not supported" so that pyl_deposit
-// routes every request to the atomic kernel.
+// K0/K1/K2: tiled deposit -- bucket particles by grid tile, accumulate every tile in shared memory
+// WITHOUT atomics, flush each tile once with coalesced reductions.
+//
+// Replaces the same reference loops as deposit_atomic.cu (MAS_library.pyx:142-166, 288-292, 388-404,
+// 481-497 and W variants).  Why: measured on B200 (profiles/r1_deposit_atomic.md) the particle-parallel
+// red.global kernel moves 21x the algorithmic bytes through DRAM (every stencil row of a randomly
+// placed particle is a 32-byte sector read-modify-write) and runs at 1.8% of the HBM roofline.
+//
+// Pipeline (all on the caller's stream, scratch in the caller's workspace):
+//   1. tile_count    one pass over pos: cell coordinate dist = fl32(pos*inv) per axis, stencil base
+//                    cell -> tile id (tile = 16 x 16 x 32 cells), histogram with red.global.u32.
+//   2. exclusive scan of the tile histogram (cub::DeviceScan).
+//   3. tile_scatter  second pass over pos: slot = atomicAdd(cursor[tile]) ; writes (dist.xyz, W) as one
+//                    aligned float4 -> the particles of a tile are contiguous ("bucket").
+//   4. tile_deposit  one CTA per tile, looping over the bucket in chunks of 2048 particles:
+//        a. counting sort of the chunk by local cell (x,y,z) inside shared memory: one packed-u16
+//           shared atomic per particle for the rank, block scan, scatter into a sorted float4 array
+//           (stencil fractions + W) -- so every (x,y) row of the tile is contiguous and z-ordered;
+//        b. each warp OWNS target x-planes of the shared accumulator (tile + stencil halo).  For a
+//           target plane X it walks the source rows x = X - l (l = 0..S-1), 32 particles at a time;
+//           lanes of equal cell form contiguous runs (sorted), so a segmented warp-shuffle scan
+//           leaves each run's sum in its head lane, and head lanes do plain shared-memory
+//           read-modify-writes.  Target planes are exclusive to a warp and a warp's instructions are
+//           ordered, hence no shared atomics and no block barriers inside the stencil loops;
+//        c. after the last chunk the accumulator (tile + halo) is added to the grid with coalesced
+//           red.global.add.f32 (halo cells are shared with neighbouring tiles).
+// Weights: fractions are taken against the same unwrapped base cell the reference uses; CIC is
+// operation-identical to the reference, TSC/PCS evaluate the same polynomials in float32 (<= 3 ulp from
+// the reference's float64-then-rounded values, far inside the 1e-5 per-cell tolerance).  Unweighted
+// NGP stays bit-exact (sums of 1.0f).
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
+#include "stencil.cuh"
 
 namespace pyl {
 
-bool deposit_tiled_supported(int, int64_t, int, int) { return false; }
-size_t deposit_tiled_workspace(int, int64_t, int, int, int) { return 0; }
-int deposit_tiled(int, const float *, float *, const float *, int64_t, int, int, float, int, void *,
-                  size_t, cudaStream_t) {
-    set_last_error("tiled deposit not built");
+constexpr int TX = 16, TY = 16, TZ = 32;        // tile extent in cells
+constexpr int TILE_CELLS = TX * TY * TZ;        // 8192
+constexpr int TNT = 256;                        // threads per tile CTA
+constexpr int CHUNK = 2048;                     // particles sorted per pass
+constexpr int PER = CHUNK / TNT;                // 8 per thread
+
+struct TileGeom {
+    int dims;
+    int ntx, nty, ntz;
+    unsigned ntiles;
+    float inv_cell_size;
+};
+
+// unwrapped base cell of the stencil (first of the S cells) and the fraction the weights depend on
+template <int MAS>
+__device__ __forceinline__ int stencil_base(float dist, float &frac) {
+    int b;
+    if (MAS == PYL_MAS_NGP) {
+        b = __double2int_rz(__dadd_rn((double)dist, 0.5));
+        frac = 0.0f;
+    } else if (MAS == PYL_MAS_CIC) {
+        b = __float2int_rz(dist);
+        frac = __fsub_rn(dist, (float)b);                 // u in [0,1)
+    } else if (MAS == PYL_MAS_TSC) {
+        b = __double2int_rd(__dadd_rn((double)dist, -1.5)) + 1;
+        frac = __fsub_rn(dist, (float)b);                 // r in [0.5,1.5)
+    } else {
+        b = __double2int_rd(__dadd_rn((double)dist, -2.0)) + 1;
+        frac = __fsub_rn(dist, (float)b);                 // 1+u in [1,2)
+    }
+    return b;
+}
+
+// all S weights of one axis from the fraction (see header comment)
+template <int MAS>
+__device__ __forceinline__ void stencil_weights(float frac, float *w) {
+    if (MAS == PYL_MAS_NGP) {
+        w[0] = 1.0f;
+    } else if (MAS == PYL_MAS_CIC) {
+        w[0] = __fsub_rn(1.0f, frac);
+        w[1] = frac;
+    } else if (MAS == PYL_MAS_TSC) {
+        // diffs: r, |r-1|, 2-r   (MAS_library.pyx:394-398)
+        const float a = 1.5f - frac;
+        const float c = frac - 0.5f;
+        const float d1 = frac - 1.0f;
+        w[0] = 0.5f * a * a;
+        w[1] = 0.75f - d1 * d1;
+        w[2] = 0.5f * c * c;
+    } else {
+        // diffs: 1+u, u, 1-u, 2-u   (MAS_library.pyx:487-491)
+        const float u = frac - 1.0f;
+        const float v = 1.0f - u;
+        const float sixth = 1.0f / 6.0f;
+        w[0] = v * v * v * sixth;
+        w[1] = (4.0f - 6.0f * u * u + 3.0f * u * u * u) * sixth;
+        w[2] = (4.0f - 6.0f * v * v + 3.0f * v * v * v) * sixth;
+        w[3] = u * u * u * sixth;
+    }
+}
+
+template <int MAS>
+__device__ __forceinline__ unsigned tile_and_local(const float d[3], const TileGeom &g, int local[3],
+                                                   float frac[3]) {
+    int t[3];
+    const int T[3] = {TX, TY, TZ};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const int b = stencil_base<MAS>(d[a], frac[a]);
+        const int wb = wrap_index(b, g.dims);
+        t[a] = wb / T[a];
+        local[a] = wb - t[a] * T[a];
+    }
+    return ((unsigned)t[0] * g.nty + t[1]) * g.ntz + t[2];
+}
+
+// ---- 1. histogram ---------------------------------------------------------------------------------
+template <int MAS>
+__global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict__ pos, int64_t particles,
+                                                         TileGeom g, unsigned *__restrict__ counts, int vec_ok) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t groups = vec_ok ? (particles >> 2) : 0;
+    int local[3];
+    float frac[3];
+    for (int64_t grp = tid; grp < groups; grp += stride) {
+        float p[12];
+        const float4 *src = reinterpret_cast<const float4 *>(pos + grp * 12);
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const float4 v = __ldg(src + q);
+            p[4 * q] = v.x; p[4 * q + 1] = v.y; p[4 * q + 2] = v.z; p[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            float d[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++) d[a] = cell_coordinate(p[3 * q + a], g.inv_cell_size);
+            atomicAdd(counts + tile_and_local<MAS>(d, g, local, frac), 1u);
+        }
+    }
+    for (int64_t i = (groups << 2) + tid; i < particles; i += stride) {
+        float d[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) d[a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
+        atomicAdd(counts + tile_and_local<MAS>(d, g, local, frac), 1u);
+    }
+}
+
+// ---- 3. scatter into buckets ----------------------------------------------------------------------
+// cursor[] enters holding the exclusive scan (bucket starts) and leaves holding the bucket ENDS.
+template <int MAS, bool WEIGHTED>
+__global__ void __launch_bounds__(256) tile_scatter_kernel(const float *__restrict__ pos,
+                                                           const float *__restrict__ W, int64_t particles,
+                                                           TileGeom g, unsigned *__restrict__ cursor,
+                                                           float4 *__restrict__ bucket, int vec_ok) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t groups = vec_ok ? (particles >> 2) : 0;
+    int local[3];
+    float frac[3];
+    for (int64_t grp = tid; grp < groups; grp += stride) {
+        float p[12];
+        const float4 *src = reinterpret_cast<const float4 *>(pos + grp * 12);
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const float4 v = __ldg(src + q);
+            p[4 * q] = v.x; p[4 * q + 1] = v.y; p[4 * q + 2] = v.z; p[4 * q + 3] = v.w;
+        }
+        float wv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+        if (WEIGHTED) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(W + grp * 4));
+            wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
+        }
+        unsigned slot[4];
+        float d[4][3];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int a = 0; a < 3; a++) d[q][a] = cell_coordinate(p[3 * q + a], g.inv_cell_size);
+            slot[q] = atomicAdd(cursor + tile_and_local<MAS>(d[q], g, local, frac), 1u);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) bucket[slot[q]] = make_float4(d[q][0], d[q][1], d[q][2], wv[q]);
+    }
+    for (int64_t i = (groups << 2) + tid; i < particles; i += stride) {
+        float d[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) d[a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
+        const float wp = WEIGHTED ? __ldg(W + i) : 1.0f;
+        const unsigned slot = atomicAdd(cursor + tile_and_local<MAS>(d, g, local, frac), 1u);
+        bucket[slot] = make_float4(d[0], d[1], d[2], wp);
+    }
+}
+
+// ---- 4. per-tile deposit ----------------------------------------------------------------------------
+template <int MAS>
+struct TileSmem {
+    static constexpr int S = MAS + 1;
+    static constexpr int AX = TX + S - 1, AY = TY + S - 1, AZ = TZ + S - 1;
+    static constexpr int ACC = AX * AY * AZ;
+    static constexpr int CNT_WORDS = TILE_CELLS / 2 + 1;      // packed u16 pairs + one end marker
+    static constexpr size_t bytes =
+        (size_t)ACC * 4 + (size_t)CNT_WORDS * 4 + (size_t)CHUNK * 16 + (size_t)CHUNK * 2 + 64;
+};
+
+__device__ __forceinline__ unsigned off16(const unsigned *cnt, int key) {
+    const unsigned w = cnt[key >> 1];
+    return (key & 1) ? (w >> 16) : (w & 0xffffu);
+}
+
+template <int MAS>
+__global__ void __launch_bounds__(TNT, 2)
+tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restrict__ ends,
+                    float *__restrict__ number, TileGeom g) {
+    using SM = TileSmem<MAS>;
+    constexpr int S = SM::S, AY = SM::AY, AZ = SM::AZ, AX = SM::AX;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *sorted = reinterpret_cast<float4 *>(smem_raw);                       // CHUNK float4
+    float *acc = reinterpret_cast<float *>(smem_raw + (size_t)CHUNK * 16);        // ACC floats
+    unsigned *cnt = reinterpret_cast<unsigned *>(acc + SM::ACC);                  // CNT_WORDS
+    unsigned short *sorted_yz = reinterpret_cast<unsigned short *>(cnt + SM::CNT_WORDS);   // CHUNK: y*TZ+z
+    unsigned *warp_part = reinterpret_cast<unsigned *>(sorted_yz + CHUNK);        // 8 words
+
+    const unsigned tile = blockIdx.x;
+    const unsigned begin = tile ? ends[tile - 1] : 0u;
+    const unsigned end = ends[tile];
+    if (begin == end) return;                                 // empty tile: nothing to add
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tz = tile % g.ntz, ty = (tile / g.ntz) % g.nty, tx = tile / (g.ntz * g.nty);
+    const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
+
+    for (int i = tid; i < SM::ACC; i += TNT) acc[i] = 0.0f;
+
+    for (unsigned c0 = begin; c0 < end; c0 += CHUNK) {
+        const int n = (int)min((unsigned)CHUNK, end - c0);
+        for (int i = tid; i < SM::CNT_WORDS; i += TNT) cnt[i] = 0u;
+        __syncthreads();
+
+        // ---- a. rank every particle within its cell ------------------------------------------------
+        float4 part[PER];
+        int key[PER];
+        unsigned rank[PER];
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int i = tid + q * TNT;
+            key[q] = -1;
+            if (i < n) {
+                const float4 v = __ldg(bucket + c0 + i);
+                const float d[3] = {v.x, v.y, v.z};
+                float fr[3];
+                int lc[3];
+                const int org[3] = {ox, oy, oz};
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    const int b = stencil_base<MAS>(d[a], fr[a]);
+                    lc[a] = wrap_index(b, g.dims) - org[a];
+                }
+                key[q] = (lc[0] * TY + lc[1]) * TZ + lc[2];
+                part[q] = make_float4(fr[0], fr[1], fr[2], v.w);
+                const unsigned old = atomicAdd(cnt + (key[q] >> 1), (key[q] & 1) ? 0x10000u : 1u);
+                rank[q] = (key[q] & 1) ? (old >> 16) : (old & 0xffffu);
+            }
+        }
+        __syncthreads();
+
+        // ---- exclusive scan of the 8192 packed counters (32 per thread) -------------------------------
+        {
+            constexpr int WPT = TILE_CELLS / 2 / TNT;          // 16 words per thread
+            unsigned words[WPT];
+            unsigned sum = 0;
+#pragma unroll
+            for (int i = 0; i < WPT; i++) {
+                words[i] = cnt[tid * WPT + i];
+                sum += (words[i] & 0xffffu) + (words[i] >> 16);
+            }
+            unsigned incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) warp_part[warp] = incl;
+            __syncthreads();
+            unsigned base = 0;
+#pragma unroll
+            for (int w = 0; w < TNT / 32; w++) base += (w < warp) ? warp_part[w] : 0u;
+            unsigned run = base + incl - sum;
+#pragma unroll
+            for (int i = 0; i < WPT; i++) {
+                const unsigned lo = words[i] & 0xffffu, hi = words[i] >> 16;
+                cnt[tid * WPT + i] = run | ((run + lo) << 16);
+                run += lo + hi;
+            }
+            if (tid == TNT - 1) cnt[TILE_CELLS / 2] = run;     // == n : end marker for the last row
+        }
+        __syncthreads();
+
+        // ---- scatter into cell order ------------------------------------------------------------------
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            if (key[q] >= 0) {
+                const unsigned dst = off16(cnt, key[q]) + rank[q];
+                sorted[dst] = part[q];
+                sorted_yz[dst] = (unsigned short)(key[q] & (TY * TZ - 1));
+            }
+        }
+        __syncthreads();
+
+        // ---- b. stencil accumulation: warp `warp` owns target planes X = warp, warp+8, warp+16 -----------
+        // (with TX = 16 and 8 warps every warp gets exactly 2*S source-plane visits: balanced)
+        for (int X = warp; X < AX; X += TNT / 32) {
+            float *plane = acc + X * AY * AZ;
+#pragma unroll 1
+            for (int l = 0; l < S; l++) {
+                const int x = X - l;                           // source plane
+                if (x < 0 || x >= TX) continue;
+                // the particles of source plane x are contiguous and ordered by (y,z); a batch of 32
+                // may span several rows -- lanes of one batch always write distinct cells of plane X
+                const int q0 = (int)off16(cnt, x * TY * TZ);
+                const int q1 = (int)off16(cnt, (x + 1) * TY * TZ);
+#pragma unroll 1
+                for (int b0 = q0; b0 < q1; b0 += 32) {
+                    const int p = b0 + lane;
+                    const bool valid = p < q1;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int yz = 0x4000 + lane;                    // invalid lanes: singleton segments
+                    if (valid) { v = sorted[p]; yz = sorted_yz[p]; }
+                    const int y = (yz >> 5) & (TY - 1), lz = yz & (TZ - 1);
+                    float wx[S], wy[S], wz[S];
+                    stencil_weights<MAS>(v.x, wx);
+                    stencil_weights<MAS>(v.y, wy);
+                    stencil_weights<MAS>(v.z, wz);
+                    float wxl = wx[0];
+#pragma unroll
+                    for (int j = 1; j < S; j++) wxl = (l == j) ? wx[j] : wxl;
+
+                    // runs of equal cell are contiguous; same[k]: lane+2^k belongs to my run
+                    const int prev = __shfl_up_sync(0xffffffffu, yz, 1);
+                    const bool head = valid && (lane == 0 || prev != yz);
+                    unsigned same = 0;
+#pragma unroll
+                    for (int k = 0; k < 5; k++) {
+                        const int o = __shfl_down_sync(0xffffffffu, yz, 1 << k);
+                        if (lane + (1 << k) < 32 && o == yz) same |= 1u << k;
+                    }
+                    const unsigned any_same = __reduce_or_sync(0xffffffffu, same);
+                    const int nsteps = 32 - __clz(any_same);
+                    float *cellp = plane + y * AZ + lz;
+
+#pragma unroll
+                    for (int m = 0; m < S; m++) {
+                        const float wxy = __fmul_rn(wxl, wy[m]);
+#pragma unroll
+                        for (int nn = 0; nn < S; nn++) {
+                            float val = __fmul_rn(__fmul_rn(wxy, wz[nn]), v.w);
+                            for (int k = 0; k < nsteps; k++) {
+                                const float o = __shfl_down_sync(0xffffffffu, val, 1 << k);
+                                if (same & (1u << k)) val += o;
+                            }
+                            if (head) cellp[m * AZ + nn] += val;
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- c. flush tile + halo into the grid ---------------------------------------------------------------
+    const int dims = g.dims;
+    for (int i = tid; i < SM::ACC; i += TNT) {
+        const float val = acc[i];
+        if (val != 0.0f) {
+            const int az = i % AZ, ay = (i / AZ) % AY, ax = i / (AZ * AY);
+            int gx = ox + ax, gy = oy + ay, gz = oz + az;
+            if (gx >= dims) gx -= dims;
+            if (gy >= dims) gy -= dims;
+            if (gz >= dims) gz -= dims;
+            atomicAdd(number + ((int64_t)gx * dims + gy) * dims + gz, val);
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+static TileGeom make_geom(int dims, float BoxSize) {
+    TileGeom g;
+    g.dims = dims;
+    g.ntx = (dims + TX - 1) / TX;
+    g.nty = (dims + TY - 1) / TY;
+    g.ntz = (dims + TZ - 1) / TZ;
+    g.ntiles = (unsigned)g.ntx * g.nty * g.ntz;
+    g.inv_cell_size = (float)dims / BoxSize;      // float32 division, MAS_library.pyx:135
+    return g;
+}
+
+static size_t scan_temp_bytes(unsigned ntiles) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (unsigned *)nullptr, (unsigned *)nullptr, (int)ntiles);
+    return bytes;
+}
+
+bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes) {
+    if (axes != 3 || dims < 64) return false;                       // halo wrap assumes dims >> stencil
+    if (particles >= ((int64_t)1 << 32) - 1) return false;          // 32-bit bucket offsets
+    const TileGeom g = make_geom(dims, 1.0f);
+    if ((int64_t)g.ntiles > ((int64_t)1 << 30)) return false;
+    return particles >= (int64_t)g.ntiles * 64;                     // sparse inputs: per-tile overhead loses
+}
+
+size_t deposit_tiled_workspace(int mas, int64_t particles, int dims, int axes, int mode) {
+    const TileGeom g = make_geom(dims, 1.0f);
+    return align_up((size_t)particles * 16, 256) + align_up(((size_t)g.ntiles + 1) * 4, 256) +
+           align_up(scan_temp_bytes(g.ntiles + 1), 256);
+}
+
+template <int MAS>
+static int run_tiled(const float *pos, float *number, const float *W, int64_t particles, int dims,
+                     float BoxSize, void *ws, cudaStream_t stream) {
+    const TileGeom g = make_geom(dims, BoxSize);
+    char *base = reinterpret_cast<char *>(ws);
+    float4 *bucket = reinterpret_cast<float4 *>(base);
+    base += align_up((size_t)particles * 16, 256);
+    unsigned *cursor = reinterpret_cast<unsigned *>(base);
+    base += align_up(((size_t)g.ntiles + 1) * 4, 256);
+    void *scan_tmp = base;
+    size_t scan_bytes = scan_temp_bytes(g.ntiles + 1);
+
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(pos) & 15) == 0) &&
+                       (W == nullptr || (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+    int64_t blocks = ((particles + 3) / 4 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+
+    PYL_CUDA_CHECK(cudaMemsetAsync(cursor, 0, ((size_t)g.ntiles + 1) * 4, stream));
+    tile_count_kernel<MAS><<<(int)blocks, 256, 0, stream>>>(pos, particles, g, cursor, vec_ok);
+    PYL_LAUNCH_CHECK();
+    PYL_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, cursor, cursor, (int)(g.ntiles + 1), stream));
+    if (W)
+        tile_scatter_kernel<MAS, true><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, cursor, bucket, vec_ok);
+    else
+        tile_scatter_kernel<MAS, false><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, cursor, bucket, vec_ok);
+    PYL_LAUNCH_CHECK();
+
+    static bool attr_done[4] = {false, false, false, false};
+    if (!attr_done[MAS]) {
+        PYL_CUDA_CHECK(cudaFuncSetAttribute(tile_deposit_kernel<MAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)TileSmem<MAS>::bytes));
+        attr_done[MAS] = true;
+    }
+    tile_deposit_kernel<MAS><<<g.ntiles, TNT, TileSmem<MAS>::bytes, stream>>>(bucket, cursor, number, g);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
+int deposit_tiled(int mas, const float *pos, float *number, const float *W, int64_t particles, int dims,
+                  int axes, float BoxSize, int mode, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    (void)axes; (void)mode; (void)ws_bytes;
+    switch (mas) {
+        case PYL_MAS_NGP: return run_tiled<PYL_MAS_NGP>(pos, number, W, particles, dims, BoxSize, ws, stream);
+        case PYL_MAS_CIC: return run_tiled<PYL_MAS_CIC>(pos, number, W, particles, dims, BoxSize, ws, stream);
+        case PYL_MAS_TSC: return run_tiled<PYL_MAS_TSC>(pos, number, W, particles, dims, BoxSize, ws, stream);
+        case PYL_MAS_PCS: return run_tiled<PYL_MAS_PCS>(pos, number, W, particles, dims, BoxSize, ws, stream);
+    }
+    set_last_error("deposit_tiled: unknown scheme %d", mas);
     return PYL_ERR_ARG;
 }
 

@@ -49,13 +49,15 @@ def rel_err(a, b, floor=0.0):
     return float(np.nanmax(np.abs(a - b) / den))
 
 
-def make_particles(seed, n, clustered=False, box=BOX):
+def make_particles(seed, n, clustered=False, box=BOX, sigma=0.04):
+    """Uniform particles; `clustered` puts half of them into 16 Gaussian clumps of width sigma*box
+    (sigma=0.04 -> density contrast of a few tens; sigma=0.01 -> thousands of particles per cell)."""
     rng = np.random.default_rng(seed)
     pos = rng.random((n, 3), dtype=np.float32) * np.float32(box)
     if clustered:
         c = rng.random((16, 3), dtype=np.float32) * np.float32(box)
         k = n // 2
-        pos[:k] = (c[rng.integers(0, 16, k)] + rng.normal(0, box * 0.01, (k, 3)).astype(np.float32)) % np.float32(box)
+        pos[:k] = (c[rng.integers(0, 16, k)] + rng.normal(0, box * sigma, (k, 3)).astype(np.float32)) % np.float32(box)
     edge = np.array([[0, 0, 0], [box, box, box], [np.nextafter(np.float32(box), np.float32(0)), 0.5, box / 2],
                      [box, 0, np.nextafter(np.float32(box), np.float32(0))]], dtype=np.float32)
     pos[:len(edge)] = edge

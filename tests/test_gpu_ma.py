@@ -1,0 +1,234 @@
+"""GPU parity tests of the mass-assignment stage: CUDA path (through the C ABI) vs the CPU oracle
+and vs the golden vectors of the compiled reference.
+
+Tolerances (BASELINE.json north_star): NGP cell counts bit-exact; CIC/TSC/PCS float32 grids within
+1e-5 relative per cell, relative to max(|cell|, mean)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import BOX, make_particles, rel_err
+
+pytestmark = pytest.mark.gpu
+MAS = ("NGP", "CIC", "TSC", "PCS")
+MODES = ("atomic", "tiled")
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from pylians3_b200 import MAS_library as MASL, _lib
+    _lib.load()
+    return torch, MASL, _lib
+
+
+def cell_err(got, ref):
+    return rel_err(got, ref, floor=max(float(np.mean(np.abs(ref))), 1e-30))
+
+
+@pytest.mark.parametrize("N", [16, 9])
+@pytest.mark.parametrize("clu", ["uni", "clu"])
+@pytest.mark.parametrize("mas", MAS)
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("mode", MODES)
+def test_ma_vs_reference_golden(env, ma_golden, N, clu, mas, weighted, mode):
+    torch, MASL, _ = env
+    tag = "N%d_%s" % (N, clu)
+    pos, W = ma_golden[tag + "_pos"], ma_golden[tag + "_W"]
+    w = W if weighted else None
+    for nd in (3, 2):
+        g = np.zeros((N,) * nd, np.float32)
+        p = pos if nd == 3 else np.ascontiguousarray(pos[:, :2])
+        MASL.MA(p, g, BOX, mas, w, mode=mode)
+        ref = ma_golden["%s_%s_%s_%dD" % (tag, mas, "W" if weighted else "U", nd)]
+        if mas == "NGP" and not weighted:
+            assert np.array_equal(g, ref), "NGP counts must be bit-exact"
+        else:
+            assert cell_err(g, ref) < TOL
+
+
+@pytest.mark.parametrize("N,npart,clustered", [(64, 300000, False), (64, 300000, True), (128, 1500000, True),
+                                               (33, 100000, True), (256, 2000000, False)])
+@pytest.mark.parametrize("mode", MODES)
+def test_ma_vs_oracle_medium(env, oracle, N, npart, clustered, mode):
+    torch, MASL, _ = env
+    pos, W = make_particles(N * 7 + int(clustered), npart, clustered)
+    for mas in MAS:
+        for w in (None, W):
+            ref = np.zeros((N, N, N), np.float32)
+            oracle.MA(pos, ref, BOX, mas, w)
+            got = np.zeros((N, N, N), np.float32)
+            MASL.MA(pos, got, BOX, mas, w, mode=mode)
+            if mas == "NGP" and w is None:
+                assert np.array_equal(got, ref)
+            else:
+                assert cell_err(got, ref) < TOL, (mas, w is not None)
+            # mass conservation, library/tests/test.py:30
+            tot = float(np.sum(W, dtype=np.float64)) if w is not None else float(npart)
+            assert abs(np.sum(got, dtype=np.float64) / tot - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_ma_extreme_clustering_accumulation_noise(env, oracle, mode):
+    """Thousands of particles per cell: a float32 sum of n terms depends on the summation order at the
+    level sqrt(n)*2^-24 (the reference itself changes by that much if the particles are shuffled), so
+    the per-cell bound is 1e-5 * max(1, sqrt(n_cell/64)); mass is still conserved to 1e-5."""
+    torch, MASL, _ = env
+    N = 128
+    pos, W = make_particles(901, 1500000, True, sigma=0.01)
+    counts = np.zeros((N, N, N), np.float32)
+    oracle.MA(pos, counts, BOX, "NGP")
+    for mas in ("CIC", "PCS"):
+        ref = np.zeros((N, N, N), np.float32)
+        oracle.MA(pos, ref, BOX, mas)
+        got = np.zeros((N, N, N), np.float32)
+        MASL.MA(pos, got, BOX, mas, mode=mode)
+        from scipy.ndimage import maximum_filter
+        n_cell = maximum_filter(counts, size=5, mode="wrap")
+        bound = TOL * np.maximum(1.0, np.sqrt(n_cell / 64.0)) * np.maximum(np.abs(ref), ref.mean())
+        assert np.all(np.abs(got - ref) <= bound), mas
+        assert abs(np.sum(got, dtype=np.float64) / len(pos) - 1.0) < 1e-5
+
+
+def test_ma_accumulates_like_reference(env, ma_golden):
+    torch, MASL, _ = env
+    pos, W = ma_golden["accum_pos"], ma_golden["accum_W"]
+    g = np.full((12, 12, 12), 0.25, np.float32)
+    MASL.MA(pos[:1500], g, BOX, "TSC", W[:1500])
+    MASL.MA(pos[1500:], g, BOX, "TSC", W[1500:])
+    assert cell_err(g, ma_golden["accum_TSC_W_3D"]) < TOL
+    g2 = np.full((12, 12), 0.25, np.float32)
+    MASL.MA(np.ascontiguousarray(pos[:, :2]), g2, BOX, "PCS", None, False, False)
+    assert cell_err(g2, ma_golden["accum_PCS_U_2D_norenorm"]) < TOL
+
+
+def test_ma_device_tensors_zero_copy_and_strided_inputs(env, oracle):
+    torch, MASL, _ = env
+    N = 48
+    pos, W = make_particles(5, 200001, True)           # odd count: exercises the scalar tail
+    ref = np.zeros((N, N, N), np.float32)
+    oracle.MA(pos, ref, BOX, "CIC", W)
+    pos_d = torch.from_numpy(pos).cuda()
+    W_d = torch.from_numpy(W).cuda()
+    grid = torch.zeros((N, N, N), dtype=torch.float32, device="cuda")
+    ptr0 = grid.data_ptr()
+    assert MASL.MA(pos_d, grid, BOX, "CIC", W_d) is None
+    assert grid.data_ptr() == ptr0
+    assert cell_err(grid.cpu().numpy(), ref) < TOL
+    # unaligned view of the positions (drops the float4 fast path) and a strided host array
+    pos_shift = torch.empty(pos.shape[0] * 3 + 1, dtype=torch.float32, device="cuda")[1:].view(-1, 3)
+    pos_shift.copy_(pos_d)
+    g2 = torch.zeros_like(grid)
+    MASL.MA(pos_shift, g2, BOX, "CIC", W_d)
+    assert cell_err(g2.cpu().numpy(), ref) < TOL
+    big = np.zeros((pos.shape[0], 6), np.float32)
+    big[:, ::2] = pos
+    g3 = np.zeros((N, N, N), np.float32)
+    MASL.MA(big[:, ::2], g3, BOX, "CIC", W)
+    assert cell_err(g3, ref) < TOL
+
+
+def test_ma_rejects_wrong_dtype(env):
+    torch, MASL, _ = env
+    with pytest.raises(ValueError):
+        MASL.MA(np.zeros((10, 3), np.float64), np.zeros((8, 8, 8), np.float32), BOX)
+    with pytest.raises(ValueError):
+        MASL.MA(np.zeros((10, 3), np.float32), np.zeros((8, 8, 8), np.float64), BOX)
+
+
+@pytest.mark.parametrize("mas", MAS)
+def test_host_pointer_entry_points_match_mas_c_signature(env, oracle, mas):
+    """pyl_NGP/CIC/TSC/PCS take the argument list of MAS_c.h:3-10 on HOST arrays."""
+    torch, MASL, _lib = env
+    lib = _lib.load()
+    N = 40
+    pos, W = make_particles(11, 150000, True)
+    fp = ctypes.c_void_p
+    for axes in (3, 2):
+        # ~2-10 particles per cell: float32 sums of O(100) terms differ by >1e-5 between summation
+        # orders (serial vs atomics), which is accumulation round-off, not a kernel property
+        npart = 150000 if axes == 3 else 4000
+        p = np.ascontiguousarray(pos[:npart, :axes])
+        for w in (None, W[:npart]):
+            ref = np.full((N,) * axes, 0.5, np.float32)
+            oracle.MA(p, ref, BOX, mas, w, renormalize_2D=False)
+            got = np.full((N,) * axes, 0.5, np.float32)
+            st = getattr(lib, "pyl_" + mas)(p.ctypes.data, got.ctypes.data, None if w is None else w.ctypes.data,
+                                            p.shape[0], N, axes, np.float32(BOX), 8)
+            assert st == 0, lib.pyl_last_error()
+            assert cell_err(got, ref) < TOL
+    assert lib.pyl_host_arena_release() == 0
+
+
+@pytest.mark.parametrize("mas", MAS)
+def test_c_core_wrappers(env, oracle, mas):
+    torch, MASL, _ = env
+    N = 32
+    pos, W = make_particles(3, 50000, False)
+    ref = np.zeros((N, N, N), np.float32)
+    oracle.MA(pos, ref, BOX, mas, W)
+    got = np.zeros((N, N, N), np.float32)
+    getattr(MASL, mas + "Wc3D")(pos, got, W, BOX, 4)
+    assert cell_err(got, ref) < TOL
+    # 2D through the C core: proper plane deposit accumulated onto existing content (MAS_c.c n_max=1)
+    p2 = np.ascontiguousarray(pos[:, :2])
+    ref2 = np.zeros((N, N), np.float32)
+    oracle.MA(p2, ref2, BOX, mas, None)
+    got2 = np.full((N, N), 2.0, np.float32)
+    getattr(MASL, mas + "c2D")(p2, got2, BOX, 4)
+    assert cell_err(got2 - 2.0, ref2) < 1e-4    # the +2 offset costs float32 digits
+
+
+@pytest.mark.parametrize("mas", MAS)
+def test_slab_deposit_with_ghost_planes(env, oracle, mas):
+    """Two x-slabs with ghost planes, merged the way the halo exchange does, equal the full grid."""
+    torch, MASL, _lib = env
+    lib = _lib.load()
+    N = 32
+    pos, W = make_particles(21, 120000, True)
+    ref = np.zeros((N, N, N), np.float32)
+    oracle.MA(pos, ref, BOX, mas, W)
+    inv = np.float32(N) / np.float32(BOX)
+    owner_plane = np.floor((pos[:, 0] * inv).astype(np.float32)).astype(np.int64) % N
+    if mas == "NGP":
+        owner_plane = (np.floor(pos[:, 0] * inv + 0.5).astype(np.int64)) % N
+    lo, hi = 1, 2                                    # ghost planes below / above (enough for PCS)
+    full = torch.zeros((N, N, N), dtype=torch.float32, device="cuda")
+    bounds = [(0, 13), (13, N)]
+    for (a, b) in bounds:
+        sel = (owner_plane >= a) & (owner_plane < b)
+        p = torch.from_numpy(pos[sel]).cuda()
+        w = torch.from_numpy(W[sel]).cuda()
+        planes = (b - a) + lo + hi
+        slab = torch.zeros((planes, N, N), dtype=torch.float32, device="cuda")
+        dropped = torch.zeros(1, dtype=torch.int64, device="cuda")
+        st = lib.pyl_deposit_slab(_lib.MAS_IDS[mas], p.data_ptr(), slab.data_ptr(), w.data_ptr(), p.shape[0], N,
+                                  np.float32(BOX), (a - lo) % N, planes, dropped.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream)
+        assert st == 0, lib.pyl_last_error()
+        assert int(dropped.item()) == 0
+        idx = (torch.arange(planes, device="cuda") + (a - lo)) % N
+        full.index_add_(0, idx, slab)
+    assert cell_err(full.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("mas", ["CIC", "PCS"])
+def test_mass_conservation_full_size(env, mas):
+    """BASELINE config 2 shape (512^3 particles on 512^3 cells), library/tests/test.py:30, plus the
+    size-independent properties: linearity in W and agreement between deposit algorithms."""
+    torch, MASL, _ = env
+    N = 512
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    pos = torch.rand((N ** 3, 3), generator=g, device="cuda", dtype=torch.float32) * BOX
+    grid = torch.zeros((N, N, N), dtype=torch.float32, device="cuda")
+    MASL.MA(pos, grid, BOX, mas)
+    total = float(grid.sum(dtype=torch.float64).item())
+    assert abs(total / N ** 3 - 1.0) < 1e-5
+    W = torch.full((N ** 3,), 2.0, dtype=torch.float32, device="cuda")
+    grid2 = torch.zeros_like(grid)
+    MASL.MA(pos, grid2, BOX, mas, W, mode="atomic")
+    scale = float(grid.abs().mean().item())
+    assert float((grid2 - 2.0 * grid).abs().max().item()) < 2e-5 * max(scale, float(grid.max().item()))
