@@ -65,13 +65,31 @@ __global__ void __launch_bounds__(256) divide_kernel(float *__restrict__ x, int6
 
 // x[i] = float(double(x[i]) / mean) - 1  with mean = sum[0]/count: what the reference's callers do
 // in NumPy, `delta /= np.mean(delta, dtype=np.float64); delta -= 1.0` (docs/source/construction.rst:50,
-// Pk_snapshot.py:88) -- the division happens in float64, the subtraction in float32.
+// Pk_snapshot.py:88) -- the division happens in float64, the subtraction in float32.  The float64
+// quotient is formed as x * (1/mean): it differs from x/mean by at most one float64 ulp, which survives
+// the rounding to float32 in about one element per 2^28.
+__device__ __forceinline__ float overdensity_of(float x, double rmean) {
+    return __fsub_rn(__double2float_rn(__dmul_rn((double)x, rmean)), 1.0f);
+}
+
 __global__ void __launch_bounds__(256) overdensity_kernel(float *__restrict__ x, int64_t n,
                                                           const double *__restrict__ sum, double count) {
-    const double mean = sum[0] / count;
+    const double rmean = count / sum[0];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        x[i] = __fsub_rn(__double2float_rn(__ddiv_rn((double)x[i], mean)), 1.0f);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const int64_t n4 = n >> 2;
+        float4 *x4 = reinterpret_cast<float4 *>(x);
+        for (int64_t i = tid; i < n4; i += stride) {
+            float4 v = x4[i];
+            v.x = overdensity_of(v.x, rmean); v.y = overdensity_of(v.y, rmean);
+            v.z = overdensity_of(v.z, rmean); v.w = overdensity_of(v.w, rmean);
+            x4[i] = v;
+        }
+        for (int64_t i = (n4 << 2) + tid; i < n; i += stride) x[i] = overdensity_of(x[i], rmean);
+    } else {
+        for (int64_t i = tid; i < n; i += stride) x[i] = overdensity_of(x[i], rmean);
+    }
 }
 
 __global__ void __launch_bounds__(256) add_kernel(float *__restrict__ out,
@@ -178,7 +196,7 @@ int pyl_overdensity_inplace(float *x, int64_t n, const double *sum, double count
     PYL_REQUIRE(x != nullptr || n == 0, "pyl_overdensity_inplace: x is NULL");
     PYL_REQUIRE(sum != nullptr && count > 0.0, "pyl_overdensity_inplace: bad sum/count");
     if (n <= 0) return PYL_OK;
-    overdensity_kernel<<<ew_grid(n * 4), 256, 0, as_stream(stream)>>>(x, n, sum, count);
+    overdensity_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, n, sum, count);
     PYL_LAUNCH_CHECK();
     return PYL_OK;
 }

@@ -7,12 +7,15 @@
 // placed particle is a 32-byte sector read-modify-write) and runs at 1.8% of the HBM roofline.
 //
 // Pipeline (all on the caller's stream, scratch in the caller's workspace):
-//   1. tile_count    one pass over pos: cell coordinate dist = fl32(pos*inv) per axis, stencil base
-//                    cell -> tile id (tile = 16 x 16 x 32 cells), histogram with red.global.u32.
-//   2. exclusive scan of the tile histogram (cub::DeviceScan).
-//   3. tile_scatter  second pass over pos: slot = atomicAdd(cursor[tile]) ; writes (dist.xyz, W) as one
-//                    aligned float4 -> the particles of a tile are contiguous ("bucket").
-//   4. tile_deposit  one CTA per tile, looping over the bucket in chunks of 2048 particles:
+//   1. tile_count    histogram of a 1-in-8 SAMPLE of the particles over tiles (tile = 8 x 16 x 32 cells):
+//                    cell coordinate dist = fl32(pos*inv) per axis, stencil base cell -> tile id.
+//   2. tile_caps + exclusive scan (cub::DeviceScan): per-tile bucket capacity = 1.125 x estimate +
+//                    4 sigma of the sampling noise + 32, and the bucket start offsets.
+//   3. tile_scatter  ONE full pass over pos: slot = atomicAdd(fill[tile]); writes (dist.xyz, W) as one
+//                    aligned float4 into the tile's bucket.  A particle that finds its bucket full (rare:
+//                    beyond 4 sigma) is deposited on the spot with red.global -- correctness never
+//                    depends on the estimate.
+//   4. tile_deposit  one CTA per tile, looping over the bucket in chunks of 1024 particles:
 //        a. counting sort of the chunk by local cell (x,y,z) inside shared memory: one packed-u16
 //           shared atomic per particle for the rank, block scan, scatter into a sorted float4 array
 //           (stencil fractions + W) -- so every (x,y) row of the tile is contiguous and z-ordered;
@@ -31,15 +34,17 @@
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
+#include "deposit_point.cuh"
 #include "stencil.cuh"
 
 namespace pyl {
 
-constexpr int TX = 16, TY = 16, TZ = 32;        // tile extent in cells
-constexpr int TILE_CELLS = TX * TY * TZ;        // 8192
+constexpr int TX = 8, TY = 16, TZ = 32;         // tile extent in cells
+constexpr int TILE_CELLS = TX * TY * TZ;        // 4096
 constexpr int TNT = 256;                        // threads per tile CTA
-constexpr int CHUNK = 2048;                     // particles sorted per pass
-constexpr int PER = CHUNK / TNT;                // 8 per thread
+constexpr int CHUNK = 1024;                     // particles sorted per pass
+constexpr int PER = CHUNK / TNT;                // 4 per thread
+constexpr int SAMPLE = 8;                       // tile_count looks at one particle group in SAMPLE
 
 struct TileGeom {
     int dims;
@@ -111,7 +116,7 @@ __device__ __forceinline__ unsigned tile_and_local(const float d[3], const TileG
     return ((unsigned)t[0] * g.nty + t[1]) * g.ntz + t[2];
 }
 
-// ---- 1. histogram ---------------------------------------------------------------------------------
+// ---- 1. sampled histogram --------------------------------------------------------------------------
 template <int MAS>
 __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict__ pos, int64_t particles,
                                                          TileGeom g, unsigned *__restrict__ counts, int vec_ok) {
@@ -120,7 +125,9 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict
     const int64_t groups = vec_ok ? (particles >> 2) : 0;
     int local[3];
     float frac[3];
-    for (int64_t grp = tid; grp < groups; grp += stride) {
+    // every SAMPLE-th group of 4 particles
+    for (int64_t sg = tid; sg * SAMPLE < groups; sg += stride) {
+        const int64_t grp = sg * SAMPLE;
         float p[12];
         const float4 *src = reinterpret_cast<const float4 *>(pos + grp * 12);
 #pragma unroll
@@ -136,7 +143,9 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict
             atomicAdd(counts + tile_and_local<MAS>(d, g, local, frac), 1u);
         }
     }
-    for (int64_t i = (groups << 2) + tid; i < particles; i += stride) {
+    // unaligned input / tail: every SAMPLE-th particle
+    for (int64_t si = tid; (groups << 2) + si * SAMPLE < particles; si += stride) {
+        const int64_t i = (groups << 2) + si * SAMPLE;
         float d[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) d[a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
@@ -144,18 +153,49 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict
     }
 }
 
-// ---- 3. scatter into buckets ----------------------------------------------------------------------
-// cursor[] enters holding the exclusive scan (bucket starts) and leaves holding the bucket ENDS.
+// ---- 2. capacities from the sampled counts (in place; then scanned into bucket starts) ---------------
+__host__ __device__ __forceinline__ unsigned tile_capacity(unsigned sampled) {
+    // 1.125 x estimate + 4 sigma (sigma of the estimate = SAMPLE*sqrt(sampled)) + 32
+    const unsigned est = sampled * SAMPLE;
+    const unsigned sig = (unsigned)(4.0f * SAMPLE * sqrtf((float)sampled)) + 1u;
+    return est + (est >> 3) + sig + 32u;
+}
+
+__global__ void tile_caps_kernel(unsigned *__restrict__ counts, unsigned ntiles) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ntiles) counts[i] = tile_capacity(counts[i]);
+    else if (i == ntiles) counts[i] = 0u;
+}
+
+// ---- 3. scatter into buckets (single full pass) --------------------------------------------------------
+template <int MAS, bool WEIGHTED>
+__device__ __forceinline__ void scatter_one(const float d[3], float wp, const TileGeom &g,
+                                            const unsigned *__restrict__ starts, unsigned *__restrict__ fill,
+                                            float4 *__restrict__ bucket, float *__restrict__ number) {
+    int local[3];
+    float frac[3];
+    const unsigned t = tile_and_local<MAS>(d, g, local, frac);
+    const unsigned s0 = __ldg(starts + t), s1 = __ldg(starts + t + 1);
+    const unsigned slot = atomicAdd(fill + t, 1u);
+    if (slot < s1 - s0) {
+        bucket[s0 + slot] = make_float4(d[0], d[1], d[2], wp);
+    } else {
+        // bucket full (capacity came from a sample): deposit this particle directly
+        unsigned long long dropped = 0;
+        deposit_dist<MAS, 3, WEIGHTED, false>(d, wp, number, g.dims, SlabWindow{0, g.dims}, dropped);
+    }
+}
+
 template <int MAS, bool WEIGHTED>
 __global__ void __launch_bounds__(256) tile_scatter_kernel(const float *__restrict__ pos,
                                                            const float *__restrict__ W, int64_t particles,
-                                                           TileGeom g, unsigned *__restrict__ cursor,
-                                                           float4 *__restrict__ bucket, int vec_ok) {
+                                                           TileGeom g, const unsigned *__restrict__ starts,
+                                                           unsigned *__restrict__ fill,
+                                                           float4 *__restrict__ bucket,
+                                                           float *__restrict__ number, int vec_ok) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t groups = vec_ok ? (particles >> 2) : 0;
-    int local[3];
-    float frac[3];
     for (int64_t grp = tid; grp < groups; grp += stride) {
         float p[12];
         const float4 *src = reinterpret_cast<const float4 *>(pos + grp * 12);
@@ -169,24 +209,19 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(const float *__restri
             const float4 v = __ldg(reinterpret_cast<const float4 *>(W + grp * 4));
             wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
         }
-        unsigned slot[4];
-        float d[4][3];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
+            float d[3];
 #pragma unroll
-            for (int a = 0; a < 3; a++) d[q][a] = cell_coordinate(p[3 * q + a], g.inv_cell_size);
-            slot[q] = atomicAdd(cursor + tile_and_local<MAS>(d[q], g, local, frac), 1u);
+            for (int a = 0; a < 3; a++) d[a] = cell_coordinate(p[3 * q + a], g.inv_cell_size);
+            scatter_one<MAS, WEIGHTED>(d, wv[q], g, starts, fill, bucket, number);
         }
-#pragma unroll
-        for (int q = 0; q < 4; q++) bucket[slot[q]] = make_float4(d[q][0], d[q][1], d[q][2], wv[q]);
     }
     for (int64_t i = (groups << 2) + tid; i < particles; i += stride) {
         float d[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) d[a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
-        const float wp = WEIGHTED ? __ldg(W + i) : 1.0f;
-        const unsigned slot = atomicAdd(cursor + tile_and_local<MAS>(d, g, local, frac), 1u);
-        bucket[slot] = make_float4(d[0], d[1], d[2], wp);
+        scatter_one<MAS, WEIGHTED>(d, WEIGHTED ? __ldg(W + i) : 1.0f, g, starts, fill, bucket, number);
     }
 }
 
@@ -207,9 +242,9 @@ __device__ __forceinline__ unsigned off16(const unsigned *cnt, int key) {
 }
 
 template <int MAS>
-__global__ void __launch_bounds__(TNT, 2)
-tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restrict__ ends,
-                    float *__restrict__ number, TileGeom g) {
+__global__ void __launch_bounds__(TNT, 4)
+tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restrict__ starts,
+                    const unsigned *__restrict__ fill, float *__restrict__ number, TileGeom g) {
     using SM = TileSmem<MAS>;
     constexpr int S = SM::S, AY = SM::AY, AZ = SM::AZ, AX = SM::AX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -220,8 +255,8 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
     unsigned *warp_part = reinterpret_cast<unsigned *>(sorted_yz + CHUNK);        // 8 words
 
     const unsigned tile = blockIdx.x;
-    const unsigned begin = tile ? ends[tile - 1] : 0u;
-    const unsigned end = ends[tile];
+    const unsigned begin = starts[tile];
+    const unsigned end = begin + min(fill[tile], starts[tile + 1] - begin);   // overflow went the direct way
     if (begin == end) return;                                 // empty tile: nothing to add
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -305,8 +340,8 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
         }
         __syncthreads();
 
-        // ---- b. stencil accumulation: warp `warp` owns target planes X = warp, warp+8, warp+16 -----------
-        // (with TX = 16 and 8 warps every warp gets exactly 2*S source-plane visits: balanced)
+        // ---- b. stencil accumulation: warp `warp` owns target planes X = warp, warp+8 -------------------
+        // (with TX = 8 and 8 warps every warp gets exactly S source-plane visits per chunk: balanced)
         for (int X = warp; X < AX; X += TNT / 32) {
             float *plane = acc + X * AY * AZ;
 #pragma unroll 1
@@ -332,32 +367,42 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
                     float wxl = wx[0];
 #pragma unroll
                     for (int j = 1; j < S; j++) wxl = (l == j) ? wx[j] : wxl;
+                    const float wxw = wxl * v.w;
 
-                    // runs of equal cell are contiguous; same[k]: lane+2^k belongs to my run
-                    const int prev = __shfl_up_sync(0xffffffffu, yz, 1);
-                    const bool head = valid && (lane == 0 || prev != yz);
-                    unsigned same = 0;
-#pragma unroll
-                    for (int k = 0; k < 5; k++) {
-                        const int o = __shfl_down_sync(0xffffffffu, yz, 1 << k);
-                        if (lane + (1 << k) < 32 && o == yz) same |= 1u << k;
-                    }
-                    const unsigned any_same = __reduce_or_sync(0xffffffffu, same);
-                    const int nsteps = 32 - __clz(any_same);
+                    // particles of equal cell are contiguous (sorted): `peers` = my run
+                    const unsigned peers = __match_any_sync(0xffffffffu, yz);
+                    const bool head = valid && (lane == __ffs(peers) - 1);
+                    const int run_max = __reduce_max_sync(0xffffffffu, __popc(peers));
                     float *cellp = plane + y * AZ + lz;
 
+                    if (run_max == 1) {
+                        // every lane owns a distinct cell of the target plane: plain read-modify-writes
 #pragma unroll
-                    for (int m = 0; m < S; m++) {
-                        const float wxy = __fmul_rn(wxl, wy[m]);
+                        for (int m = 0; m < S; m++) {
+                            const float wxy = wxw * wy[m];
 #pragma unroll
-                        for (int nn = 0; nn < S; nn++) {
-                            float val = __fmul_rn(__fmul_rn(wxy, wz[nn]), v.w);
-                            for (int k = 0; k < nsteps; k++) {
-                                const float o = __shfl_down_sync(0xffffffffu, val, 1 << k);
-                                if (same & (1u << k)) val += o;
+                            for (int nn = 0; nn < S; nn++) {
+                                if (valid) cellp[m * AZ + nn] += wxy * wz[nn];
+                                __syncwarp();
                             }
-                            if (head) cellp[m * AZ + nn] += val;
-                            __syncwarp();
+                        }
+                    } else {
+                        // segmented suffix scan over each run; its head lane adds the run's sum
+                        const unsigned above = peers >> lane;          // bit d: lane+d is in my run
+                        const int nsteps = 32 - __clz(run_max - 1);
+#pragma unroll
+                        for (int m = 0; m < S; m++) {
+                            const float wxy = wxw * wy[m];
+#pragma unroll
+                            for (int nn = 0; nn < S; nn++) {
+                                float val = wxy * wz[nn];
+                                for (int k = 0; k < nsteps; k++) {
+                                    const float o = __shfl_down_sync(0xffffffffu, val, 1 << k);
+                                    if (above & (1u << (1 << k))) val += o;
+                                }
+                                if (head) cellp[m * AZ + nn] += val;
+                                __syncwarp();
+                            }
                         }
                     }
                 }
@@ -393,37 +438,67 @@ static TileGeom make_geom(int dims, float BoxSize) {
     return g;
 }
 
-static size_t scan_temp_bytes(unsigned ntiles) {
+static size_t scan_temp_bytes(unsigned n) {
     size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (unsigned *)nullptr, (unsigned *)nullptr, (int)ntiles);
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (unsigned *)nullptr, (unsigned *)nullptr, (int)n);
     return bytes;
 }
 
+// upper bound of sum_t tile_capacity(c_t) given sum_t c_t <= particles/SAMPLE + 4 (Cauchy-Schwarz on
+// the sqrt term); the scatter kernel can therefore never write past the bucket array
+static size_t bucket_slots_bound(int64_t particles, unsigned ntiles) {
+    const double sampled = (double)particles / SAMPLE + 8.0;
+    const double bound = 1.125 * SAMPLE * sampled + (4.0 * SAMPLE + 1.0) * sqrt((double)ntiles * sampled) +
+                         34.0 * (double)ntiles;
+    return (size_t)bound + 1024;
+}
+
 bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes) {
+    (void)mas;
     if (axes != 3 || dims < 64) return false;                       // halo wrap assumes dims >> stencil
-    if (particles >= ((int64_t)1 << 32) - 1) return false;          // 32-bit bucket offsets
     const TileGeom g = make_geom(dims, 1.0f);
     if ((int64_t)g.ntiles > ((int64_t)1 << 30)) return false;
+    if (bucket_slots_bound(particles, g.ntiles) >= ((size_t)1 << 32)) return false;   // 32-bit offsets
     return particles >= (int64_t)g.ntiles * 64;                     // sparse inputs: per-tile overhead loses
 }
 
+struct TiledWorkspace {
+    float4 *bucket;
+    unsigned *starts;   // ntiles + 1 : sampled counts -> capacities -> exclusive scan
+    unsigned *fill;     // ntiles     : bucket cursors
+    void *scan_tmp;
+    size_t scan_bytes;
+    size_t total;
+};
+
+static TiledWorkspace carve(void *ws, int64_t particles, unsigned ntiles) {
+    TiledWorkspace w;
+    char *base = reinterpret_cast<char *>(ws);
+    size_t off = 0;
+    w.bucket = reinterpret_cast<float4 *>(base + off);
+    off += align_up(bucket_slots_bound(particles, ntiles) * 16, 256);
+    w.starts = reinterpret_cast<unsigned *>(base + off);
+    off += align_up(((size_t)ntiles + 1) * 4, 256);
+    w.fill = reinterpret_cast<unsigned *>(base + off);
+    off += align_up((size_t)ntiles * 4, 256);
+    w.scan_tmp = base + off;
+    w.scan_bytes = scan_temp_bytes(ntiles + 1);
+    off += align_up(w.scan_bytes, 256);
+    w.total = off;
+    return w;
+}
+
 size_t deposit_tiled_workspace(int mas, int64_t particles, int dims, int axes, int mode) {
+    (void)mas; (void)axes; (void)mode;
     const TileGeom g = make_geom(dims, 1.0f);
-    return align_up((size_t)particles * 16, 256) + align_up(((size_t)g.ntiles + 1) * 4, 256) +
-           align_up(scan_temp_bytes(g.ntiles + 1), 256);
+    return carve(nullptr, particles, g.ntiles).total;
 }
 
 template <int MAS>
 static int run_tiled(const float *pos, float *number, const float *W, int64_t particles, int dims,
                      float BoxSize, void *ws, cudaStream_t stream) {
     const TileGeom g = make_geom(dims, BoxSize);
-    char *base = reinterpret_cast<char *>(ws);
-    float4 *bucket = reinterpret_cast<float4 *>(base);
-    base += align_up((size_t)particles * 16, 256);
-    unsigned *cursor = reinterpret_cast<unsigned *>(base);
-    base += align_up(((size_t)g.ntiles + 1) * 4, 256);
-    void *scan_tmp = base;
-    size_t scan_bytes = scan_temp_bytes(g.ntiles + 1);
+    const TiledWorkspace w = carve(ws, particles, g.ntiles);
 
     const int vec_ok = ((reinterpret_cast<uintptr_t>(pos) & 15) == 0) &&
                        (W == nullptr || (reinterpret_cast<uintptr_t>(W) & 15) == 0);
@@ -431,15 +506,25 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    int64_t cblocks = (blocks + SAMPLE - 1) / SAMPLE;
+    if (cblocks < 1) cblocks = 1;
 
-    PYL_CUDA_CHECK(cudaMemsetAsync(cursor, 0, ((size_t)g.ntiles + 1) * 4, stream));
-    tile_count_kernel<MAS><<<(int)blocks, 256, 0, stream>>>(pos, particles, g, cursor, vec_ok);
+    // starts[] and fill[] are adjacent: one memset clears both
+    PYL_CUDA_CHECK(cudaMemsetAsync(w.starts, 0,
+                                   reinterpret_cast<char *>(w.fill) - reinterpret_cast<char *>(w.starts) +
+                                       (size_t)g.ntiles * 4, stream));
+    tile_count_kernel<MAS><<<(int)cblocks, 256, 0, stream>>>(pos, particles, g, w.starts, vec_ok);
     PYL_LAUNCH_CHECK();
-    PYL_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, cursor, cursor, (int)(g.ntiles + 1), stream));
+    tile_caps_kernel<<<(g.ntiles + 1 + 255) / 256, 256, 0, stream>>>(w.starts, g.ntiles);
+    PYL_LAUNCH_CHECK();
+    PYL_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.scan_tmp, const_cast<size_t &>(w.scan_bytes), w.starts, w.starts,
+                                                 (int)(g.ntiles + 1), stream));
     if (W)
-        tile_scatter_kernel<MAS, true><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, cursor, bucket, vec_ok);
+        tile_scatter_kernel<MAS, true><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, w.starts, w.fill,
+                                                                        w.bucket, number, vec_ok);
     else
-        tile_scatter_kernel<MAS, false><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, cursor, bucket, vec_ok);
+        tile_scatter_kernel<MAS, false><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, w.starts, w.fill,
+                                                                         w.bucket, number, vec_ok);
     PYL_LAUNCH_CHECK();
 
     static bool attr_done[4] = {false, false, false, false};
@@ -448,7 +533,7 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
                                             (int)TileSmem<MAS>::bytes));
         attr_done[MAS] = true;
     }
-    tile_deposit_kernel<MAS><<<g.ntiles, TNT, TileSmem<MAS>::bytes, stream>>>(bucket, cursor, number, g);
+    tile_deposit_kernel<MAS><<<g.ntiles, TNT, TileSmem<MAS>::bytes, stream>>>(w.bucket, w.starts, w.fill, number, g);
     PYL_LAUNCH_CHECK();
     return PYL_OK;
 }
