@@ -34,7 +34,7 @@ EPS_FFT = 1e-5
 
 
 def _tol(ref, scale, tol):
-    """|got-ref| <= tol*|ref| + EPS_FFT*sqrt(scale*max(scale)).
+    """|got-ref| <= tol*|ref| + EPS_FFT*sqrt(scale*max(scale)) + EPS_FFT^2*max(scale).
 
     The first term is the north_star bound.  The second is the single-precision FFT floor: two float32
     FFTs (cuFFT here, pocketfft in the oracle, FFTW in the reference) agree per mode to ~1e-6 of the
@@ -43,7 +43,9 @@ def _tol(ref, scale, tol):
     With tol=TOL and same-delta_k inputs (test_bin_kernel_same_delta_k) the second term is dropped."""
     scale = np.abs(np.where(np.isnan(scale), 0.0, scale))
     peak = float(np.max(scale)) if scale.size else 0.0
-    return tol * np.abs(ref) + EPS_FFT * np.sqrt(scale * peak)
+    # third term: a mode whose own amplitude is ~0 (the DC mode of a zero-mean field) still carries the
+    # amplitude error eps*A_peak, i.e. a power of eps^2 * P_peak
+    return tol * np.abs(ref) + EPS_FFT * np.sqrt(scale * peak) + EPS_FFT ** 2 * peak
 
 
 def check_pk(got, ref, cross=False, tol=TOL, fft_floor=True):
