@@ -86,6 +86,14 @@ int pyl_deposit_slab(int mas, const float *pos, float *number, const float *W,
                      int64_t particles, int dims, float BoxSize, int x_origin, int x_planes,
                      int64_t *dropped, pyl_stream_t stream);
 
+/* plane[i] = wrapped x index of the FIRST stencil cell of particle i (NGP: the cell itself; CIC:
+ * floor(dist); TSC: floor(dist-1.5)+1; PCS: floor(dist-2)+1), computed with the deposit's own
+ * arithmetic.  The multi-GPU path routes a particle to the rank owning that plane; its stencil then
+ * covers planes plane .. plane+S-1 (S = 1,2,3,4), i.e. only upward ghost planes are needed.
+ * pos: DEVICE float32 [particles][3]; plane: DEVICE int32 [particles]. */
+int pyl_stencil_base_plane(int mas, const float *pos, int64_t particles, int dims, float BoxSize,
+                           int32_t *plane, pyl_stream_t stream);
+
 /* x[i] /= divisor, IEEE float32 division: the 2D renormalisation `number2 /= 2.0|3.0|4.0`
  * of MAS_library.pyx:90-107 */
 int pyl_divide_inplace(float *x, int64_t n, float divisor, pyl_stream_t stream);

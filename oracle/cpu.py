@@ -118,10 +118,12 @@ def bin_raw(delta_k_list, dims, mas_indices, axis, BoxSize, phase=False):
 class Pk:
     """Pk_library.pyx:263-420."""
 
-    def __init__(self, delta, BoxSize, axis=2, MAS="CIC", threads=1, verbose=True):
-        dims = len(delta)
+    def __init__(self, delta, BoxSize, axis=2, MAS="CIC", threads=1, verbose=True, delta_k=None):
+        """`delta_k` (test hook): bin this half-spectrum instead of transforming `delta`."""
+        dims = len(delta) if delta_k is None else delta_k.shape[0]
         kF, kN, kmax_par, kmax_per, kmax = frequencies(BoxSize, dims)
-        r = bin_raw([fft3d_r2c(delta, threads)], dims, [MAS_function(MAS)], axis, BoxSize, phase=True)
+        dk = fft3d_r2c(delta, threads) if delta_k is None else delta_k
+        r = bin_raw([dk], dims, [MAS_function(MAS)], axis, BoxSize, phase=True)
         fact = (BoxSize / dims ** 2) ** 3
 
         # 1D (:384-391): drop the DC bin, units, <k_par>, perpendicular-area weight
@@ -162,14 +164,16 @@ class Pk:
 class XPk:
     """Pk_library.pyx:529-793."""
 
-    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1):
-        dims = len(delta[0]); F = len(delta); X = F * (F - 1) // 2
-        for d in delta[1:]:
+    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1, delta_k=None):
+        """`delta_k` (test hook): list of half-spectra to bin instead of transforming `delta`."""
+        src = delta if delta_k is None else delta_k
+        dims = len(src[0]); F = len(src); X = F * (F - 1) // 2
+        for d in src[1:]:
             if len(d) != dims:
                 raise ValueError("Fields have different grid sizes!!!")
         kF, kN, kmax_par, kmax_per, kmax = frequencies(BoxSize, dims)
-        r = bin_raw([fft3d_r2c(d, threads) for d in delta], dims,
-                    [MAS_function(m) for m in MAS], axis, BoxSize)
+        dks = [fft3d_r2c(d, threads) for d in delta] if delta_k is None else list(delta_k)
+        r = bin_raw(dks, dims, [MAS_function(m) for m in MAS], axis, BoxSize)
         fact = (BoxSize / dims ** 2) ** 3
 
         k1D = r["k1D"][1:].copy(); Nm1D = r["Nm1D"][1:].copy()

@@ -10,6 +10,8 @@ int deposit_tiled(int mas, const float *pos, float *number, const float *W, int6
                   int dims, int axes, float BoxSize, int mode, void *ws, size_t ws_bytes,
                   cudaStream_t stream);
 bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes);
+int stencil_base_plane(int mas, const float *pos, int64_t particles, int dims, float BoxSize, int32_t *plane,
+                       cudaStream_t stream);
 }  // namespace pyl
 
 using namespace pyl;
@@ -53,6 +55,15 @@ int pyl_deposit(int mas, const float *pos, float *number, const float *W, int64_
     }
     return deposit_tiled(mas, pos, number, W, particles, dims, axes, BoxSize, m, ws, ws_bytes,
                          as_stream(stream));
+}
+
+int pyl_stencil_base_plane(int mas, const float *pos, int64_t particles, int dims, float BoxSize,
+                           int32_t *plane, pyl_stream_t stream) {
+    PYL_REQUIRE(mas >= PYL_MAS_NGP && mas <= PYL_MAS_PCS, "pyl_stencil_base_plane: unknown scheme");
+    PYL_REQUIRE(dims > 0 && BoxSize > 0.0f && particles >= 0, "pyl_stencil_base_plane: bad sizes");
+    if (particles == 0) return PYL_OK;
+    PYL_REQUIRE(pos != nullptr && plane != nullptr, "pyl_stencil_base_plane: NULL pointer");
+    return stencil_base_plane(mas, pos, particles, dims, BoxSize, plane, as_stream(stream));
 }
 
 int pyl_deposit_slab(int mas, const float *pos, float *number, const float *W,

@@ -86,6 +86,38 @@ static int dispatch_atomic(const float *pos, const float *W, float *number, int6
              : launch_atomic<MAS, 2, false, false>(pos, W, number, particles, dims, inv, win, dropped, s);
 }
 
+// first stencil cell along x (wrapped), same arithmetic as axis_stencil<MAS>
+template <int MAS>
+__global__ void __launch_bounds__(256) base_plane_kernel(const float *__restrict__ pos, int64_t particles,
+                                                         int dims, float inv_cell_size,
+                                                         int32_t *__restrict__ plane) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < particles; i += stride) {
+        int idx[StencilWidth<MAS>::value];
+        float w[StencilWidth<MAS>::value];
+        axis_stencil<MAS>(cell_coordinate(__ldg(pos + i * 3), inv_cell_size), dims, idx, w);
+        plane[i] = idx[0];
+    }
+}
+
+int stencil_base_plane(int mas, const float *pos, int64_t particles, int dims, float BoxSize,
+                       int32_t *plane, cudaStream_t stream) {
+    const float inv = (float)dims / BoxSize;
+    int64_t blocks = (particles + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    switch (mas) {
+        case PYL_MAS_NGP: base_plane_kernel<PYL_MAS_NGP><<<(int)blocks, 256, 0, stream>>>(pos, particles, dims, inv, plane); break;
+        case PYL_MAS_CIC: base_plane_kernel<PYL_MAS_CIC><<<(int)blocks, 256, 0, stream>>>(pos, particles, dims, inv, plane); break;
+        case PYL_MAS_TSC: base_plane_kernel<PYL_MAS_TSC><<<(int)blocks, 256, 0, stream>>>(pos, particles, dims, inv, plane); break;
+        case PYL_MAS_PCS: base_plane_kernel<PYL_MAS_PCS><<<(int)blocks, 256, 0, stream>>>(pos, particles, dims, inv, plane); break;
+        default: set_last_error("stencil_base_plane: unknown scheme %d", mas); return PYL_ERR_ARG;
+    }
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
 // shared with deposit.cu
 int deposit_atomic(int mas, const float *pos, float *number, const float *W, int64_t particles,
                    int dims, int axes, float BoxSize, bool slab, int x_origin, int x_planes,

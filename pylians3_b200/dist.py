@@ -1,0 +1,277 @@
+"""Slab-decomposed multi-GPU MA -> delta -> Pk/XPk (one process per GPU, torch.distributed).
+
+The reference has no distributed path (one process, whole grid in host RAM).
+This module shards the SAME computation over P ranks by x-slabs of the grid:
+
+  route      each particle goes to the rank owning the x-plane of its FIRST stencil cell
+             (all-to-all of positions/weights; skipped when the caller already holds its own)
+  deposit    into [own planes + S-1 upward ghost planes]  (pyl_deposit_slab)
+  halo       ghost planes travel to the next rank (ring send/recv, periodic) and are added
+             into its first planes (pyl_add_inplace)
+  delta      local float64 sum -> all-reduce -> n/<n> - 1 (pyl_overdensity_inplace)
+  FFT        batched 2D r2c over (y,z) of the local planes (pyl_fft_slab_yz) -> all-to-all
+             transpose (ky chunks) -> 1D c2c along x (pyl_fft_slab_x); no transpose back: the bin
+             kernel only needs to know which ky rows it holds
+  bin        pyl_pk_bin on the (dims, nky_local, dims/2+1) block -> all-reduce of the raw
+             accumulators -> host finalisation (identical on every rank)
+
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the plumbing; every arithmetic step is
+a kernel of libpyl_b200.so reached through `DeviceOps`.  The CPU tests inject numpy stand-ins for
+those kernels to exercise the communication skeleton with world_size 2 and no GPU.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _device as D
+from . import _lib as L
+from . import Pk_library as PKL
+
+_S = {"NGP": 1, "CIC": 2, "TSC": 3, "PCS": 4}
+
+
+def split_sizes(n, parts):
+    """Contiguous split of range(n) into `parts` pieces (first n%parts pieces get one more)."""
+    base, extra = divmod(n, parts)
+    sizes = [base + (1 if r < extra else 0) for r in range(parts)]
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    return sizes, offs
+
+
+class DeviceOps:
+    """The compute kernels of the path, bound to libpyl_b200.so (device pointers, current stream)."""
+
+    def __init__(self, device):
+        self.lib = L.load()
+        self.device = device
+
+    def _s(self):
+        return D.stream_ptr(self.device)
+
+    def base_plane(self, mas, pos, dims, BoxSize):
+        out = torch.empty(pos.shape[0], dtype=torch.int32, device=pos.device)
+        L.check(self.lib.pyl_stencil_base_plane(L.MAS_IDS[mas], D.ptr(pos), pos.shape[0], dims,
+                                                float(np.float32(BoxSize)), D.ptr(out), self._s()),
+                "pyl_stencil_base_plane")
+        return out
+
+    def deposit_slab(self, mas, pos, work, W, dims, BoxSize, x_origin, dropped):
+        L.check(self.lib.pyl_deposit_slab(L.MAS_IDS[mas], D.ptr(pos), D.ptr(work), D.ptr(W), pos.shape[0], dims,
+                                          float(np.float32(BoxSize)), int(x_origin), work.shape[0],
+                                          D.ptr(dropped), self._s()), "pyl_deposit_slab")
+
+    def add_inplace(self, out, inp):
+        L.check(self.lib.pyl_add_inplace(D.ptr(out), D.ptr(inp), out.numel(), self._s()), "pyl_add_inplace")
+
+    def sum_f64(self, x):
+        out = torch.empty(1, dtype=torch.float64, device=x.device)
+        L.check(self.lib.pyl_sum_f64(D.ptr(x), x.numel(), D.ptr(out), self._s()), "pyl_sum_f64")
+        return out
+
+    def overdensity_(self, x, total, cells):
+        L.check(self.lib.pyl_overdensity_inplace(D.ptr(x), x.numel(), D.ptr(total), float(cells), self._s()),
+                "pyl_overdensity_inplace")
+
+    def fft_yz(self, slab, dims):
+        nx = slab.shape[0]
+        out = torch.empty((nx, dims, dims // 2 + 1), dtype=torch.complex64, device=slab.device)
+        need = self.lib.pyl_fft_slab_workspace_bytes(dims, nx, 0)
+        if need == ctypes.c_size_t(-1).value:
+            L.check(-3, "pyl_fft_slab_workspace_bytes")
+        ws = D.workspace(need, slab.device, "fft")
+        L.check(self.lib.pyl_fft_slab_yz(D.ptr(slab), D.ptr(out), dims, nx, D.ptr(ws), need, self._s()),
+                "pyl_fft_slab_yz")
+        return out
+
+    def fft_x_(self, cols, dims):
+        nky = cols.shape[1]
+        need = self.lib.pyl_fft_slab_workspace_bytes(dims, 0, nky)
+        if need == ctypes.c_size_t(-1).value:
+            L.check(-3, "pyl_fft_slab_workspace_bytes")
+        ws = D.workspace(need, cols.device, "fft")
+        L.check(self.lib.pyl_fft_slab_x(D.ptr(cols), dims, nky, D.ptr(ws), need, self._s()), "pyl_fft_slab_x")
+        return cols
+
+    def bin(self, dk_list, mas_index, dims, axis, want_phase, ky_lo, nky):
+        return PKL.bin_device(dk_list, mas_index, dims, axis, want_phase, ky_lo, nky)
+
+
+class _Result:
+    pass
+
+
+class SlabContext:
+    """Per-rank state of one slab-decomposed grid: plane ranges, neighbours, scratch buffers."""
+
+    def __init__(self, dims, BoxSize, group=None, device=None, ops=None):
+        if not dist.is_initialized():
+            raise RuntimeError("SlabContext needs torch.distributed to be initialised")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.dims = int(dims)
+        self.BoxSize = float(BoxSize)
+        self.nz = self.dims // 2 + 1
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.ops = ops if ops is not None else DeviceOps(self.device)
+        self.x_sizes, self.x_offs = split_sizes(self.dims, self.world)
+        self.ky_sizes, self.ky_offs = split_sizes(self.dims, self.world)
+        self.x_range = (self.x_offs[self.rank], self.x_offs[self.rank + 1])
+        self.ky_range = (self.ky_offs[self.rank], self.ky_offs[self.rank + 1])
+        self.nx = self.x_sizes[self.rank]
+        self.nky = self.ky_sizes[self.rank]
+        if min(self.x_sizes) < 3:
+            raise ValueError("slabs thinner than the PCS ghost width (dims=%d over %d ranks)" % (dims, self.world))
+        self.dropped = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._plane_owner = None
+
+    # ---- helpers ----------------------------------------------------------------------------------
+    def new_slab(self):
+        return torch.zeros((self.nx, self.dims, self.dims), dtype=torch.float32, device=self.device)
+
+    def plane_owner(self):
+        if self._plane_owner is None:
+            own = torch.empty(self.dims, dtype=torch.int64)
+            for r in range(self.world):
+                own[self.x_offs[r]:self.x_offs[r + 1]] = r
+            self._plane_owner = own.to(self.device)
+        return self._plane_owner
+
+    def _all_to_all(self, recv, send, recv_sizes, send_sizes):
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_sizes, input_split_sizes=send_sizes,
+                               group=self.group)
+
+    # ---- particles -> owner ranks ----------------------------------------------------------------
+    def route(self, pos, MAS, W=None):
+        """Send every particle to the rank that owns the x-plane of its first stencil cell."""
+        plane = self.ops.base_plane(MAS, pos, self.dims, self.BoxSize)
+        owner = self.plane_owner()[plane.long()]
+        order = torch.argsort(owner, stable=True)
+        send_counts = torch.bincount(owner, minlength=self.world)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc = [int(c) for c in send_counts.cpu()]
+        rc = [int(c) for c in recv_counts.cpu()]
+        pos_s = pos[order].contiguous()
+        pos_r = torch.empty((sum(rc), 3), dtype=torch.float32, device=pos.device)
+        self._all_to_all(pos_r.view(-1), pos_s.view(-1), [3 * c for c in rc], [3 * c for c in sc])
+        W_r = None
+        if W is not None:
+            W_s = W[order].contiguous()
+            W_r = torch.empty(sum(rc), dtype=torch.float32, device=pos.device)
+            self._all_to_all(W_r, W_s, rc, sc)
+        return pos_r, W_r
+
+    # ---- mass assignment -------------------------------------------------------------------------
+    def MA(self, pos, slab, MAS="CIC", W=None, routed=False):
+        """slab (nx_local, dims, dims) += deposit of this rank's share; ghost planes go to the next rank."""
+        if MAS not in _S:
+            raise ValueError("option not valid!!!")
+        if not routed:
+            pos, W = self.route(pos, MAS, W)
+        ghosts = _S[MAS] - 1
+        x0 = self.x_range[0]
+        if ghosts == 0:
+            self.ops.deposit_slab(MAS, pos, slab, W, self.dims, self.BoxSize, x0, self.dropped)
+            return
+        work = torch.zeros((self.nx + ghosts, self.dims, self.dims), dtype=torch.float32, device=self.device)
+        self.ops.deposit_slab(MAS, pos, work, W, self.dims, self.BoxSize, x0, self.dropped)
+        halo_out = work[self.nx:]                        # planes x1 .. x1+ghosts-1 belong to the next rank
+        if self.world == 1:
+            halo_in = halo_out
+        else:
+            halo_in = torch.empty_like(halo_out)
+            nxt, prv = (self.rank + 1) % self.world, (self.rank - 1) % self.world
+            ops = [dist.P2POp(dist.isend, halo_out, nxt, self.group), dist.P2POp(dist.irecv, halo_in, prv, self.group)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        self.ops.add_inplace(slab, work[:self.nx])
+        self.ops.add_inplace(slab[:ghosts], halo_in)
+
+    def check_dropped(self):
+        """Raise if any stencil contribution fell outside a rank's planes (mis-routed particles)."""
+        d = self.dropped.clone()
+        dist.all_reduce(d, group=self.group)
+        n = int(d.item())
+        if n:
+            raise RuntimeError("%d stencil contributions fell outside their slab: particles were not routed" % n)
+
+    # ---- delta = n/<n> - 1 -----------------------------------------------------------------------
+    def overdensity_(self, slab):
+        total = self.ops.sum_f64(slab)
+        dist.all_reduce(total, group=self.group)
+        self.ops.overdensity_(slab, total, float(self.dims) ** 3)
+        return slab
+
+    # ---- distributed r2c: (nx_local, N, N) real -> (N, nky_local, nz) complex ---------------------
+    def fft(self, slab):
+        N, nz, P = self.dims, self.nz, self.world
+        a = self.ops.fft_yz(slab, N)                                   # (nx, N, nz)
+        if P == 1:
+            return self.ops.fft_x_(a, N)
+        send = torch.empty(self.nx * N * nz, dtype=a.dtype, device=slab.device)
+        send_sizes, off = [], 0                                        # (complex64 on the GPU path)
+        for r in range(P):                                             # pack: ky chunk r of every local plane
+            k0, k1 = self.ky_offs[r], self.ky_offs[r + 1]
+            n = self.nx * (k1 - k0) * nz
+            send[off:off + n].view(self.nx, k1 - k0, nz).copy_(a[:, k0:k1, :])
+            send_sizes.append(2 * n)
+            off += n
+        del a
+        recv_sizes = [2 * self.x_sizes[s] * self.nky * nz for s in range(P)]
+        recv = torch.empty((N, self.nky, nz), dtype=send.dtype, device=slab.device)
+        # blocks arrive ordered by source rank = ascending x: the receive buffer IS (N, nky, nz)
+        self._all_to_all(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1), recv_sizes, send_sizes)
+        del send
+        return self.ops.fft_x_(recv, N)
+
+    # ---- spectra -----------------------------------------------------------------------------------
+    def _reduce(self, out, lay):
+        """All-reduce the raw accumulators.  Counts (uint64 words) become float64 first -- exact below
+        2^53 -- so that one float64 SUM covers the whole buffer."""
+        f64 = out.view(torch.float64)
+        for off, n in ((lay.Nm3D, lay.kmax + 1), (lay.Nm1D, lay.kmax_par + 1), (lay.Nm2D, lay.n2d)):
+            f64[off:off + n] = out[off:off + n].to(torch.float64)
+        dist.all_reduce(f64, group=self.group)
+        return f64
+
+    def _raw(self, dk_list, mas_index, axis, want_phase):
+        out, lay = self.ops.bin(dk_list, mas_index, self.dims, axis, want_phase, self.ky_range[0], self.nky)
+        f64 = self._reduce(out, lay).cpu().numpy()
+        words = f64.view(np.int64).copy()
+        for off, n in ((lay.Nm3D, lay.kmax + 1), (lay.Nm1D, lay.kmax_par + 1), (lay.Nm2D, lay.n2d)):
+            words[off:off + n] = np.rint(f64[off:off + n]).astype(np.int64)
+        return PKL.unpack_raw(words, lay)
+
+    def Pk(self, slab, axis=2, MAS="CIC"):
+        """Pk_library.Pk of the slab-distributed field; every rank gets the full result."""
+        dk = self.fft(slab)
+        raw = self._raw([dk], [PKL.MAS_function(MAS)], axis, True)
+        o = PKL._finalize(raw, self.BoxSize, self.dims)
+        r = _Result()
+        r.k1D, r.Pk1D, r.Nmodes1D = o["k1D"], o["Pk1D"][:, 0], o["Nmodes1D"]
+        r.kpar, r.kper, r.Pk2D, r.Nmodes2D = o["kpar"], o["kper"], o["Pk2D"][:, 0], o["Nmodes2D"]
+        r.k3D, r.Nmodes3D = o["k3D"], o["Nmodes3D"]
+        r.Pk, r.Pkphase = np.ascontiguousarray(o["Pk"][:, :, 0]), o["Pkphase"]
+        return r
+
+    def XPk(self, slabs, axis=2, MAS=None):
+        """Pk_library.XPk of several slab-distributed fields (<= L.MAX_FIELDS per launch)."""
+        if MAS is None or len(MAS) != len(slabs):
+            raise TypeError("MAS must be a list with one scheme per field")
+        if len(slabs) > L.MAX_FIELDS:
+            raise ValueError("the distributed XPk bins at most %d fields per call" % L.MAX_FIELDS)
+        dk = [self.fft(s) for s in slabs]
+        raw = self._raw(dk, [PKL.MAS_function(m) for m in MAS], axis, False)
+        o = PKL._finalize(raw, self.BoxSize, self.dims)
+        r = _Result()
+        r.k1D, r.Nmodes1D, r.Pk1D, r.PkX1D = o["k1D"], o["Nmodes1D"], o["Pk1D"], o["PkX1D"]
+        r.kpar, r.kper, r.Nmodes2D, r.Pk2D, r.PkX2D = o["kpar"], o["kper"], o["Nmodes2D"], o["Pk2D"], o["PkX2D"]
+        r.k3D, r.Nmodes3D, r.Pk, r.XPk = o["k3D"], o["Nmodes3D"], o["Pk"], o["XPk"]
+        return r

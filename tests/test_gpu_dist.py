@@ -1,0 +1,91 @@
+"""GPU, 2 ranks over NCCL: the slab-decomposed path (pylians3_b200.dist with the real CUDA kernels)
+against the CPU oracle.  Skipped on boxes with a single GPU (the CPU/gloo twin is test_dist_cpu.py)."""
+import os
+import socket
+import sys
+import traceback
+
+import numpy as np
+import pytest
+
+from conftest import BOX, ROOT, make_particles, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, N, q):
+    try:
+        import torch
+        import torch.distributed as dist
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        from pylians3_b200 import dist as PD
+        from oracle import cpu as O
+        ctx = PD.SlabContext(N, BOX)
+        pos, W = make_particles(77, 4 * N ** 3, True)
+        mine = slice(rank, None, world)
+        x0, x1 = ctx.x_range
+        res = {}
+        slabs, refs = {}, {}
+        for mas, w in (("NGP", None), ("CIC", W), ("TSC", None), ("PCS", W)):
+            slab = ctx.new_slab()
+            ctx.MA(torch.from_numpy(pos[mine].copy()).to(dev), slab, mas,
+                   None if w is None else torch.from_numpy(w[mine].copy()).to(dev))
+            ref = np.zeros((N, N, N), np.float32)
+            O.MA(pos, ref, BOX, mas, w)
+            got = slab.cpu().numpy()
+            res["ma_" + mas] = rel_err(got, ref[x0:x1], floor=float(np.mean(np.abs(ref))))
+            slabs[mas], refs[mas] = slab, ref
+        ctx.check_dropped()
+        for mas in ("CIC", "PCS"):
+            ref = refs[mas]
+            ref /= np.mean(ref, dtype=np.float64)
+            ref -= 1.0
+            ctx.overdensity_(slabs[mas])
+        from test_gpu_pk import check_pk, quiet
+        for axis in (0, 1, 2):
+            got = ctx.Pk(slabs["PCS"], axis, "PCS")
+            want = O.Pk(refs["PCS"], BOX, axis, "PCS", 1, False)
+            check_pk(got, want)
+        gx = ctx.XPk([slabs["PCS"], slabs["CIC"]], 0, ["PCS", "CIC"])
+        wx = quiet(O.XPk, [refs["PCS"], refs["CIC"]], BOX, 0, ["PCS", "CIC"], 1)
+        check_pk(gx, wx, cross=True)
+        q.put((rank, "ok", res))
+        dist.destroy_process_group()
+    except Exception:
+        q.put((rank, "fail", traceback.format_exc()))
+
+
+@pytest.mark.parametrize("N", [64, 45])
+def test_two_gpu_slab_pipeline(oracle, N):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, N, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, payload in out:
+        assert status == "ok", "rank %d:\n%s" % (rank, payload)
+        assert payload["ma_NGP"] == 0.0
+        for k in ("ma_CIC", "ma_TSC", "ma_PCS"):
+            assert payload[k] < 1e-5, (k, payload[k])
