@@ -78,13 +78,17 @@ int pyl_deposit(int mas, const float *pos, float *number, const float *W, int64_
                 pyl_stream_t stream);
 
 /* Slab variant for one rank of a multi-GPU run (x-slab decomposition).
- * `number` holds `x_planes` consecutive x-planes of the global grid starting at global
- * plane `x_origin` (periodic: plane index is taken modulo dims), i.e. the rank's own planes
- * plus its ghost planes.  A stencil cell whose x-plane falls outside is NOT deposited and is
- * counted in *dropped (DEVICE int64, may be NULL; the caller checks it is 0). 3D only. */
+ * `number` holds `x_planes` consecutive x-planes of the global grid starting at global plane
+ * `x_origin` (periodic: plane indices are taken modulo dims): the rank's `x_own` own planes followed
+ * by x_planes - x_own upward ghost planes.  Particles must have been routed by
+ * pyl_stencil_base_plane (first stencil plane among the own planes).  A stencil cell whose plane
+ * falls outside the window is NOT deposited and is counted in *dropped (DEVICE int64, may be NULL;
+ * the caller checks that it stays 0).  3D only.  With a workspace of
+ * pyl_deposit_slab_workspace_bytes() bytes the tiled kernel is used, otherwise (ws NULL) the atomic. */
+size_t pyl_deposit_slab_workspace_bytes(int mas, int64_t particles, int dims, int x_own);
 int pyl_deposit_slab(int mas, const float *pos, float *number, const float *W,
-                     int64_t particles, int dims, float BoxSize, int x_origin, int x_planes,
-                     int64_t *dropped, pyl_stream_t stream);
+                     int64_t particles, int dims, float BoxSize, int x_origin, int x_own, int x_planes,
+                     int64_t *dropped, void *ws, size_t ws_bytes, pyl_stream_t stream);
 
 /* plane[i] = wrapped x index of the FIRST stencil cell of particle i (NGP: the cell itself; CIC:
  * floor(dist); TSC: floor(dist-1.5)+1; PCS: floor(dist-2)+1), computed with the deposit's own

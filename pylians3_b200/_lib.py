@@ -41,7 +41,8 @@ PROTOTYPES = {
     "pyl_kernel_launches": (ctypes.c_ulonglong, []),
     "pyl_deposit_workspace_bytes": (_sz, [_i, _i64, _i, _i, _i]),
     "pyl_deposit": (_i, [_i, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, _sz, _vp]),
-    "pyl_deposit_slab": (_i, [_i, _vp, _vp, _vp, _i64, _i, _f, _i, _i, _vp, _vp]),
+    "pyl_deposit_slab_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
+    "pyl_deposit_slab": (_i, [_i, _vp, _vp, _vp, _i64, _i, _f, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "pyl_stencil_base_plane": (_i, [_i, _vp, _i64, _i, _f, _vp, _vp]),
     "pyl_divide_inplace": (_i, [_vp, _i64, _f, _vp]),
     "pyl_scale_inplace": (_i, [_vp, _i64, _f, _vp]),

@@ -5,11 +5,11 @@ namespace pyl {
 int deposit_atomic(int mas, const float *pos, float *number, const float *W, int64_t particles,
                    int dims, int axes, float BoxSize, bool slab, int x_origin, int x_planes,
                    int64_t *dropped, cudaStream_t stream);
-size_t deposit_tiled_workspace(int mas, int64_t particles, int dims, int axes, int mode);
-int deposit_tiled(int mas, const float *pos, float *number, const float *W, int64_t particles,
-                  int dims, int axes, float BoxSize, int mode, void *ws, size_t ws_bytes,
+size_t deposit_tiled_workspace(int mas, int64_t particles, int dims, int axes, int mode, int x_own);
+int deposit_tiled(int mas, const float *pos, float *number, const float *W, int64_t particles, int dims,
+                  float BoxSize, int x_origin, int x_own, int x_planes, int64_t *dropped, void *ws,
                   cudaStream_t stream);
-bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes);
+bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes, int x_own);
 int stencil_base_plane(int mas, const float *pos, int64_t particles, int dims, float BoxSize, int32_t *plane,
                        cudaStream_t stream);
 }  // namespace pyl
@@ -18,7 +18,7 @@ using namespace pyl;
 
 static int resolve_mode(int mas, int64_t particles, int dims, int axes, int mode) {
     if (mode == PYL_MODE_ATOMIC) return mode;
-    const bool ok = deposit_tiled_supported(mas, particles, dims, axes);
+    const bool ok = deposit_tiled_supported(mas, particles, dims, axes, -1);
     if (mode == PYL_MODE_AUTO) return ok ? PYL_MODE_TILED : PYL_MODE_ATOMIC;
     return ok ? mode : PYL_MODE_ATOMIC;   // TILED / DETERMINISTIC requested but not applicable
 }
@@ -29,7 +29,7 @@ size_t pyl_deposit_workspace_bytes(int mas, int64_t particles, int dims, int axe
     if (mas < PYL_MAS_NGP || mas > PYL_MAS_PCS || particles <= 0 || dims <= 0) return 0;
     const int m = resolve_mode(mas, particles, dims, axes, mode);
     if (m == PYL_MODE_ATOMIC) return 0;
-    return deposit_tiled_workspace(mas, particles, dims, axes, m);
+    return deposit_tiled_workspace(mas, particles, dims, axes, m, -1);
 }
 
 int pyl_deposit(int mas, const float *pos, float *number, const float *W, int64_t particles,
@@ -48,12 +48,12 @@ int pyl_deposit(int mas, const float *pos, float *number, const float *W, int64_
     if (m == PYL_MODE_ATOMIC)
         return deposit_atomic(mas, pos, number, W, particles, dims, axes, BoxSize, false, 0, dims,
                               nullptr, as_stream(stream));
-    const size_t need = deposit_tiled_workspace(mas, particles, dims, axes, m);
+    const size_t need = deposit_tiled_workspace(mas, particles, dims, axes, m, -1);
     if (ws == nullptr || ws_bytes < need) {
         set_last_error("pyl_deposit: workspace of %zu bytes required, %zu given", need, ws_bytes);
         return PYL_ERR_WORKSPACE;
     }
-    return deposit_tiled(mas, pos, number, W, particles, dims, axes, BoxSize, m, ws, ws_bytes,
+    return deposit_tiled(mas, pos, number, W, particles, dims, BoxSize, 0, -1, -1, nullptr, ws,
                          as_stream(stream));
 }
 
@@ -66,15 +66,27 @@ int pyl_stencil_base_plane(int mas, const float *pos, int64_t particles, int dim
     return stencil_base_plane(mas, pos, particles, dims, BoxSize, plane, as_stream(stream));
 }
 
+size_t pyl_deposit_slab_workspace_bytes(int mas, int64_t particles, int dims, int x_own) {
+    if (mas < PYL_MAS_NGP || mas > PYL_MAS_PCS || particles <= 0 || dims <= 0 || x_own <= 0) return 0;
+    if (!deposit_tiled_supported(mas, particles, dims, 3, x_own)) return 0;
+    return deposit_tiled_workspace(mas, particles, dims, 3, PYL_MODE_TILED, x_own);
+}
+
 int pyl_deposit_slab(int mas, const float *pos, float *number, const float *W,
-                     int64_t particles, int dims, float BoxSize, int x_origin, int x_planes,
-                     int64_t *dropped, pyl_stream_t stream) {
+                     int64_t particles, int dims, float BoxSize, int x_origin, int x_own, int x_planes,
+                     int64_t *dropped, void *ws, size_t ws_bytes, pyl_stream_t stream) {
     PYL_REQUIRE(mas >= PYL_MAS_NGP && mas <= PYL_MAS_PCS, "pyl_deposit_slab: unknown scheme");
     PYL_REQUIRE(dims > 0 && x_planes > 0 && x_planes <= dims, "pyl_deposit_slab: bad plane window");
+    PYL_REQUIRE(x_own > 0 && x_own <= x_planes, "pyl_deposit_slab: x_own must be in 1..x_planes");
     PYL_REQUIRE(x_origin >= 0 && x_origin < dims, "pyl_deposit_slab: x_origin outside [0,dims)");
     PYL_REQUIRE(particles >= 0 && BoxSize > 0.0f, "pyl_deposit_slab: bad particles/BoxSize");
     if (particles == 0) return PYL_OK;
     PYL_REQUIRE(pos != nullptr && number != nullptr, "pyl_deposit_slab: NULL pos/number");
+    const size_t need = pyl_deposit_slab_workspace_bytes(mas, particles, dims, x_own);
+    if (need > 0 && ws != nullptr && ws_bytes >= need && x_planes < dims)
+        return deposit_tiled(mas, pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dropped,
+                             ws, as_stream(stream));
+    // no (or too small a) workspace, sparse input, or a window spanning the whole grid: atomic kernel
     return deposit_atomic(mas, pos, number, W, particles, dims, 3, BoxSize, true, x_origin,
                           x_planes, dropped, as_stream(stream));
 }

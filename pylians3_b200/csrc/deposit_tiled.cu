@@ -51,7 +51,14 @@ struct TileGeom {
     int ntx, nty, ntz;
     unsigned ntiles;
     float inv_cell_size;
+    // x window of the destination buffer (multi-GPU slabs).  Whole grid: x_origin = 0, x_own = x_planes =
+    // dims and planes wrap periodically.  Slab: the buffer holds global planes x_origin .. x_origin +
+    // x_planes - 1; a particle belongs here iff its first stencil plane is one of the first x_own planes
+    // (the other x_planes - x_own planes are the upward ghost planes its stencil may reach).
+    int x_origin, x_own, x_planes;
 };
+
+constexpr unsigned NO_TILE = 0xffffffffu;
 
 // unwrapped base cell of the stencil (first of the S cells) and the fraction the weights depend on
 template <int MAS>
@@ -106,14 +113,20 @@ __device__ __forceinline__ unsigned tile_and_local(const float d[3], const TileG
                                                    float frac[3]) {
     int t[3];
     const int T[3] = {TX, TY, TZ};
+    bool mine = true;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         const int b = stencil_base<MAS>(d[a], frac[a]);
-        const int wb = wrap_index(b, g.dims);
+        int wb = wrap_index(b, g.dims);
+        if (a == 0) {                       // plane index inside the destination window
+            wb -= g.x_origin;
+            if (wb < 0) wb += g.dims;
+            mine = wb < g.x_own;
+        }
         t[a] = wb / T[a];
         local[a] = wb - t[a] * T[a];
     }
-    return ((unsigned)t[0] * g.nty + t[1]) * g.ntz + t[2];
+    return mine ? ((unsigned)t[0] * g.nty + t[1]) * g.ntz + t[2] : NO_TILE;
 }
 
 // ---- 1. sampled histogram --------------------------------------------------------------------------
@@ -140,7 +153,8 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict
             float d[3];
 #pragma unroll
             for (int a = 0; a < 3; a++) d[a] = cell_coordinate(p[3 * q + a], g.inv_cell_size);
-            atomicAdd(counts + tile_and_local<MAS>(d, g, local, frac), 1u);
+            const unsigned t = tile_and_local<MAS>(d, g, local, frac);
+            if (t != NO_TILE) atomicAdd(counts + t, 1u);
         }
     }
     // unaligned input / tail: every SAMPLE-th particle
@@ -149,7 +163,8 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict
         float d[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) d[a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
-        atomicAdd(counts + tile_and_local<MAS>(d, g, local, frac), 1u);
+        const unsigned t = tile_and_local<MAS>(d, g, local, frac);
+        if (t != NO_TILE) atomicAdd(counts + t, 1u);
     }
 }
 
@@ -171,18 +186,25 @@ __global__ void tile_caps_kernel(unsigned *__restrict__ counts, unsigned ntiles)
 template <int MAS, bool WEIGHTED>
 __device__ __forceinline__ void scatter_one(const float d[3], float wp, const TileGeom &g,
                                             const unsigned *__restrict__ starts, unsigned *__restrict__ fill,
-                                            float4 *__restrict__ bucket, float *__restrict__ number) {
+                                            float4 *__restrict__ bucket, float *__restrict__ number,
+                                            unsigned long long &dropped) {
     int local[3];
     float frac[3];
     const unsigned t = tile_and_local<MAS>(d, g, local, frac);
+    if (t == NO_TILE) {                 // not routed to this slab: nothing of it is deposited here
+        dropped += StencilWidth<MAS>::value * StencilWidth<MAS>::value * StencilWidth<MAS>::value;
+        return;
+    }
     const unsigned s0 = __ldg(starts + t), s1 = __ldg(starts + t + 1);
     const unsigned slot = atomicAdd(fill + t, 1u);
     if (slot < s1 - s0) {
         bucket[s0 + slot] = make_float4(d[0], d[1], d[2], wp);
     } else {
         // bucket full (capacity came from a sample): deposit this particle directly
-        unsigned long long dropped = 0;
-        deposit_dist<MAS, 3, WEIGHTED, false>(d, wp, number, g.dims, SlabWindow{0, g.dims}, dropped);
+        if (g.x_planes == g.dims)
+            deposit_dist<MAS, 3, WEIGHTED, false>(d, wp, number, g.dims, SlabWindow{0, g.dims}, dropped);
+        else
+            deposit_dist<MAS, 3, WEIGHTED, true>(d, wp, number, g.dims, SlabWindow{g.x_origin, g.x_planes}, dropped);
     }
 }
 
@@ -192,10 +214,13 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(const float *__restri
                                                            TileGeom g, const unsigned *__restrict__ starts,
                                                            unsigned *__restrict__ fill,
                                                            float4 *__restrict__ bucket,
-                                                           float *__restrict__ number, int vec_ok) {
+                                                           float *__restrict__ number,
+                                                           unsigned long long *__restrict__ dropped_out,
+                                                           int vec_ok) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t groups = vec_ok ? (particles >> 2) : 0;
+    unsigned long long dropped = 0;
     for (int64_t grp = tid; grp < groups; grp += stride) {
         float p[12];
         const float4 *src = reinterpret_cast<const float4 *>(pos + grp * 12);
@@ -214,15 +239,16 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(const float *__restri
             float d[3];
 #pragma unroll
             for (int a = 0; a < 3; a++) d[a] = cell_coordinate(p[3 * q + a], g.inv_cell_size);
-            scatter_one<MAS, WEIGHTED>(d, wv[q], g, starts, fill, bucket, number);
+            scatter_one<MAS, WEIGHTED>(d, wv[q], g, starts, fill, bucket, number, dropped);
         }
     }
     for (int64_t i = (groups << 2) + tid; i < particles; i += stride) {
         float d[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) d[a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
-        scatter_one<MAS, WEIGHTED>(d, WEIGHTED ? __ldg(W + i) : 1.0f, g, starts, fill, bucket, number);
+        scatter_one<MAS, WEIGHTED>(d, WEIGHTED ? __ldg(W + i) : 1.0f, g, starts, fill, bucket, number, dropped);
     }
+    if (dropped_out != nullptr && dropped != 0) atomicAdd(dropped_out, dropped);
 }
 
 // ---- 4. per-tile deposit ----------------------------------------------------------------------------
@@ -287,7 +313,9 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
                     const int b = stencil_base<MAS>(d[a], fr[a]);
-                    lc[a] = wrap_index(b, g.dims) - org[a];
+                    int wb = wrap_index(b, g.dims);
+                    if (a == 0) { wb -= g.x_origin; if (wb < 0) wb += g.dims; }
+                    lc[a] = wb - org[a];
                 }
                 key[q] = (lc[0] * TY + lc[1]) * TZ + lc[2];
                 part[q] = make_float4(fr[0], fr[1], fr[2], v.w);
@@ -417,8 +445,8 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
         const float val = acc[i];
         if (val != 0.0f) {
             const int az = i % AZ, ay = (i / AZ) % AY, ax = i / (AZ * AY);
-            int gx = ox + ax, gy = oy + ay, gz = oz + az;
-            if (gx >= dims) gx -= dims;
+            int gx = ox + ax, gy = oy + ay, gz = oz + az;     // gx: plane inside the destination buffer
+            if (gx >= g.x_planes) gx -= g.x_planes;           // only when the buffer is the whole periodic grid
             if (gy >= dims) gy -= dims;
             if (gz >= dims) gz -= dims;
             atomicAdd(number + ((int64_t)gx * dims + gy) * dims + gz, val);
@@ -427,10 +455,13 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
-static TileGeom make_geom(int dims, float BoxSize) {
+static TileGeom make_geom(int dims, float BoxSize, int x_origin = 0, int x_own = -1, int x_planes = -1) {
     TileGeom g;
     g.dims = dims;
-    g.ntx = (dims + TX - 1) / TX;
+    g.x_origin = x_origin;
+    g.x_own = x_own < 0 ? dims : x_own;
+    g.x_planes = x_planes < 0 ? dims : x_planes;
+    g.ntx = (g.x_own + TX - 1) / TX;
     g.nty = (dims + TY - 1) / TY;
     g.ntz = (dims + TZ - 1) / TZ;
     g.ntiles = (unsigned)g.ntx * g.nty * g.ntz;
@@ -453,10 +484,10 @@ static size_t bucket_slots_bound(int64_t particles, unsigned ntiles) {
     return (size_t)bound + 1024;
 }
 
-bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes) {
+bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes, int x_own) {
     (void)mas;
     if (axes != 3 || dims < 64) return false;                       // halo wrap assumes dims >> stencil
-    const TileGeom g = make_geom(dims, 1.0f);
+    const TileGeom g = make_geom(dims, 1.0f, 0, x_own, x_own);
     if ((int64_t)g.ntiles > ((int64_t)1 << 30)) return false;
     if (bucket_slots_bound(particles, g.ntiles) >= ((size_t)1 << 32)) return false;   // 32-bit offsets
     return particles >= (int64_t)g.ntiles * 64;                     // sparse inputs: per-tile overhead loses
@@ -488,16 +519,17 @@ static TiledWorkspace carve(void *ws, int64_t particles, unsigned ntiles) {
     return w;
 }
 
-size_t deposit_tiled_workspace(int mas, int64_t particles, int dims, int axes, int mode) {
+size_t deposit_tiled_workspace(int mas, int64_t particles, int dims, int axes, int mode, int x_own) {
     (void)mas; (void)axes; (void)mode;
-    const TileGeom g = make_geom(dims, 1.0f);
+    const TileGeom g = make_geom(dims, 1.0f, 0, x_own, x_own);
     return carve(nullptr, particles, g.ntiles).total;
 }
 
 template <int MAS>
 static int run_tiled(const float *pos, float *number, const float *W, int64_t particles, int dims,
-                     float BoxSize, void *ws, cudaStream_t stream) {
-    const TileGeom g = make_geom(dims, BoxSize);
+                     float BoxSize, int x_origin, int x_own, int x_planes, unsigned long long *dropped,
+                     void *ws, cudaStream_t stream) {
+    const TileGeom g = make_geom(dims, BoxSize, x_origin, x_own, x_planes);
     const TiledWorkspace w = carve(ws, particles, g.ntiles);
 
     const int vec_ok = ((reinterpret_cast<uintptr_t>(pos) & 15) == 0) &&
@@ -521,10 +553,10 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
                                                  (int)(g.ntiles + 1), stream));
     if (W)
         tile_scatter_kernel<MAS, true><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, w.starts, w.fill,
-                                                                        w.bucket, number, vec_ok);
+                                                                        w.bucket, number, dropped, vec_ok);
     else
         tile_scatter_kernel<MAS, false><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, w.starts, w.fill,
-                                                                         w.bucket, number, vec_ok);
+                                                                         w.bucket, number, dropped, vec_ok);
     PYL_LAUNCH_CHECK();
 
     static bool attr_done[4] = {false, false, false, false};
@@ -538,14 +570,16 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
     return PYL_OK;
 }
 
+// x_own < 0: whole periodic grid.  Otherwise the slab window of pyl_deposit_slab.
 int deposit_tiled(int mas, const float *pos, float *number, const float *W, int64_t particles, int dims,
-                  int axes, float BoxSize, int mode, void *ws, size_t ws_bytes, cudaStream_t stream) {
-    (void)axes; (void)mode; (void)ws_bytes;
+                  float BoxSize, int x_origin, int x_own, int x_planes, int64_t *dropped, void *ws,
+                  cudaStream_t stream) {
+    unsigned long long *dr = reinterpret_cast<unsigned long long *>(dropped);
     switch (mas) {
-        case PYL_MAS_NGP: return run_tiled<PYL_MAS_NGP>(pos, number, W, particles, dims, BoxSize, ws, stream);
-        case PYL_MAS_CIC: return run_tiled<PYL_MAS_CIC>(pos, number, W, particles, dims, BoxSize, ws, stream);
-        case PYL_MAS_TSC: return run_tiled<PYL_MAS_TSC>(pos, number, W, particles, dims, BoxSize, ws, stream);
-        case PYL_MAS_PCS: return run_tiled<PYL_MAS_PCS>(pos, number, W, particles, dims, BoxSize, ws, stream);
+        case PYL_MAS_NGP: return run_tiled<PYL_MAS_NGP>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, stream);
+        case PYL_MAS_CIC: return run_tiled<PYL_MAS_CIC>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, stream);
+        case PYL_MAS_TSC: return run_tiled<PYL_MAS_TSC>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, stream);
+        case PYL_MAS_PCS: return run_tiled<PYL_MAS_PCS>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, stream);
     }
     set_last_error("deposit_tiled: unknown scheme %d", mas);
     return PYL_ERR_ARG;

@@ -59,10 +59,12 @@ class DeviceOps:
                 "pyl_stencil_base_plane")
         return out
 
-    def deposit_slab(self, mas, pos, work, W, dims, BoxSize, x_origin, dropped):
+    def deposit_slab(self, mas, pos, work, W, dims, BoxSize, x_origin, x_own, dropped):
+        need = self.lib.pyl_deposit_slab_workspace_bytes(L.MAS_IDS[mas], pos.shape[0], dims, int(x_own))
+        ws = D.workspace(need, work.device, "deposit")
         L.check(self.lib.pyl_deposit_slab(L.MAS_IDS[mas], D.ptr(pos), D.ptr(work), D.ptr(W), pos.shape[0], dims,
-                                          float(np.float32(BoxSize)), int(x_origin), work.shape[0],
-                                          D.ptr(dropped), self._s()), "pyl_deposit_slab")
+                                          float(np.float32(BoxSize)), int(x_origin), int(x_own), work.shape[0],
+                                          D.ptr(dropped), D.ptr(ws), need, self._s()), "pyl_deposit_slab")
 
     def add_inplace(self, out, inp):
         L.check(self.lib.pyl_add_inplace(D.ptr(out), D.ptr(inp), out.numel(), self._s()), "pyl_add_inplace")
@@ -178,10 +180,10 @@ class SlabContext:
         ghosts = _S[MAS] - 1
         x0 = self.x_range[0]
         if ghosts == 0:
-            self.ops.deposit_slab(MAS, pos, slab, W, self.dims, self.BoxSize, x0, self.dropped)
+            self.ops.deposit_slab(MAS, pos, slab, W, self.dims, self.BoxSize, x0, self.nx, self.dropped)
             return
         work = torch.zeros((self.nx + ghosts, self.dims, self.dims), dtype=torch.float32, device=self.device)
-        self.ops.deposit_slab(MAS, pos, work, W, self.dims, self.BoxSize, x0, self.dropped)
+        self.ops.deposit_slab(MAS, pos, work, W, self.dims, self.BoxSize, x0, self.nx, self.dropped)
         halo_out = work[self.nx:]                        # planes x1 .. x1+ghosts-1 belong to the next rank
         if self.world == 1:
             halo_in = halo_out

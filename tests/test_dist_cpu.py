@@ -110,7 +110,7 @@ class NumpyOps:
         b = base_cell(mas, (pos[:, 0].numpy() * inv).astype(np.float32))
         return torch.from_numpy((b % dims).astype(np.int32))
 
-    def deposit_slab(self, mas, pos, work, W, dims, BoxSize, x_origin, dropped):
+    def deposit_slab(self, mas, pos, work, W, dims, BoxSize, x_origin, x_own, dropped):
         full = np.zeros((dims, dims, dims), np.float32)
         self.O.MA(pos.numpy(), full, BoxSize, mas, None if W is None else W.numpy())
         # like the kernel: global plane p lands in local plane (p - x_origin) mod dims, if that exists

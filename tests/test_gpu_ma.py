@@ -206,13 +206,56 @@ def test_slab_deposit_with_ghost_planes(env, oracle, mas):
         slab = torch.zeros((planes, N, N), dtype=torch.float32, device="cuda")
         dropped = torch.zeros(1, dtype=torch.int64, device="cuda")
         st = lib.pyl_deposit_slab(_lib.MAS_IDS[mas], p.data_ptr(), slab.data_ptr(), w.data_ptr(), p.shape[0], N,
-                                  np.float32(BOX), (a - lo) % N, planes, dropped.data_ptr(),
+                                  np.float32(BOX), (a - lo) % N, planes, planes, dropped.data_ptr(), None, 0,
                                   torch.cuda.current_stream().cuda_stream)
         assert st == 0, lib.pyl_last_error()
         assert int(dropped.item()) == 0
         idx = (torch.arange(planes, device="cuda") + (a - lo)) % N
         full.index_add_(0, idx, slab)
     assert cell_err(full.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("mas", MAS)
+def test_tiled_slab_deposit_routed_by_base_plane(env, oracle, mas):
+    """The multi-GPU form of the tiled kernel: particles routed by pyl_stencil_base_plane, every slab has
+    S-1 upward ghost planes, the workspace enables the tiled path; slabs + ghosts add up to the grid."""
+    torch, MASL, _lib = env
+    lib = _lib.load()
+    N = 128
+    S = MAS.index(mas) + 1
+    pos, W = make_particles(31, 1200000, True)
+    ref = np.zeros((N, N, N), np.float32)
+    oracle.MA(pos, ref, BOX, mas, W)
+    pos_d, W_d = torch.from_numpy(pos).cuda(), torch.from_numpy(W).cuda()
+    plane = torch.empty(len(pos), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.pyl_stencil_base_plane(_lib.MAS_IDS[mas], pos_d.data_ptr(), len(pos), N, np.float32(BOX),
+                                      plane.data_ptr(), stream) == 0
+    full = torch.zeros((N, N, N), dtype=torch.float32, device="cuda")
+    dropped = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for (a, b) in ((0, 41), (41, 90), (90, N)):
+        sel = (plane >= a) & (plane < b)
+        p, w = pos_d[sel].contiguous(), W_d[sel].contiguous()
+        planes = (b - a) + S - 1
+        slab = torch.zeros((planes, N, N), dtype=torch.float32, device="cuda")
+        need = lib.pyl_deposit_slab_workspace_bytes(_lib.MAS_IDS[mas], p.shape[0], N, b - a)
+        assert need > 0
+        ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+        st = lib.pyl_deposit_slab(_lib.MAS_IDS[mas], p.data_ptr(), slab.data_ptr(), w.data_ptr(), p.shape[0], N,
+                                  np.float32(BOX), a, b - a, planes, dropped.data_ptr(), ws.data_ptr(), need, stream)
+        assert st == 0, lib.pyl_last_error()
+        idx = (torch.arange(planes, device="cuda") + a) % N
+        full.index_add_(0, idx, slab)
+    assert int(dropped.item()) == 0
+    assert cell_err(full.cpu().numpy(), ref) < TOL
+    # mis-routed particles are reported, not silently lost
+    slab = torch.zeros((20 + S - 1, N, N), dtype=torch.float32, device="cuda")
+    need = lib.pyl_deposit_slab_workspace_bytes(_lib.MAS_IDS[mas], len(pos), N, 20)
+    ws = torch.empty(max(need, 1), dtype=torch.uint8, device="cuda")
+    st = lib.pyl_deposit_slab(_lib.MAS_IDS[mas], pos_d.data_ptr(), slab.data_ptr(), W_d.data_ptr(), len(pos), N,
+                              np.float32(BOX), 0, 20, 20 + S - 1, dropped.data_ptr(), ws.data_ptr(), need, stream)
+    assert st == 0
+    assert int(dropped.item()) > 0
 
 
 @pytest.mark.parametrize("mas", ["CIC", "PCS"])
