@@ -4,7 +4,7 @@
 namespace pyl {
 int deposit_atomic(int mas, const float *pos, float *number, const float *W, int64_t particles,
                    int dims, int axes, float BoxSize, bool slab, int x_origin, int x_planes,
-                   int64_t *dropped, cudaStream_t stream);
+                   int64_t *dropped, cudaStream_t stream, float plane_mult = 0.0f);
 size_t deposit_tiled_workspace(int mas, int64_t particles, int dims, int axes, int mode, int x_own);
 int deposit_tiled(int mas, const float *pos, float *number, const float *W, int64_t particles, int dims,
                   float BoxSize, int x_origin, int x_own, int x_planes, int64_t *dropped, void *ws,
@@ -22,6 +22,14 @@ static int resolve_mode(int mas, int64_t particles, int dims, int axes, int mode
     if (mode == PYL_MODE_AUTO) return ok ? PYL_MODE_TILED : PYL_MODE_ATOMIC;
     return ok ? mode : PYL_MODE_ATOMIC;   // TILED / DETERMINISTIC requested but not applicable
 }
+
+namespace pyl {
+// MAS_c.c semantics for planes (one add per cell): used by the host-pointer entry points
+int deposit_plane_c_core(int mas, const float *pos, float *number, const float *W, int64_t particles, int dims,
+                         float BoxSize, cudaStream_t stream) {
+    return deposit_atomic(mas, pos, number, W, particles, dims, 2, BoxSize, false, 0, dims, nullptr, stream, 1.0f);
+}
+}  // namespace pyl
 
 extern "C" {
 

@@ -121,11 +121,11 @@ int stencil_base_plane(int mas, const float *pos, int64_t particles, int dims, f
 // shared with deposit.cu
 int deposit_atomic(int mas, const float *pos, float *number, const float *W, int64_t particles,
                    int dims, int axes, float BoxSize, bool slab, int x_origin, int x_planes,
-                   int64_t *dropped, cudaStream_t stream) {
+                   int64_t *dropped, cudaStream_t stream, float plane_mult) {
     // inv_cell_size = dims/BoxSize evaluated in float32 like `cdef float inv_cell_size`
     // (MAS_library.pyx:135); IEEE division on the host, identical to the CPU's.
     const float inv = (float)dims / BoxSize;
-    SlabWindow win{x_origin, x_planes};
+    SlabWindow win{x_origin, x_planes, plane_mult};
     unsigned long long *dr = reinterpret_cast<unsigned long long *>(dropped);
     switch (mas) {
         case PYL_MAS_NGP: return dispatch_atomic<PYL_MAS_NGP>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream);

@@ -9,6 +9,7 @@ namespace pyl {
 struct SlabWindow {
     int x_origin;   // global plane stored at local plane 0
     int x_planes;   // number of local planes (== dims for the whole grid)
+    float plane_mult = 0.0f;   // 2D only: adds per plane cell; 0 -> S (MA's Cython path), 1 -> MAS_c.c
 };
 
 // `dist` = cell coordinates fl32(pos*inv_cell_size) of one particle
@@ -53,7 +54,7 @@ __device__ __forceinline__ void deposit_dist(const float *dist, float wp, float 
             for (int m = 0; m < S; m++) {
                 float v = __fmul_rn(w[0][l], w[1][m]);
                 if (WEIGHTED) v = __fmul_rn(v, wp);
-                atomicAdd(row + idx[1][m], v * (float)S);
+                atomicAdd(row + idx[1][m], v * (win.plane_mult > 0.0f ? win.plane_mult : (float)S));
             }
         }
     }

@@ -202,9 +202,9 @@ __device__ __forceinline__ void scatter_one(const float d[3], float wp, const Ti
     } else {
         // bucket full (capacity came from a sample): deposit this particle directly
         if (g.x_planes == g.dims)
-            deposit_dist<MAS, 3, WEIGHTED, false>(d, wp, number, g.dims, SlabWindow{0, g.dims}, dropped);
+            deposit_dist<MAS, 3, WEIGHTED, false>(d, wp, number, g.dims, SlabWindow{0, g.dims, 0.0f}, dropped);
         else
-            deposit_dist<MAS, 3, WEIGHTED, true>(d, wp, number, g.dims, SlabWindow{g.x_origin, g.x_planes}, dropped);
+            deposit_dist<MAS, 3, WEIGHTED, true>(d, wp, number, g.dims, SlabWindow{g.x_origin, g.x_planes, 0.0f}, dropped);
     }
 }
 

@@ -13,6 +13,9 @@
 
 namespace pyl {
 
+int deposit_plane_c_core(int mas, const float *pos, float *number, const float *W, int64_t particles, int dims,
+                         float BoxSize, cudaStream_t stream);
+
 struct Arena {
     void *ptr = nullptr;
     size_t bytes = 0;
@@ -69,8 +72,11 @@ static int deposit_host(int mas, float *pos, float *number, float *W, long parti
     PYL_CUDA_CHECK(cudaMemcpyAsync(d_pos, pos, (size_t)particles * axes * sizeof(float), cudaMemcpyHostToDevice, s));
     if (W) PYL_CUDA_CHECK(cudaMemcpyAsync(d_w, W, (size_t)particles * sizeof(float), cudaMemcpyHostToDevice, s));
     PYL_CUDA_CHECK(cudaMemcpyAsync(d_grid, number, cells * sizeof(float), cudaMemcpyHostToDevice, s));
-    st = pyl_deposit(mas, d_pos, d_grid, d_w, particles, dims, axes, BoxSize, PYL_MODE_AUTO, d_ws, b_ws,
-                     reinterpret_cast<pyl_stream_t>(s));
+    if (axes == 2)   // MAS_c.c deposits a plane with n_max = 1: ONE add per cell (unlike MA's Cython 2D path)
+        st = deposit_plane_c_core(mas, d_pos, d_grid, d_w, particles, dims, BoxSize, s);
+    else
+        st = pyl_deposit(mas, d_pos, d_grid, d_w, particles, dims, axes, BoxSize, PYL_MODE_AUTO, d_ws, b_ws,
+                         reinterpret_cast<pyl_stream_t>(s));
     if (st != PYL_OK) return st;
     PYL_CUDA_CHECK(cudaMemcpyAsync(number, d_grid, cells * sizeof(float), cudaMemcpyDeviceToHost, s));
     PYL_CUDA_CHECK(cudaStreamSynchronize(s));

@@ -153,8 +153,11 @@ def test_host_pointer_entry_points_match_mas_c_signature(env, oracle, mas):
         npart = 150000 if axes == 3 else 4000
         p = np.ascontiguousarray(pos[:npart, :axes])
         for w in (None, W[:npart]):
-            ref = np.full((N,) * axes, 0.5, np.float32)
-            oracle.MA(p, ref, BOX, mas, w, renormalize_2D=False)
+            # MAS_c.c semantics: accumulate; planes get ONE add per cell (n_max = 1, MAS_c.c:29-34),
+            # i.e. the renormalised Cython plane added onto the existing content
+            dep = np.zeros((N,) * axes, np.float32)
+            oracle.MA(p, dep, BOX, mas, w)
+            ref = np.full((N,) * axes, 0.5, np.float32) + dep
             got = np.full((N,) * axes, 0.5, np.float32)
             st = getattr(lib, "pyl_" + mas)(p.ctypes.data, got.ctypes.data, None if w is None else w.ctypes.data,
                                             p.shape[0], N, axes, np.float32(BOX), 8)
