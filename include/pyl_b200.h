@@ -60,7 +60,7 @@ unsigned long long pyl_kernel_launches(void);
 #define PYL_MODE_AUTO (-1)         /* pick by particle density and scheme                  */
 #define PYL_MODE_ATOMIC 0          /* one red.global.add.f32 per stencil cell              */
 #define PYL_MODE_TILED 1           /* bucket by tile, accumulate in shared memory, flush   */
-#define PYL_MODE_DETERMINISTIC 2   /* as TILED, fixed summation order: bit-reproducible    */
+#define PYL_MODE_DETERMINISTIC 2   /* sort by cell, fixed-order segmented sums: bit-reproducible */
 
 /* Scratch bytes pyl_deposit needs for this problem (0 for PYL_MODE_ATOMIC). */
 size_t pyl_deposit_workspace_bytes(int mas, int64_t particles, int dims, int axes, int mode);

@@ -3,6 +3,7 @@
 
     python profiles/run_stage.py deposit CIC auto 512 [reps]
     python profiles/run_stage.py pk 512 [axis] [reps]
+    python profiles/run_stage.py step 512 [reps]          # the bench.py step: zero, MA(CIC), delta, Pk
 """
 import os
 import sys
@@ -24,6 +25,18 @@ if what == "deposit":
         MASL.MA(pos, grid, BOX, mas, mode=mode)
     torch.cuda.synchronize()
     print("sum/N^3 =", float(grid.sum(dtype=torch.float64)) / N ** 3 / reps)
+elif what == "step":
+    N = int(sys.argv[2])
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    pos = synth.uniform_device(N ** 3, BOX, 1, dev)
+    grid = torch.zeros((N, N, N), dtype=torch.float32, device=dev)
+    for _ in range(reps):
+        grid.zero_()
+        MASL.MA(pos, grid, BOX, "CIC")
+        overdensity_(grid)
+        pk = PKL.Pk(grid, BOX, 0, "CIC", verbose=False)
+    torch.cuda.synchronize()
+    print("Pk0[:3] =", pk.Pk[:3, 0])
 else:
     N = int(sys.argv[2])
     axis = int(sys.argv[3]) if len(sys.argv) > 3 else 0

@@ -10,6 +10,10 @@ int deposit_tiled(int mas, const float *pos, float *number, const float *W, int6
                   float BoxSize, int x_origin, int x_own, int x_planes, int64_t *dropped, void *ws,
                   cudaStream_t stream);
 bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes, int x_own);
+bool deposit_sorted_supported(int64_t particles);
+size_t deposit_sorted_workspace(int64_t particles, int dims, int axes);
+int deposit_sorted(int mas, const float *pos, float *number, const float *W, int64_t particles, int dims,
+                   int axes, float BoxSize, void *ws, cudaStream_t stream);
 int stencil_base_plane(int mas, const float *pos, int64_t particles, int dims, float BoxSize, int32_t *plane,
                        cudaStream_t stream);
 }  // namespace pyl
@@ -18,6 +22,7 @@ using namespace pyl;
 
 static int resolve_mode(int mas, int64_t particles, int dims, int axes, int mode) {
     if (mode == PYL_MODE_ATOMIC) return mode;
+    if (mode == PYL_MODE_DETERMINISTIC) return mode;      // sorted-segment kernel: any dims, 2D or 3D
     const bool ok = deposit_tiled_supported(mas, particles, dims, axes, -1);
     if (mode == PYL_MODE_AUTO) return ok ? PYL_MODE_TILED : PYL_MODE_ATOMIC;
     return ok ? mode : PYL_MODE_ATOMIC;   // TILED / DETERMINISTIC requested but not applicable
@@ -37,6 +42,8 @@ size_t pyl_deposit_workspace_bytes(int mas, int64_t particles, int dims, int axe
     if (mas < PYL_MAS_NGP || mas > PYL_MAS_PCS || particles <= 0 || dims <= 0) return 0;
     const int m = resolve_mode(mas, particles, dims, axes, mode);
     if (m == PYL_MODE_ATOMIC) return 0;
+    if (m == PYL_MODE_DETERMINISTIC)
+        return deposit_sorted_supported(particles) ? deposit_sorted_workspace(particles, dims, axes) : 0;
     return deposit_tiled_workspace(mas, particles, dims, axes, m, -1);
 }
 
@@ -49,18 +56,22 @@ int pyl_deposit(int mas, const float *pos, float *number, const float *W, int64_
     PYL_REQUIRE(particles >= 0, "pyl_deposit: negative particle count");
     PYL_REQUIRE(BoxSize > 0.0f, "pyl_deposit: BoxSize must be positive");
     PYL_REQUIRE(mode >= PYL_MODE_AUTO && mode <= PYL_MODE_DETERMINISTIC, "pyl_deposit: unknown mode");
-    PYL_REQUIRE(mode != PYL_MODE_DETERMINISTIC, "pyl_deposit: PYL_MODE_DETERMINISTIC is not implemented yet");
     if (particles == 0) return PYL_OK;
     PYL_REQUIRE(pos != nullptr && number != nullptr, "pyl_deposit: NULL pos/number");
     const int m = resolve_mode(mas, particles, dims, axes, mode);
     if (m == PYL_MODE_ATOMIC)
         return deposit_atomic(mas, pos, number, W, particles, dims, axes, BoxSize, false, 0, dims,
                               nullptr, as_stream(stream));
-    const size_t need = deposit_tiled_workspace(mas, particles, dims, axes, m, -1);
+    if (m == PYL_MODE_DETERMINISTIC)
+        PYL_REQUIRE(deposit_sorted_supported(particles), "pyl_deposit: deterministic mode takes < 2^32 particles per call");
+    const size_t need = m == PYL_MODE_DETERMINISTIC ? deposit_sorted_workspace(particles, dims, axes)
+                                                    : deposit_tiled_workspace(mas, particles, dims, axes, m, -1);
     if (ws == nullptr || ws_bytes < need) {
         set_last_error("pyl_deposit: workspace of %zu bytes required, %zu given", need, ws_bytes);
         return PYL_ERR_WORKSPACE;
     }
+    if (m == PYL_MODE_DETERMINISTIC)
+        return deposit_sorted(mas, pos, number, W, particles, dims, axes, BoxSize, ws, as_stream(stream));
     return deposit_tiled(mas, pos, number, W, particles, dims, BoxSize, 0, -1, -1, nullptr, ws,
                          as_stream(stream));
 }

@@ -31,6 +31,8 @@
 // operation-identical to the reference, TSC/PCS evaluate the same polynomials in float32 (<= 3 ulp from
 // the reference's float64-then-rounded values, far inside the 1e-5 per-cell tolerance).  Unweighted
 // NGP stays bit-exact (sums of 1.0f).
+#include <stdlib.h>
+
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -56,6 +58,9 @@ struct TileGeom {
     // x_planes - 1; a particle belongs here iff its first stencil plane is one of the first x_own planes
     // (the other x_planes - x_own planes are the upward ghost planes its stencil may reach).
     int x_origin, x_own, x_planes;
+    // bucket cursors live one per 2^fill_shift words: atomics of neighbouring tiles must not share a 32-byte
+    // L2 sector (same-sector atomic requests serialise in the L2 slice)
+    int fill_shift;
 };
 
 constexpr unsigned NO_TILE = 0xffffffffu;
@@ -196,7 +201,7 @@ __device__ __forceinline__ void scatter_one(const float d[3], float wp, const Ti
         return;
     }
     const unsigned s0 = __ldg(starts + t), s1 = __ldg(starts + t + 1);
-    const unsigned slot = atomicAdd(fill + t, 1u);
+    const unsigned slot = atomicAdd(fill + ((size_t)t << g.fill_shift), 1u);
     if (slot < s1 - s0) {
         bucket[s0 + slot] = make_float4(d[0], d[1], d[2], wp);
     } else {
@@ -282,7 +287,7 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
 
     const unsigned tile = blockIdx.x;
     const unsigned begin = starts[tile];
-    const unsigned end = begin + min(fill[tile], starts[tile + 1] - begin);   // overflow went the direct way
+    const unsigned end = begin + min(fill[(size_t)tile << g.fill_shift], starts[tile + 1] - begin);   // overflow went the direct way
     if (begin == end) return;                                 // empty tile: nothing to add
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -376,13 +381,17 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
             for (int l = 0; l < S; l++) {
                 const int x = X - l;                           // source plane
                 if (x < 0 || x >= TX) continue;
-                // the particles of source plane x are contiguous and ordered by (y,z); a batch of 32
-                // may span several rows -- lanes of one batch always write distinct cells of plane X
+                // the particles of source plane x are contiguous and ordered by (y,z).  Lane i takes the slots
+                // q0 + i*nb + j: lanes of one batch are nb sorted slots apart, so two of them share a cell only
+                // when a run of equal cells is longer than nb -- at ~1 particle per cell almost never, and every
+                // lane then owns a distinct cell of plane X (plain read-modify-writes, no shuffles).  nb is made
+                // odd so that the 16-byte reads of `sorted` at stride nb stay free of bank conflicts.
                 const int q0 = (int)off16(cnt, x * TY * TZ);
                 const int q1 = (int)off16(cnt, (x + 1) * TY * TZ);
+                const int nb = q1 > q0 ? (((q1 - q0 + 31) >> 5) | 1) : 0;
 #pragma unroll 1
-                for (int b0 = q0; b0 < q1; b0 += 32) {
-                    const int p = b0 + lane;
+                for (int j = 0; j < nb; j++) {
+                    const int p = q0 + lane * nb + j;
                     const bool valid = p < q1;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     int yz = 0x4000 + lane;                    // invalid lanes: singleton segments
@@ -394,13 +403,20 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
                     stencil_weights<MAS>(v.z, wz);
                     float wxl = wx[0];
 #pragma unroll
-                    for (int j = 1; j < S; j++) wxl = (l == j) ? wx[j] : wxl;
+                    for (int jj = 1; jj < S; jj++) wxl = (l == jj) ? wx[jj] : wxl;
                     const float wxw = wxl * v.w;
 
-                    // particles of equal cell are contiguous (sorted): `peers` = my run
-                    const unsigned peers = __match_any_sync(0xffffffffu, yz);
-                    const bool head = valid && (lane == __ffs(peers) - 1);
-                    const int run_max = __reduce_max_sync(0xffffffffu, __popc(peers));
+                    // sorted slots are monotone in the lane: equal cells are adjacent lanes
+                    const int yz_up = __shfl_down_sync(0xffffffffu, yz, 1);
+                    const bool dup = __any_sync(0xffffffffu, lane < 31 && yz_up == yz);
+                    unsigned peers = 1u << lane;
+                    bool head = valid;
+                    int run_max = 1;
+                    if (dup) {
+                        peers = __match_any_sync(0xffffffffu, yz);
+                        head = valid && (lane == __ffs(peers) - 1);
+                        run_max = __reduce_max_sync(0xffffffffu, __popc(peers));
+                    }
                     float *cellp = plane + y * AZ + lz;
 
                     if (run_max == 1) {
@@ -439,22 +455,36 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
         __syncthreads();
     }
 
-    // ---- c. flush tile + halo into the grid ---------------------------------------------------------------
+    // ---- c. flush tile + halo into the grid: a warp per (x,y) row, lanes along z (coalesced reductions) -----
     const int dims = g.dims;
-    for (int i = tid; i < SM::ACC; i += TNT) {
-        const float val = acc[i];
-        if (val != 0.0f) {
-            const int az = i % AZ, ay = (i / AZ) % AY, ax = i / (AZ * AY);
-            int gx = ox + ax, gy = oy + ay, gz = oz + az;     // gx: plane inside the destination buffer
-            if (gx >= g.x_planes) gx -= g.x_planes;           // only when the buffer is the whole periodic grid
-            if (gy >= dims) gy -= dims;
+    for (int r = warp; r < AX * AY; r += TNT / 32) {
+        const int ax = r / AY, ay = r - ax * AY;
+        int gx = ox + ax, gy = oy + ay;                        // gx: plane inside the destination buffer
+        if (gx >= g.x_planes) gx -= g.x_planes;                // only when the buffer is the whole periodic grid
+        if (gy >= dims) gy -= dims;
+        float *row = number + ((int64_t)gx * dims + gy) * dims;
+        for (int az = lane; az < AZ; az += 32) {
+            const float val = acc[r * AZ + az];
+            int gz = oz + az;
             if (gz >= dims) gz -= dims;
-            atomicAdd(number + ((int64_t)gx * dims + gy) * dims + gz, val);
+            if (val != 0.0f) atomicAdd(row + gz, val);
         }
     }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
+constexpr int FILL_SHIFT_MAX = 5;
+static int fill_shift_for(unsigned ntiles) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char *e = getenv("PYL_FILL_SHIFT");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced >= 0 && forced <= FILL_SHIFT_MAX) return forced;
+    (void)ntiles;
+    return 3;
+}
+
 static TileGeom make_geom(int dims, float BoxSize, int x_origin = 0, int x_own = -1, int x_planes = -1) {
     TileGeom g;
     g.dims = dims;
@@ -466,6 +496,7 @@ static TileGeom make_geom(int dims, float BoxSize, int x_origin = 0, int x_own =
     g.ntz = (dims + TZ - 1) / TZ;
     g.ntiles = (unsigned)g.ntx * g.nty * g.ntz;
     g.inv_cell_size = (float)dims / BoxSize;      // float32 division, MAS_library.pyx:135
+    g.fill_shift = fill_shift_for(g.ntiles);
     return g;
 }
 
@@ -511,7 +542,7 @@ static TiledWorkspace carve(void *ws, int64_t particles, unsigned ntiles) {
     w.starts = reinterpret_cast<unsigned *>(base + off);
     off += align_up(((size_t)ntiles + 1) * 4, 256);
     w.fill = reinterpret_cast<unsigned *>(base + off);
-    off += align_up((size_t)ntiles * 4, 256);
+    off += align_up(((size_t)ntiles << FILL_SHIFT_MAX) * 4, 256);
     w.scan_tmp = base + off;
     w.scan_bytes = scan_temp_bytes(ntiles + 1);
     off += align_up(w.scan_bytes, 256);
@@ -544,7 +575,7 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
     // starts[] and fill[] are adjacent: one memset clears both
     PYL_CUDA_CHECK(cudaMemsetAsync(w.starts, 0,
                                    reinterpret_cast<char *>(w.fill) - reinterpret_cast<char *>(w.starts) +
-                                       (size_t)g.ntiles * 4, stream));
+                                       ((size_t)g.ntiles << g.fill_shift) * 4, stream));
     tile_count_kernel<MAS><<<(int)cblocks, 256, 0, stream>>>(pos, particles, g, w.starts, vec_ok);
     PYL_LAUNCH_CHECK();
     tile_caps_kernel<<<(g.ntiles + 1 + 255) / 256, 256, 0, stream>>>(w.starts, g.ntiles);

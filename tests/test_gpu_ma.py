@@ -12,7 +12,7 @@ from conftest import BOX, make_particles, rel_err
 
 pytestmark = pytest.mark.gpu
 MAS = ("NGP", "CIC", "TSC", "PCS")
-MODES = ("atomic", "tiled")
+MODES = ("atomic", "tiled", "deterministic")
 TOL = 1e-5
 
 
@@ -91,6 +91,36 @@ def test_ma_extreme_clustering_accumulation_noise(env, oracle, mode):
         bound = TOL * np.maximum(1.0, np.sqrt(n_cell / 64.0)) * np.maximum(np.abs(ref), ref.mean())
         assert np.all(np.abs(got - ref) <= bound), mas
         assert abs(np.sum(got, dtype=np.float64) / len(pos) - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("mas", MAS)
+def test_ma_deterministic_mode_is_bit_reproducible(env, oracle, mas):
+    """north_star: "a deterministic sorted-segment mode also offered".  Same input twice -> identical bits
+    (3D and 2D, weighted, strongly clustered so that many particles share a cell), and the result accumulates
+    onto an existing grid like every other mode."""
+    torch, MASL, _ = env
+    N = 96
+    pos, W = make_particles(77, 700001, True, sigma=0.01)
+    pos_d, W_d = torch.from_numpy(pos).cuda(), torch.from_numpy(W).cuda()
+    runs = []
+    for _ in range(3):
+        g = torch.full((N, N, N), 0.5, dtype=torch.float32, device="cuda")
+        MASL.MA(pos_d, g, BOX, mas, W_d, mode="deterministic")
+        runs.append(g.cpu().numpy())
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    # parity on a moderately clustered set (the extreme set above is summation-order noise limited, see
+    # test_ma_extreme_clustering_accumulation_noise)
+    pos_m, W_m = make_particles(78, 400000, True)
+    ref = np.full((N, N, N), 0.5, np.float32)
+    oracle.MA(pos_m, ref, BOX, mas, W_m)
+    got = np.full((N, N, N), 0.5, np.float32)
+    MASL.MA(pos_m, got, BOX, mas, W_m, mode="deterministic")
+    assert cell_err(got, ref) < TOL
+    p2 = np.ascontiguousarray(pos[:, :2])
+    a, b = np.zeros((N, N), np.float32), np.zeros((N, N), np.float32)
+    MASL.MA(p2, a, BOX, mas, W, mode="deterministic")
+    MASL.MA(p2, b, BOX, mas, W, mode="deterministic")
+    assert np.array_equal(a, b)
 
 
 def test_ma_accumulates_like_reference(env, ma_golden):
