@@ -323,6 +323,28 @@ def run_ours(args):
                     ma_rates[mas + tag + ("" if mode == "auto" else "[atomic]")] = npart / (a.elapsed_time(b) / reps * 1e-3)
         del W
 
+    if world > 1:
+        # stage breakdown of the distributed step (device time on this rank, max over ranks)
+        def ev():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+        reps = 3
+        acc = {k: 0.0 for k in ("zero", "deposit+halo", "overdensity", "fft(yz,transpose,x)", "bin+allreduce+finalise")}
+        for _ in range(reps):
+            e0 = ev(); slab.zero_()
+            e1 = ev(); ctx.MA(pos, slab, MAS, routed=True)
+            e2 = ev(); ctx.overdensity_(slab)
+            e3 = ev(); dk = ctx.fft(slab)
+            e4 = ev(); raw = ctx._raw([dk], [PKL.MAS_function(MAS)], AXIS, True); PKL._finalize(raw, BOX, grid_n)
+            e5 = ev(); torch.cuda.synchronize()
+            for k, (a, b) in zip(acc, ((e0, e1), (e1, e2), (e2, e3), (e3, e4), (e4, e5))):
+                acc[k] += a.elapsed_time(b) / reps
+            del dk
+        t = torch.tensor(list(acc.values()), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stages = {k: round(float(v), 4) for k, v in zip(acc, t.tolist())}
+
     # ---- timed region 2: end to end from pinned host memory --------------------------------------
     pos_host = torch.empty(pos.shape, dtype=torch.float32, pin_memory=True)
     pos_host.copy_(pos)

@@ -58,7 +58,7 @@ def main():
         a = agg[key]
         a["samples"] += float(r[col["# Samples"]] or 0)
         a["inst"] += float(r[col["Instructions Executed"]] or 0)
-        a["excess"] += float(r[col["L1 Wavefronts Shared Excessive"]] or 0)
+        a["excess"] += float(r[col["L1 Wavefronts Shared Excessive"]] or 0) if "L1 Wavefronts Shared Excessive" in col else 0.0
         for s in stalls:
             a[s] += float(r[col[s]] or 0)
     ts = sum(a["samples"] for a in agg.values()) or 1

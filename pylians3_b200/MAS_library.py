@@ -48,6 +48,60 @@ def _deposit_device(mas_id, pos_d, number_d, W_d, dims, axes, BoxSize, mode):
     L.check(st, "pyl_deposit")
 
 
+# Host-resident particles are streamed: chunk k+1 crosses PCIe (copy stream, double-buffered staging)
+# while chunk k is deposited.  Each chunk is a complete deposit into the same grid (MA accumulates,
+# MAS_library.pyx:57-112 / MAS_gadget.py:63-75), so nothing has to wait for the whole array.
+STREAM_CHUNK = 16 * 1024 * 1024          # particles per chunk (192 MB of positions: ~3.5 ms of PCIe gen5)
+_copy_streams = {}
+
+
+def _host_f32(x, name):
+    """numpy array / CPU tensor -> contiguous float32 CPU tensor sharing memory when possible."""
+    if isinstance(x, torch.Tensor):
+        if x.dtype != torch.float32:
+            raise ValueError("%s must be float32, got %s" % (name, x.dtype))
+        return x.contiguous()
+    a = np.asarray(x)
+    if a.dtype != np.float32:
+        raise ValueError("%s must be float32 (Buffer dtype mismatch, expected 'float32_t' but got '%s')"
+                         % (name, a.dtype))
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def stream_host_chunks(pos_h, W_h, dev, chunk, consume):
+    """Feed host-resident particles to `consume(pos_chunk_d, W_chunk_d)` chunk by chunk: the copy of chunk
+    k+1 (copy stream, double-buffered staging in HBM) overlaps whatever `consume` enqueued for chunk k."""
+    n, axes = pos_h.shape
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    copy_stream = _copy_streams.get(key)
+    if copy_stream is None:
+        copy_stream = _copy_streams[key] = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    stage = D.workspace(2 * chunk * (axes + 1) * 4, dev, "ma_stage").view(torch.float32)
+    pbuf = [stage[j * chunk * axes:(j + 1) * chunk * axes].view(chunk, axes) for j in range(2)]
+    wbuf = [stage[2 * chunk * axes + j * chunk:2 * chunk * axes + (j + 1) * chunk] for j in range(2)]
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    copy_stream.wait_stream(main)                 # staging buffers may still be read by earlier work
+    for k, a in enumerate(range(0, n, chunk)):
+        b, j = min(a + chunk, n), k & 1
+        with torch.cuda.stream(copy_stream):
+            if k >= 2:
+                copy_stream.wait_event(done[j])   # the deposit that last read this buffer has finished
+            pbuf[j][:b - a].copy_(pos_h[a:b], non_blocking=True)
+            if W_h is not None:
+                wbuf[j][:b - a].copy_(W_h[a:b], non_blocking=True)
+            copied[j].record(copy_stream)
+        main.wait_event(copied[j])
+        consume(pbuf[j][:b - a], None if W_h is None else wbuf[j][:b - a])
+        done[j].record(main)
+
+
+def _deposit_streamed(mas_id, pos_h, number_d, W_h, dims, axes, BoxSize, mode, chunk):
+    stream_host_chunks(pos_h, W_h, number_d.device, chunk,
+                       lambda p, w: _deposit_device(mas_id, p, number_d, w, dims, axes, BoxSize, mode))
+
+
 def MA(pos, number, BoxSize, MAS="CIC", W=None, verbose=False, renormalize_2D=True, *, mode="auto"):
     """Mass assignment: number += deposit(pos[, W]) with NGP/CIC/TSC/PCS, 2D or 3D.
 
@@ -71,12 +125,20 @@ def MA(pos, number, BoxSize, MAS="CIC", W=None, verbose=False, renormalize_2D=Tr
     if any(s != dims for s in number.shape):
         raise ValueError("number must be a (dims,)*%d grid, got %s" % (coord, tuple(number.shape)))
     dev = D.pick_device(number, pos, W)
-    pos_d, _ = D.to_device_f32(pos, dev, "pos")
-    W_d = None
-    if W is not None:
-        W_d, _ = D.to_device_f32(W, dev, "W")
-        if W_d.ndim != 1 or W_d.shape[0] != pos_d.shape[0]:
+    streamed = (not D.is_cuda_tensor(pos)) and (W is None or not D.is_cuda_tensor(W)) and \
+        pos.shape[0] >= 2 * STREAM_CHUNK
+    pos_d = W_d = None
+    if streamed:
+        pos_h = _host_f32(pos, "pos")
+        W_h = None if W is None else _host_f32(W, "W")
+        if W_h is not None and (W_h.ndim != 1 or W_h.shape[0] != pos_h.shape[0]):
             raise ValueError("W must have one weight per particle")
+    else:
+        pos_d, _ = D.to_device_f32(pos, dev, "pos")
+        if W is not None:
+            W_d, _ = D.to_device_f32(W, dev, "W")
+            if W_d.ndim != 1 or W_d.shape[0] != pos_d.shape[0]:
+                raise ValueError("W must have one weight per particle")
 
     inplace = D.is_cuda_tensor(number) and number.is_contiguous()
     if inplace:
@@ -86,7 +148,12 @@ def MA(pos, number, BoxSize, MAS="CIC", W=None, verbose=False, renormalize_2D=Tr
     else:
         number_d, _ = D.to_device_f32(number, dev, "number")   # staged copy (host or strided)
 
-    _deposit_device(L.MAS_IDS[MAS], pos_d, number_d, W_d, dims, coord, BoxSize, L.MODE_IDS[mode])
+    if streamed:
+        with torch.cuda.device(dev):
+            _deposit_streamed(L.MAS_IDS[MAS], pos_h, number_d, W_h, dims, coord, BoxSize, L.MODE_IDS[mode],
+                              STREAM_CHUNK)
+    else:
+        _deposit_device(L.MAS_IDS[MAS], pos_d, number_d, W_d, dims, coord, BoxSize, L.MODE_IDS[mode])
     if coord == 2 and renormalize_2D and MAS != "NGP":
         # number2 /= 2.0|3.0|4.0 -- the WHOLE accumulated plane (MAS_library.pyx:90-107)
         with torch.cuda.device(dev):

@@ -203,11 +203,22 @@ def bin_fields(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=No
 
 
 # ---- host finalisation (vectorised restatement of :384-418 / :735-791) --------------------
+_kpk_cache = {}
+
+
 def _kpar_kper(kmax_par, kmax_per, kF):
-    i2 = np.arange((kmax_par + 1) * (kmax_per + 1))
-    k_par = i2 % (kmax_par + 1)
-    k_per = i2 // (kmax_par + 1)
-    return 0.5 * (k_par + k_par + 1) * kF, 0.5 * (k_per + k_per + 1) * kF
+    """Bin-centre kpar/kper of the 2D array (Pk_library.pyx:394-399); the index arithmetic is cached per
+    geometry, callers get fresh copies."""
+    key = (kmax_par, kmax_per, kF)
+    hit = _kpk_cache.get(key)
+    if hit is None:
+        k_par = np.tile(np.arange(kmax_par + 1), kmax_per + 1)          # i2 % (kmax_par+1)
+        k_per = np.repeat(np.arange(kmax_per + 1), kmax_par + 1)        # i2 // (kmax_par+1)
+        hit = (0.5 * (k_par + k_par + 1) * kF, 0.5 * (k_per + k_per + 1) * kF)
+        if len(_kpk_cache) > 8:
+            _kpk_cache.clear()
+        _kpk_cache[key] = hit
+    return hit[0].copy(), hit[1].copy()
 
 
 def _finalize(raw, BoxSize, dims):

@@ -11,8 +11,8 @@
 //                    cell coordinate dist = fl32(pos*inv) per axis, stencil base cell -> tile id.
 //   2. tile_caps + exclusive scan (cub::DeviceScan): per-tile bucket capacity = 1.125 x estimate +
 //                    4 sigma of the sampling noise + 32, and the bucket start offsets.
-//   3. tile_scatter  ONE full pass over pos: slot = atomicAdd(fill[tile]); writes (dist.xyz, W) as one
-//                    aligned float4 into the tile's bucket.  A particle that finds its bucket full (rare:
+//   3. tile_scatter  ONE full pass over pos: one 64-bit atomicAdd on the tile's packed cursor returns the slot
+//                    and the bucket end; writes (dist.xyz, W) as one aligned float4 into the tile's bucket.  A particle that finds its bucket full (rare:
 //                    beyond 4 sigma) is deposited on the spot with red.global -- correctness never
 //                    depends on the estimate.
 //   4. tile_deposit  one CTA per tile, looping over the bucket in chunks of 1024 particles:
@@ -31,8 +31,6 @@
 // operation-identical to the reference, TSC/PCS evaluate the same polynomials in float32 (<= 3 ulp from
 // the reference's float64-then-rounded values, far inside the 1e-5 per-cell tolerance).  Unweighted
 // NGP stays bit-exact (sums of 1.0f).
-#include <stdlib.h>
-
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -58,9 +56,6 @@ struct TileGeom {
     // x_planes - 1; a particle belongs here iff its first stencil plane is one of the first x_own planes
     // (the other x_planes - x_own planes are the upward ghost planes its stencil may reach).
     int x_origin, x_own, x_planes;
-    // bucket cursors live one per 2^fill_shift words: atomics of neighbouring tiles must not share a 32-byte
-    // L2 sector (same-sector atomic requests serialise in the L2 slice)
-    int fill_shift;
 };
 
 constexpr unsigned NO_TILE = 0xffffffffu;
@@ -187,37 +182,66 @@ __global__ void tile_caps_kernel(unsigned *__restrict__ counts, unsigned ntiles)
     else if (i == ntiles) counts[i] = 0u;
 }
 
+// cursor[t] = (bucket end << 32) | next free slot: ONE 64-bit atomicAdd in the scatter kernel returns both the
+// slot and the capacity limit (measured: the two extra loads of `starts` per particle were 25% of the scatter
+// kernel's L2 requests, and the kernel is bound by the L2 request rate)
+__global__ void tile_cursor_kernel(const unsigned *__restrict__ starts, unsigned long long *__restrict__ cursor,
+                                   unsigned ntiles) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ntiles) cursor[i] = ((unsigned long long)starts[i + 1] << 32) | starts[i];
+}
+
 // ---- 3. scatter into buckets (single full pass) --------------------------------------------------------
+// bucket full (capacity came from a sample): deposit the particle directly.  Out of line: it is rare, and
+// inlined four times it made every atomicAdd below wait for the previous particle's branch.
 template <int MAS, bool WEIGHTED>
-__device__ __forceinline__ void scatter_one(const float d[3], float wp, const TileGeom &g,
-                                            const unsigned *__restrict__ starts, unsigned *__restrict__ fill,
-                                            float4 *__restrict__ bucket, float *__restrict__ number,
-                                            unsigned long long &dropped) {
-    int local[3];
-    float frac[3];
-    const unsigned t = tile_and_local<MAS>(d, g, local, frac);
-    if (t == NO_TILE) {                 // not routed to this slab: nothing of it is deposited here
-        dropped += StencilWidth<MAS>::value * StencilWidth<MAS>::value * StencilWidth<MAS>::value;
-        return;
+__device__ __noinline__ void scatter_overflow(float d0, float d1, float d2, float wp, TileGeom g,
+                                              float *__restrict__ number, unsigned long long *dropped) {
+    const float d[3] = {d0, d1, d2};
+    unsigned long long dr = 0;
+    if (g.x_planes == g.dims)
+        deposit_dist<MAS, 3, WEIGHTED, false>(d, wp, number, g.dims, SlabWindow{0, g.dims, 0.0f}, dr);
+    else
+        deposit_dist<MAS, 3, WEIGHTED, true>(d, wp, number, g.dims, SlabWindow{g.x_origin, g.x_planes, 0.0f}, dr);
+    *dropped += dr;
+}
+
+// NP particles at once: all bucket lookups, then all cursor atomics, then all stores -- the kernel is bound by
+// the latency of the atomic round trips, so they must be in flight together, not chained through branches.
+template <int MAS, bool WEIGHTED, int NP>
+__device__ __forceinline__ void scatter_many(const float (&d)[NP][3], const float (&wp)[NP], const bool (&live)[NP],
+                                             const TileGeom &g, unsigned long long *__restrict__ cursor,
+                                             float4 *__restrict__ bucket,
+                                             float *__restrict__ number, unsigned long long &dropped) {
+    constexpr int S = StencilWidth<MAS>::value;
+    unsigned t[NP];
+    unsigned long long cur[NP];
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        int local[3];
+        float frac[3];
+        t[q] = live[q] ? tile_and_local<MAS>(d[q], g, local, frac) : NO_TILE;
     }
-    const unsigned s0 = __ldg(starts + t), s1 = __ldg(starts + t + 1);
-    const unsigned slot = atomicAdd(fill + ((size_t)t << g.fill_shift), 1u);
-    if (slot < s1 - s0) {
-        bucket[s0 + slot] = make_float4(d[0], d[1], d[2], wp);
-    } else {
-        // bucket full (capacity came from a sample): deposit this particle directly
-        if (g.x_planes == g.dims)
-            deposit_dist<MAS, 3, WEIGHTED, false>(d, wp, number, g.dims, SlabWindow{0, g.dims, 0.0f}, dropped);
-        else
-            deposit_dist<MAS, 3, WEIGHTED, true>(d, wp, number, g.dims, SlabWindow{g.x_origin, g.x_planes, 0.0f}, dropped);
+#pragma unroll
+    for (int q = 0; q < NP; q++) cur[q] = (t[q] != NO_TILE) ? atomicAdd(cursor + t[q], 1ull) : 0ull;
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        const unsigned slot = (unsigned)cur[q], end = (unsigned)(cur[q] >> 32);
+        if (t[q] != NO_TILE && slot < end) bucket[slot] = make_float4(d[q][0], d[q][1], d[q][2], wp[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+        if (!live[q]) continue;
+        if (t[q] == NO_TILE) dropped += S * S * S;      // not routed to this slab: nothing of it is deposited here
+        else if ((unsigned)cur[q] >= (unsigned)(cur[q] >> 32))
+            scatter_overflow<MAS, WEIGHTED>(d[q][0], d[q][1], d[q][2], wp[q], g, number, &dropped);
     }
 }
 
 template <int MAS, bool WEIGHTED>
 __global__ void __launch_bounds__(256) tile_scatter_kernel(const float *__restrict__ pos,
                                                            const float *__restrict__ W, int64_t particles,
-                                                           TileGeom g, const unsigned *__restrict__ starts,
-                                                           unsigned *__restrict__ fill,
+                                                           TileGeom g, unsigned long long *__restrict__ cursor,
                                                            float4 *__restrict__ bucket,
                                                            float *__restrict__ number,
                                                            unsigned long long *__restrict__ dropped_out,
@@ -239,19 +263,21 @@ __global__ void __launch_bounds__(256) tile_scatter_kernel(const float *__restri
             const float4 v = __ldg(reinterpret_cast<const float4 *>(W + grp * 4));
             wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
         }
+        float d[4][3];
+        const bool live[4] = {true, true, true, true};
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            float d[3];
+        for (int q = 0; q < 4; q++)
 #pragma unroll
-            for (int a = 0; a < 3; a++) d[a] = cell_coordinate(p[3 * q + a], g.inv_cell_size);
-            scatter_one<MAS, WEIGHTED>(d, wv[q], g, starts, fill, bucket, number, dropped);
-        }
+            for (int a = 0; a < 3; a++) d[q][a] = cell_coordinate(p[3 * q + a], g.inv_cell_size);
+        scatter_many<MAS, WEIGHTED, 4>(d, wv, live, g, cursor, bucket, number, dropped);
     }
     for (int64_t i = (groups << 2) + tid; i < particles; i += stride) {
-        float d[3];
+        float d[1][3];
 #pragma unroll
-        for (int a = 0; a < 3; a++) d[a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
-        scatter_one<MAS, WEIGHTED>(d, WEIGHTED ? __ldg(W + i) : 1.0f, g, starts, fill, bucket, number, dropped);
+        for (int a = 0; a < 3; a++) d[0][a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
+        const float wv[1] = {WEIGHTED ? __ldg(W + i) : 1.0f};
+        const bool live[1] = {true};
+        scatter_many<MAS, WEIGHTED, 1>(d, wv, live, g, cursor, bucket, number, dropped);
     }
     if (dropped_out != nullptr && dropped != 0) atomicAdd(dropped_out, dropped);
 }
@@ -274,8 +300,8 @@ __device__ __forceinline__ unsigned off16(const unsigned *cnt, int key) {
 
 template <int MAS>
 __global__ void __launch_bounds__(TNT, 4)
-tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restrict__ starts,
-                    const unsigned *__restrict__ fill, float *__restrict__ number, TileGeom g) {
+tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned long long *__restrict__ cursor,
+                    float *__restrict__ number, TileGeom g) {
     using SM = TileSmem<MAS>;
     constexpr int S = SM::S, AY = SM::AY, AZ = SM::AZ, AX = SM::AX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -286,8 +312,11 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
     unsigned *warp_part = reinterpret_cast<unsigned *>(sorted_yz + CHUNK);        // 8 words
 
     const unsigned tile = blockIdx.x;
-    const unsigned begin = starts[tile];
-    const unsigned end = begin + min(fill[(size_t)tile << g.fill_shift], starts[tile + 1] - begin);   // overflow went the direct way
+    // cursor = (bucket end << 32) | (bucket begin + particles that asked for a slot); the next tile's bucket
+    // begins where this one ends, so this tile's begin is the previous tile's end
+    const unsigned long long cur = cursor[tile];
+    const unsigned begin = tile == 0 ? 0u : (unsigned)(cursor[tile - 1] >> 32);
+    const unsigned end = min((unsigned)cur, (unsigned)(cur >> 32));            // overflow went the direct way
     if (begin == end) return;                                 // empty tile: nothing to add
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -473,18 +502,6 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
-constexpr int FILL_SHIFT_MAX = 5;
-static int fill_shift_for(unsigned ntiles) {
-    static int forced = -2;
-    if (forced == -2) {
-        const char *e = getenv("PYL_FILL_SHIFT");
-        forced = e ? atoi(e) : -1;
-    }
-    if (forced >= 0 && forced <= FILL_SHIFT_MAX) return forced;
-    (void)ntiles;
-    return 3;
-}
-
 static TileGeom make_geom(int dims, float BoxSize, int x_origin = 0, int x_own = -1, int x_planes = -1) {
     TileGeom g;
     g.dims = dims;
@@ -496,7 +513,6 @@ static TileGeom make_geom(int dims, float BoxSize, int x_origin = 0, int x_own =
     g.ntz = (dims + TZ - 1) / TZ;
     g.ntiles = (unsigned)g.ntx * g.nty * g.ntz;
     g.inv_cell_size = (float)dims / BoxSize;      // float32 division, MAS_library.pyx:135
-    g.fill_shift = fill_shift_for(g.ntiles);
     return g;
 }
 
@@ -520,14 +536,15 @@ bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes, int
     if (axes != 3 || dims < 64) return false;                       // halo wrap assumes dims >> stencil
     const TileGeom g = make_geom(dims, 1.0f, 0, x_own, x_own);
     if ((int64_t)g.ntiles > ((int64_t)1 << 30)) return false;
-    if (bucket_slots_bound(particles, g.ntiles) >= ((size_t)1 << 32)) return false;   // 32-bit offsets
+    // 32-bit slots; the cursor's low word may run past its bucket by the number of overflowing particles
+    if (bucket_slots_bound(particles, g.ntiles) + (size_t)particles >= ((size_t)1 << 32)) return false;
     return particles >= (int64_t)g.ntiles * 64;                     // sparse inputs: per-tile overhead loses
 }
 
 struct TiledWorkspace {
     float4 *bucket;
     unsigned *starts;   // ntiles + 1 : sampled counts -> capacities -> exclusive scan
-    unsigned *fill;     // ntiles     : bucket cursors
+    unsigned long long *cursor;   // ntiles : (bucket end << 32) | next free slot
     void *scan_tmp;
     size_t scan_bytes;
     size_t total;
@@ -541,8 +558,8 @@ static TiledWorkspace carve(void *ws, int64_t particles, unsigned ntiles) {
     off += align_up(bucket_slots_bound(particles, ntiles) * 16, 256);
     w.starts = reinterpret_cast<unsigned *>(base + off);
     off += align_up(((size_t)ntiles + 1) * 4, 256);
-    w.fill = reinterpret_cast<unsigned *>(base + off);
-    off += align_up(((size_t)ntiles << FILL_SHIFT_MAX) * 4, 256);
+    w.cursor = reinterpret_cast<unsigned long long *>(base + off);
+    off += align_up((size_t)ntiles * 8, 256);
     w.scan_tmp = base + off;
     w.scan_bytes = scan_temp_bytes(ntiles + 1);
     off += align_up(w.scan_bytes, 256);
@@ -572,22 +589,21 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
     int64_t cblocks = (blocks + SAMPLE - 1) / SAMPLE;
     if (cblocks < 1) cblocks = 1;
 
-    // starts[] and fill[] are adjacent: one memset clears both
-    PYL_CUDA_CHECK(cudaMemsetAsync(w.starts, 0,
-                                   reinterpret_cast<char *>(w.fill) - reinterpret_cast<char *>(w.starts) +
-                                       ((size_t)g.ntiles << g.fill_shift) * 4, stream));
+    PYL_CUDA_CHECK(cudaMemsetAsync(w.starts, 0, ((size_t)g.ntiles + 1) * 4, stream));
     tile_count_kernel<MAS><<<(int)cblocks, 256, 0, stream>>>(pos, particles, g, w.starts, vec_ok);
     PYL_LAUNCH_CHECK();
     tile_caps_kernel<<<(g.ntiles + 1 + 255) / 256, 256, 0, stream>>>(w.starts, g.ntiles);
     PYL_LAUNCH_CHECK();
     PYL_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.scan_tmp, const_cast<size_t &>(w.scan_bytes), w.starts, w.starts,
                                                  (int)(g.ntiles + 1), stream));
+    tile_cursor_kernel<<<(g.ntiles + 255) / 256, 256, 0, stream>>>(w.starts, w.cursor, g.ntiles);
+    PYL_LAUNCH_CHECK();
     if (W)
-        tile_scatter_kernel<MAS, true><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, w.starts, w.fill,
-                                                                        w.bucket, number, dropped, vec_ok);
+        tile_scatter_kernel<MAS, true><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, w.cursor, w.bucket,
+                                                                        number, dropped, vec_ok);
     else
-        tile_scatter_kernel<MAS, false><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, w.starts, w.fill,
-                                                                         w.bucket, number, dropped, vec_ok);
+        tile_scatter_kernel<MAS, false><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, w.cursor, w.bucket,
+                                                                         number, dropped, vec_ok);
     PYL_LAUNCH_CHECK();
 
     static bool attr_done[4] = {false, false, false, false};
@@ -596,7 +612,7 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
                                             (int)TileSmem<MAS>::bytes));
         attr_done[MAS] = true;
     }
-    tile_deposit_kernel<MAS><<<g.ntiles, TNT, TileSmem<MAS>::bytes, stream>>>(w.bucket, w.starts, w.fill, number, g);
+    tile_deposit_kernel<MAS><<<g.ntiles, TNT, TileSmem<MAS>::bytes, stream>>>(w.bucket, w.cursor, number, g);
     PYL_LAUNCH_CHECK();
     return PYL_OK;
 }

@@ -27,6 +27,7 @@ import torch.distributed as dist
 
 from . import _device as D
 from . import _lib as L
+from . import MAS_library as MASL
 from . import Pk_library as PKL
 
 _S = {"NGP": 1, "CIC": 2, "TSC": 3, "PCS": 4}
@@ -175,15 +176,33 @@ class SlabContext:
         """slab (nx_local, dims, dims) += deposit of this rank's share; ghost planes go to the next rank."""
         if MAS not in _S:
             raise ValueError("option not valid!!!")
+        host = isinstance(pos, torch.Tensor) and not pos.is_cuda
         if not routed:
+            if host:
+                pos, W = pos.to(self.device), (None if W is None else W.to(self.device))
+                host = False
             pos, W = self.route(pos, MAS, W)
         ghosts = _S[MAS] - 1
         x0 = self.x_range[0]
+
+        def deposit(target):
+            if host and pos.shape[0] >= 2 * MASL.STREAM_CHUNK:
+                # routed particles still in (pinned) host memory: stream them, one slab deposit per chunk
+                MASL.stream_host_chunks(pos, W, self.device, MASL.STREAM_CHUNK,
+                                        lambda p, w: self.ops.deposit_slab(MAS, p, target, w, self.dims, self.BoxSize,
+                                                                           x0, self.nx, self.dropped))
+            elif host:
+                self.ops.deposit_slab(MAS, pos.to(self.device, non_blocking=True), target,
+                                      None if W is None else W.to(self.device, non_blocking=True), self.dims,
+                                      self.BoxSize, x0, self.nx, self.dropped)
+            else:
+                self.ops.deposit_slab(MAS, pos, target, W, self.dims, self.BoxSize, x0, self.nx, self.dropped)
+
         if ghosts == 0:
-            self.ops.deposit_slab(MAS, pos, slab, W, self.dims, self.BoxSize, x0, self.nx, self.dropped)
+            deposit(slab)
             return
         work = torch.zeros((self.nx + ghosts, self.dims, self.dims), dtype=torch.float32, device=self.device)
-        self.ops.deposit_slab(MAS, pos, work, W, self.dims, self.BoxSize, x0, self.nx, self.dropped)
+        deposit(work)
         halo_out = work[self.nx:]                        # planes x1 .. x1+ghosts-1 belong to the next rank
         if self.world == 1:
             halo_in = halo_out

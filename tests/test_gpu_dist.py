@@ -1,5 +1,5 @@
-"""GPU, 2 ranks over NCCL: the slab-decomposed path (pylians3_b200.dist with the real CUDA kernels)
-against the CPU oracle.  Skipped on boxes with a single GPU (the CPU/gloo twin is test_dist_cpu.py)."""
+"""GPU, 2/4/8 ranks over NCCL: the slab-decomposed path (pylians3_b200.dist with the real CUDA kernels)
+against the CPU oracle.  Cases needing more GPUs than the box has are skipped (the CPU/gloo twin is test_dist_cpu.py)."""
 import os
 import socket
 import sys
@@ -79,16 +79,16 @@ def _worker(rank, world, port, N, q):
         q.put((rank, "fail", traceback.format_exc()))
 
 
-@pytest.mark.parametrize("N", [64, 45])
-def test_two_gpu_slab_pipeline(oracle, N):
+@pytest.mark.parametrize("world,N", [(2, 64), (2, 45), (4, 64), (4, 45), (8, 64)])
+def test_multi_gpu_slab_pipeline(oracle, world, N):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, N, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, q)) for r in range(world)]
     for p in procs:
         p.start()
     out = [q.get(timeout=600) for _ in procs]

@@ -123,6 +123,34 @@ def test_ma_deterministic_mode_is_bit_reproducible(env, oracle, mas):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_ma_streams_host_particles_in_chunks(env, oracle, monkeypatch, pinned):
+    """Host-resident particles cross PCIe chunk by chunk while the previous chunk is deposited; the result is
+    the same accumulate as one call (odd chunk count, ragged last chunk, weights, 3D and 2D)."""
+    torch, MASL, _ = env
+    monkeypatch.setattr(MASL, "STREAM_CHUNK", 70001)
+    N = 64
+    pos, W = make_particles(11, 400003, True)
+    for mas in ("NGP", "PCS"):
+        for w in (None, W):
+            ref = np.full((N, N, N), 0.125, np.float32)
+            oracle.MA(pos, ref, BOX, mas, w)
+            got = torch.full((N, N, N), 0.125, dtype=torch.float32, device="cuda")
+            p_in = torch.from_numpy(pos).pin_memory() if pinned else pos
+            w_in = None if w is None else (torch.from_numpy(w).pin_memory() if pinned else w)
+            MASL.MA(p_in, got, BOX, mas, w_in)
+            got = got.cpu().numpy()
+            if mas == "NGP" and w is None:
+                assert np.array_equal(got, ref)
+            else:
+                assert cell_err(got, ref) < TOL
+    p2 = np.ascontiguousarray(pos[:, :2])
+    ref2, got2 = np.zeros((N, N), np.float32), np.zeros((N, N), np.float32)
+    oracle.MA(p2, ref2, BOX, "TSC", W)
+    MASL.MA(p2, got2, BOX, "TSC", W)
+    assert cell_err(got2, ref2) < TOL
+
+
 def test_ma_accumulates_like_reference(env, ma_golden):
     torch, MASL, _ = env
     pos, W = ma_golden["accum_pos"], ma_golden["accum_W"]
