@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Per-source-line hot spots of one kernel from an .ncu-rep (captured with --import-source on / -lineinfo).
 
-    python profiles/hotlines.py gpurun_out/prof.ncu-rep <kernel regex> <cubin> [min_pct]
+    python profiles/hotlines.py gpurun_out/prof.ncu-rep <kernel regex> <cubin> [min_pct] [mangled-name regex]
+
+The mangled-name regex selects ONE instantiation in the cubin (e.g. tile_deposit_kernelILi1E); without it the
+kernel regex is used, which is ambiguous for templates.
 
 ncu's CSV source page is per SASS instruction; the line table comes from `nvdisasm -g` on the cubin the
 report was taken from (cuobjdump -xelf all libpyl_b200.so).  Prints, per source line, the share of stall
@@ -42,7 +45,7 @@ def main():
     hdr = rows[h]
     col = {n: i for i, n in enumerate(hdr)}
     stalls = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
-    table = line_table(cubin, kre)
+    table = line_table(cubin, sys.argv[5] if len(sys.argv) > 5 else kre)
     base = None
     agg = collections.defaultdict(lambda: collections.Counter())
     for r in rows[h + 1:]:

@@ -206,78 +206,52 @@ __device__ __noinline__ void scatter_overflow(float d0, float d1, float d2, floa
     *dropped += dr;
 }
 
-// NP particles at once: all bucket lookups, then all cursor atomics, then all stores -- the kernel is bound by
-// the latency of the atomic round trips, so they must be in flight together, not chained through branches.
-template <int MAS, bool WEIGHTED, int NP>
-__device__ __forceinline__ void scatter_many(const float (&d)[NP][3], const float (&wp)[NP], const bool (&live)[NP],
-                                             const TileGeom &g, unsigned long long *__restrict__ cursor,
-                                             float4 *__restrict__ bucket,
-                                             float *__restrict__ number, unsigned long long &dropped) {
-    constexpr int S = StencilWidth<MAS>::value;
-    unsigned t[NP];
-    unsigned long long cur[NP];
-#pragma unroll
-    for (int q = 0; q < NP; q++) {
-        int local[3];
-        float frac[3];
-        t[q] = live[q] ? tile_and_local<MAS>(d[q], g, local, frac) : NO_TILE;
-    }
-#pragma unroll
-    for (int q = 0; q < NP; q++) cur[q] = (t[q] != NO_TILE) ? atomicAdd(cursor + t[q], 1ull) : 0ull;
-#pragma unroll
-    for (int q = 0; q < NP; q++) {
-        const unsigned slot = (unsigned)cur[q], end = (unsigned)(cur[q] >> 32);
-        if (t[q] != NO_TILE && slot < end) bucket[slot] = make_float4(d[q][0], d[q][1], d[q][2], wp[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < NP; q++) {
-        if (!live[q]) continue;
-        if (t[q] == NO_TILE) dropped += S * S * S;      // not routed to this slab: nothing of it is deposited here
-        else if ((unsigned)cur[q] >= (unsigned)(cur[q] >> 32))
-            scatter_overflow<MAS, WEIGHTED>(d[q][0], d[q][1], d[q][2], wp[q], g, number, &dropped);
-    }
-}
-
+// One particle per thread, scalar loads: measured on B200 (scratch/s1_bench.cu) this simplest form beats the
+// float4 / 4-particles-per-thread form (2.85 vs 3.25 ms at 512^3) -- the kernel is bound by the rate of
+// returning atomics (1.5 ms for 134 M of them) plus the scattered 16-byte stores, and more independent
+// threads keep more of both in flight.  A two-level shared-memory-staged partition was prototyped in the
+// same file and lost (3.2 ms).
+// Lanes of a warp that go to the same tile share ONE atomic (match_any + leader): snapshot-ordered inputs
+// (lattice order, Peano-Hilbert order) send whole warps to one tile, and same-address returning atomics
+// serialise in L2 (measured 9.7 ms instead of 2.8 ms on a Zel'dovich-displaced lattice without this).
 template <int MAS, bool WEIGHTED>
-__global__ void __launch_bounds__(256) tile_scatter_kernel(const float *__restrict__ pos,
+__global__ void __launch_bounds__(512) tile_scatter_kernel(const float *__restrict__ pos,
                                                            const float *__restrict__ W, int64_t particles,
                                                            TileGeom g, unsigned long long *__restrict__ cursor,
                                                            float4 *__restrict__ bucket,
                                                            float *__restrict__ number,
-                                                           unsigned long long *__restrict__ dropped_out,
-                                                           int vec_ok) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t groups = vec_ok ? (particles >> 2) : 0;
-    unsigned long long dropped = 0;
-    for (int64_t grp = tid; grp < groups; grp += stride) {
-        float p[12];
-        const float4 *src = reinterpret_cast<const float4 *>(pos + grp * 12);
+                                                           unsigned long long *__restrict__ dropped_out) {
+    constexpr int S = StencilWidth<MAS>::value;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < particles;
+    const int lane = threadIdx.x & 31;
+    float d[3] = {0.f, 0.f, 0.f};
+    float wp = 1.0f;
+    unsigned t = NO_TILE;
+    if (live) {
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
-            const float4 v = __ldg(src + q);
-            p[4 * q] = v.x; p[4 * q + 1] = v.y; p[4 * q + 2] = v.z; p[4 * q + 3] = v.w;
-        }
-        float wv[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-        if (WEIGHTED) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(W + grp * 4));
-            wv[0] = v.x; wv[1] = v.y; wv[2] = v.z; wv[3] = v.w;
-        }
-        float d[4][3];
-        const bool live[4] = {true, true, true, true};
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-#pragma unroll
-            for (int a = 0; a < 3; a++) d[q][a] = cell_coordinate(p[3 * q + a], g.inv_cell_size);
-        scatter_many<MAS, WEIGHTED, 4>(d, wv, live, g, cursor, bucket, number, dropped);
+        for (int a = 0; a < 3; a++) d[a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
+        if (WEIGHTED) wp = __ldg(W + i);
+        int local[3];
+        float frac[3];
+        t = tile_and_local<MAS>(d, g, local, frac);
     }
-    for (int64_t i = (groups << 2) + tid; i < particles; i += stride) {
-        float d[1][3];
-#pragma unroll
-        for (int a = 0; a < 3; a++) d[0][a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
-        const float wv[1] = {WEIGHTED ? __ldg(W + i) : 1.0f};
-        const bool live[1] = {true};
-        scatter_many<MAS, WEIGHTED, 1>(d, wv, live, g, cursor, bucket, number, dropped);
+    // match_any only when neighbouring lanes agree (ordered input); for scattered input it would cost ~8%
+    unsigned peers = 1u << lane;
+    if (__any_sync(0xffffffffu, __shfl_down_sync(0xffffffffu, t, 1) == t && lane < 31))
+        peers = __match_any_sync(0xffffffffu, t);
+    const int leader = __ffs(peers) - 1;
+    const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+    unsigned long long cur = 0ull;
+    if (lane == leader && t != NO_TILE) cur = atomicAdd(cursor + t, (unsigned long long)__popc(peers));
+    cur = __shfl_sync(0xffffffffu, cur, leader);
+    const unsigned slot = (unsigned)cur + rank, end = (unsigned)(cur >> 32);
+    unsigned long long dropped = 0;
+    if (t != NO_TILE) {
+        if (slot < end) bucket[slot] = make_float4(d[0], d[1], d[2], wp);
+        else scatter_overflow<MAS, WEIGHTED>(d[0], d[1], d[2], wp, g, number, &dropped);
+    } else if (live) {
+        dropped = S * S * S;            // not routed to this slab: nothing of it is deposited here
     }
     if (dropped_out != nullptr && dropped != 0) atomicAdd(dropped_out, dropped);
 }
@@ -325,21 +299,33 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned long long 
 
     for (int i = tid; i < SM::ACC; i += TNT) acc[i] = 0.0f;
 
+    // the next chunk's particles are fetched while the current chunk is accumulated (the exposed latency of
+    // this load was 18% of the kernel's stall samples)
+    float4 nxt[PER];
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+        const unsigned i = begin + tid + q * TNT;
+        nxt[q] = i < end ? __ldg(bucket + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
     for (unsigned c0 = begin; c0 < end; c0 += CHUNK) {
         const int n = (int)min((unsigned)CHUNK, end - c0);
         for (int i = tid; i < SM::CNT_WORDS; i += TNT) cnt[i] = 0u;
         __syncthreads();
 
         // ---- a. rank every particle within its cell ------------------------------------------------
+        // sort key: source plane, then the shared-memory BANK of the particle's first target cell, then y.
+        // Lanes of one accumulation batch sit nb sorted slots apart (below), i.e. in different banks most
+        // of the time: the read-modify-writes of a batch then need ~2 wavefronts instead of ~5.
         float4 part[PER];
-        int key[PER];
+        int key[PER], yzq[PER];
         unsigned rank[PER];
 #pragma unroll
         for (int q = 0; q < PER; q++) {
             const int i = tid + q * TNT;
             key[q] = -1;
             if (i < n) {
-                const float4 v = __ldg(bucket + c0 + i);
+                const float4 v = nxt[q];
                 const float d[3] = {v.x, v.y, v.z};
                 float fr[3];
                 int lc[3];
@@ -351,7 +337,9 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned long long 
                     if (a == 0) { wb -= g.x_origin; if (wb < 0) wb += g.dims; }
                     lc[a] = wb - org[a];
                 }
-                key[q] = (lc[0] * TY + lc[1]) * TZ + lc[2];
+                const int bank = (lc[1] * (S - 1) + lc[2]) & (TZ - 1);       // (y*AZ + z) mod 32, AZ = 32+S-1
+                key[q] = (lc[0] * TZ + bank) * TY + lc[1];
+                yzq[q] = lc[1] * TZ + lc[2];
                 part[q] = make_float4(fr[0], fr[1], fr[2], v.w);
                 const unsigned old = atomicAdd(cnt + (key[q] >> 1), (key[q] & 1) ? 0x10000u : 1u);
                 rank[q] = (key[q] & 1) ? (old >> 16) : (old & 0xffffu);
@@ -397,10 +385,18 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned long long 
             if (key[q] >= 0) {
                 const unsigned dst = off16(cnt, key[q]) + rank[q];
                 sorted[dst] = part[q];
-                sorted_yz[dst] = (unsigned short)(key[q] & (TY * TZ - 1));
+                sorted_yz[dst] = (unsigned short)yzq[q];
             }
         }
         __syncthreads();
+
+        if (c0 + CHUNK < end) {
+#pragma unroll
+            for (int q = 0; q < PER; q++) {
+                const unsigned i = c0 + CHUNK + tid + q * TNT;
+                nxt[q] = i < end ? __ldg(bucket + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
 
         // ---- b. stencil accumulation: warp `warp` owns target planes X = warp, warp+8 -------------------
         // (with TX = 8 and 8 warps every warp gets exactly S source-plane visits per chunk: balanced)
@@ -598,12 +594,13 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
                                                  (int)(g.ntiles + 1), stream));
     tile_cursor_kernel<<<(g.ntiles + 255) / 256, 256, 0, stream>>>(w.starts, w.cursor, g.ntiles);
     PYL_LAUNCH_CHECK();
+    const unsigned sblocks = (unsigned)((particles + 511) / 512);
     if (W)
-        tile_scatter_kernel<MAS, true><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, w.cursor, w.bucket,
-                                                                        number, dropped, vec_ok);
+        tile_scatter_kernel<MAS, true><<<sblocks, 512, 0, stream>>>(pos, W, particles, g, w.cursor, w.bucket, number,
+                                                                    dropped);
     else
-        tile_scatter_kernel<MAS, false><<<(int)blocks, 256, 0, stream>>>(pos, W, particles, g, w.cursor, w.bucket,
-                                                                         number, dropped, vec_ok);
+        tile_scatter_kernel<MAS, false><<<sblocks, 512, 0, stream>>>(pos, W, particles, g, w.cursor, w.bucket, number,
+                                                                     dropped);
     PYL_LAUNCH_CHECK();
 
     static bool attr_done[4] = {false, false, false, false};
