@@ -11,6 +11,7 @@
  *                                             FLOAT *W, long particles, int dims, int axes,
  *                                             FLOAT BoxSize, int threads)
  *   library/MAS_library/MAS_library.pyx:72-80 MA()'s dispatch to NGP/CIC/TSC/PCS(+W)
+ *   library/MAS_library/MAS_library.pyx:558-599 CIC_interp(density, BoxSize, pos, den)
  *   library/Pk_library/Pk_library.pyx:117-130 FFT3Dr_f(a, threads)
  *   library/Pk_library/Pk_library.pyx:311-378 Pk.__init__ hot loop   (no native ABI exists)
  *   library/Pk_library/Pk_library.pyx:623-732 XPk.__init__ hot loop  (no native ABI exists)
@@ -97,6 +98,12 @@ int pyl_deposit_slab(int mas, const float *pos, float *number, const float *W,
  * pos: DEVICE float32 [particles][3]; plane: DEVICE int32 [particles]. */
 int pyl_stencil_base_plane(int mas, const float *pos, int64_t particles, int dims, float BoxSize,
                            int32_t *plane, pyl_stream_t stream);
+
+/* Grid -> particle CIC interpolation: den[i] = sum of the 8 cells of `density` (dims^3 float32, DEVICE) around
+ * pos[i] times the CIC weights; `den` (DEVICE float32 [particles]) is overwritten.
+ * Replaces MAS_library.pyx:558-599 (CIC_interp). */
+int pyl_cic_interp(const float *density, int dims, float BoxSize, const float *pos, int64_t particles,
+                   float *den, pyl_stream_t stream);
 
 /* x[i] /= divisor, IEEE float32 division: the 2D renormalisation `number2 /= 2.0|3.0|4.0`
  * of MAS_library.pyx:90-107 */

@@ -32,6 +32,8 @@ def lib():
         L.oracle_ma.argtypes = [ctypes.c_int, fp, fp, fp, ctypes.c_long, ctypes.c_int,
                                 ctypes.c_int, ctypes.c_float]
         L.oracle_ma.restype = None
+        L.oracle_cic_interp.argtypes = [fp, ctypes.c_int, ctypes.c_float, fp, ctypes.c_long, fp]
+        L.oracle_cic_interp.restype = None
         L.oracle_pk_bin.argtypes = [fp, ctypes.c_int, ctypes.c_int, ip, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_int, ctypes.c_int] + [dp] * 12
         L.oracle_pk_bin.restype = None
@@ -61,6 +63,14 @@ def MA(pos, number, BoxSize, MAS="CIC", W=None, verbose=False, renormalize_2D=Tr
                     pos.shape[0], number.shape[0], coord, np.float32(BoxSize))
     if coord == 2 and renormalize_2D and MAS != "NGP":
         number /= _NREP[MAS]          # :90-107 -- divides the whole accumulated plane
+
+
+def CIC_interp(density, BoxSize, pos, den):
+    """MAS_library.pyx:558-599: den[i] = CIC-interpolated value of the 3D grid at pos[i] (overwritten)."""
+    assert density.dtype == np.float32 and density.flags.c_contiguous and density.ndim == 3
+    assert den.dtype == np.float32 and den.flags.c_contiguous
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    lib().oracle_cic_interp(_fp(density), density.shape[0], np.float32(BoxSize), _fp(pos), pos.shape[0], _fp(den))
 
 
 def frequencies(BoxSize, dims):

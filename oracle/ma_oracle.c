@@ -16,6 +16,7 @@
  *   PCS / PCSW : library/MAS_library/MAS_library.pyx:463-497 / 510-545
  *   2D mode    : library/MAS_library/MAS_library.pyx:84-110 (third axis pinned to cell 0
  *                with unit weight, so each particle lands 1/2/3/4 times in the plane)
+ *   CIC_interp : library/MAS_library/MAS_library.pyx:558-599 (grid -> particle gather)
  *
  * The serial particle order of the reference is kept, so float32 accumulation order is the
  * same as the reference's.
@@ -121,5 +122,32 @@ void oracle_ma(int mas, const float *pos, float *number, const float *W, long pa
                         number[idx[0][l] * s0 + idx[1][m] * s1 + idx[2][q] * s2] +=
                             w[0][l] * w[1][m] * w[2][q] * wp;
         }
+    }
+}
+
+/* Grid -> particle CIC interpolation (gather), library/MAS_library/MAS_library.pyx:558-599:
+ * den[i] = sum over the 8 cells around pos[i] of density[cell]*weight, weights and indices as in
+ * CIC (:585-590); each term is ((density*wx)*wy)*wz in float32, summed left to right (:592-599).
+ * den is OVERWRITTEN. */
+void oracle_cic_interp(const float *density, int dims, float BoxSize, const float *pos, long particles,
+                       float *den)
+{
+    const float inv_cell_size = (float)dims / BoxSize;
+    for (long p = 0; p < particles; p++) {
+        int id[3], iu[3];
+        float u[3], d[3];
+        for (int a = 0; a < 3; a++) {
+            volatile float dist = pos[(int64_t)p * 3 + a] * inv_cell_size;
+            u[a] = dist - (float)(int)dist;
+            d[a] = (float)(1.0 - (double)u[a]);
+            id[a] = ((int)dist) % dims;
+            iu[a] = (id[a] + 1) % dims;
+        }
+#define DEN(i, j, k) density[((int64_t)(i) * dims + (j)) * dims + (k)]
+        den[p] = DEN(id[0], id[1], id[2]) * d[0] * d[1] * d[2] + DEN(id[0], id[1], iu[2]) * d[0] * d[1] * u[2] +
+                 DEN(id[0], iu[1], id[2]) * d[0] * u[1] * d[2] + DEN(id[0], iu[1], iu[2]) * d[0] * u[1] * u[2] +
+                 DEN(iu[0], id[1], id[2]) * u[0] * d[1] * d[2] + DEN(iu[0], id[1], iu[2]) * u[0] * d[1] * u[2] +
+                 DEN(iu[0], iu[1], id[2]) * u[0] * u[1] * d[2] + DEN(iu[0], iu[1], iu[2]) * u[0] * u[1] * u[2];
+#undef DEN
     }
 }

@@ -24,7 +24,7 @@ from . import _device as D
 from . import _lib as L
 from .errors import reference_exit
 
-__all__ = ["MA", "FLOAT_type",
+__all__ = ["MA", "CIC_interp", "FLOAT_type",
            "NGPc3D", "NGPWc3D", "NGPc2D", "NGPWc2D", "CICc3D", "CICWc3D", "CICc2D", "CICWc2D",
            "TSCc3D", "TSCWc3D", "TSCc2D", "TSCWc2D", "PCSc3D", "PCSWc3D", "PCSc2D", "PCSWc2D"]
 
@@ -168,6 +168,39 @@ def MA(pos, number, BoxSize, MAS="CIC", W=None, verbose=False, renormalize_2D=Tr
         if D.is_cuda_tensor(number):
             torch.cuda.synchronize(dev)
         print("Time taken = %.3f seconds\n" % (time.time() - start))
+
+
+def CIC_interp(density, BoxSize, pos, den):
+    """den[i] = CIC-interpolated value of the 3D grid `density` at pos[i]; `den` is overwritten in place.
+
+    Reference: MAS_library.pyx:558-599 (used for marked power spectra).  NumPy float32 arrays or torch
+    CUDA float32 tensors (zero-copy); returns None."""
+    D.require_cuda()
+    if density.ndim != 3 or pos.ndim != 2 or pos.shape[1] != 3 or den.ndim != 1:
+        raise ValueError("Buffer has wrong number of dimensions (density 3D, pos (N,3), den (N,))")
+    dims = density.shape[0]
+    if any(s != dims for s in density.shape):
+        raise ValueError("density must be a (dims,dims,dims) grid, got %s" % (tuple(density.shape),))
+    if den.shape[0] != pos.shape[0]:
+        raise ValueError("den must have one entry per position")
+    dev = D.pick_device(density, pos, den)
+    density_d, _ = D.to_device_f32(density, dev, "density")
+    pos_d, _ = D.to_device_f32(pos, dev, "pos")
+    inplace = D.is_cuda_tensor(den) and den.is_contiguous()
+    if inplace and den.dtype != torch.float32:
+        raise ValueError("den must be float32, got %s" % den.dtype)
+    if not inplace and not isinstance(den, torch.Tensor) and np.asarray(den).dtype != np.float32:
+        raise ValueError("den must be float32 (Buffer dtype mismatch, expected 'float32_t' but got '%s')"
+                         % np.asarray(den).dtype)
+    den_d = den if inplace else torch.empty(pos_d.shape[0], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.load().pyl_cic_interp(D.ptr(density_d), dims, float(np.float32(BoxSize)), D.ptr(pos_d),
+                                        pos_d.shape[0], D.ptr(den_d), D.stream_ptr(dev)), "pyl_cic_interp")
+    if not inplace:
+        if isinstance(den, torch.Tensor):
+            den.copy_(den_d)
+        else:
+            den[...] = den_d.cpu().numpy()
 
 
 # ---- MAS_c (OpenMP C core) wrappers, MAS_library.pyx:1305-1389 ---------------------------

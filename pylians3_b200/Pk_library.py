@@ -162,7 +162,7 @@ def bin_fields(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=No
                               want_phase and len(idx) == 1, ky_lo, nky)
         if reduce_fn is not None:
             out = reduce_fn(out, lay)
-        return unpack_raw(out.cpu().numpy(), lay)
+        return unpack_raw(D.to_host_numpy(out), lay)
 
     if F <= L.MAX_FIELDS:
         return run(list(range(F)))

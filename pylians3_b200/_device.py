@@ -47,6 +47,28 @@ def release_workspaces():
     _ws_cache.clear()
 
 
+_pinned = {}
+
+
+def to_host_numpy(t):
+    """Device tensor -> NumPy array through a cached PINNED staging buffer (a pageable `.cpu()` of the few-MB
+    accumulator buffer was measured at 0.8-2.9 ms; pinned it is PCIe-bound).  The returned array aliases the
+    staging buffer: it is valid until the next call for the same device -- copy what must outlive that."""
+    if not t.is_cuda:
+        return t.numpy()
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    key = t.device.index
+    buf = _pinned.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        _pinned[key] = buf
+    view = buf[:nbytes].view(t.dtype).view(t.shape)
+    view.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return view.numpy()
+
+
 def to_device_f32(x, device, name):
     """numpy float32 array or torch tensor -> contiguous float32 CUDA tensor (zero-copy if possible).
 

@@ -264,7 +264,7 @@ class SlabContext:
 
     def _raw(self, dk_list, mas_index, axis, want_phase):
         out, lay = self.ops.bin(dk_list, mas_index, self.dims, axis, want_phase, self.ky_range[0], self.nky)
-        f64 = self._reduce(out, lay).cpu().numpy()
+        f64 = D.to_host_numpy(self._reduce(out, lay))
         words = f64.view(np.int64).copy()
         for off, n in ((lay.Nm3D, lay.kmax + 1), (lay.Nm1D, lay.kmax_par + 1), (lay.Nm2D, lay.n2d)):
             words[off:off + n] = np.rint(f64[off:off + n]).astype(np.int64)

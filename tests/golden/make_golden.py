@@ -8,6 +8,7 @@ The fixtures are small on purpose (a few hundred kB) and are committed; the GPU 
 
 Reference entry points exercised:
   MAS_library.MA            library/MAS_library/MAS_library.pyx:57-112
+  MAS_library.CIC_interp    library/MAS_library/MAS_library.pyx:558-599
   Pk_library.Pk             library/Pk_library/Pk_library.pyx:263-420
   Pk_library.XPk            library/Pk_library/Pk_library.pyx:529-793
 (the FFT inside Pk/XPk goes through oracle/pyfftw_shim -> scipy pocketfft, float32)
@@ -71,6 +72,13 @@ def main():
     g2 = np.full((12, 12), 0.25, np.float32)          # 2D without the final renormalisation
     M.MA(np.ascontiguousarray(pos[:, :2]), g2, BOX, "PCS", None, False, False)
     out["accum_PCS_U_2D_norenorm"] = g2
+    # CIC_interp (grid -> particles), MAS_library.pyx:558-599: a signed field, edge positions included
+    for N in (16, 9):
+        pos, _ = particles(300 + N, 5000, clustered=True)
+        field = np.random.default_rng(400 + N).standard_normal((N, N, N)).astype(np.float32)
+        den = np.zeros(len(pos), np.float32)
+        M.CIC_interp(field, BOX, pos, den)
+        out["interp_N%d_pos" % N], out["interp_N%d_field" % N], out["interp_N%d_den" % N] = pos, field, den
     np.savez_compressed(os.path.join(HERE, "ma_golden.npz"), **out)
 
     # ---- Pk / XPk

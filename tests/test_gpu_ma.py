@@ -336,3 +336,32 @@ def test_mass_conservation_full_size(env, mas):
     MASL.MA(pos, grid2, BOX, mas, W, mode="atomic")
     scale = float(grid.abs().mean().item())
     assert float((grid2 - 2.0 * grid).abs().max().item()) < 2e-5 * max(scale, float(grid.max().item()))
+
+
+@pytest.mark.parametrize("N", [16, 9])
+def test_cic_interp_vs_reference_golden(env, ma_golden, N):
+    """Grid -> particle CIC interpolation (MAS_library.pyx:558-599) against the compiled reference."""
+    torch, MASL, _ = env
+    pos, field, ref = (ma_golden["interp_N%d_%s" % (N, k)] for k in ("pos", "field", "den"))
+    den = np.full(len(pos), 7.0, np.float32)
+    assert MASL.CIC_interp(field, BOX, pos, den) is None
+    assert rel_err(den, ref, floor=float(np.abs(field).mean())) < TOL
+
+
+def test_cic_interp_vs_oracle_medium_and_device_tensors(env, oracle):
+    torch, MASL, _ = env
+    N = 128
+    pos, _ = make_particles(21, 1000003, True)
+    field = np.random.default_rng(5).standard_normal((N, N, N)).astype(np.float32)
+    ref = np.zeros(len(pos), np.float32)
+    oracle.CIC_interp(field, BOX, pos, ref)
+    den = torch.full((len(pos),), -3.0, dtype=torch.float32, device="cuda")
+    ptr0 = den.data_ptr()
+    MASL.CIC_interp(torch.from_numpy(field).cuda(), BOX, torch.from_numpy(pos).cuda(), den)
+    assert den.data_ptr() == ptr0
+    assert rel_err(den.cpu().numpy(), ref, floor=float(np.abs(field).mean())) < TOL
+    # interpolating a constant field returns the constant (weights sum to 1), the transpose of mass conservation
+    one = np.ones((N, N, N), np.float32)
+    out = np.zeros(len(pos), np.float32)
+    MASL.CIC_interp(one, BOX, pos, out)
+    assert np.max(np.abs(out - 1.0)) < 1e-6

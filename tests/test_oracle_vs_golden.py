@@ -46,6 +46,16 @@ def test_ma_oracle_accumulates(oracle, ma_golden):
     assert np.array_equal(g2, ma_golden["accum_PCS_U_2D_norenorm"])
 
 
+@pytest.mark.parametrize("N", [16, 9])
+def test_cic_interp_oracle_matches_reference(oracle, ma_golden, N):
+    """MAS_library.pyx:558-599: the reference is compiled with -ffast-math (free to reassociate the 8-term sum),
+    so float32 round-off of the sum is allowed: 1e-6 of the field's scale."""
+    pos, field, ref = (ma_golden["interp_N%d_%s" % (N, k)] for k in ("pos", "field", "den"))
+    den = np.full(len(pos), 7.0, np.float32)          # overwritten, not accumulated
+    oracle.CIC_interp(field, BOX, pos, den)
+    assert rel_err(den, ref, floor=float(np.abs(field).mean())) < 1e-6
+
+
 PK_ATTRS = ("k3D", "Pk", "Nmodes3D", "Pkphase", "k1D", "Pk1D", "Nmodes1D", "kpar", "kper", "Pk2D", "Nmodes2D")
 XPK_ATTRS = ("k3D", "Pk", "XPk", "Nmodes3D", "k1D", "Pk1D", "PkX1D", "Nmodes1D", "kpar", "kper", "Pk2D",
              "PkX2D", "Nmodes2D")
