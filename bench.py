@@ -192,6 +192,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0 prints ONE JSON line on stdout: NCCL's own version/debug lines go to a file instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pyl_b200_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, _lib, overdensity_, synth
@@ -288,14 +290,13 @@ def run_ours(args):
             e.record()
             return e
         reps = 3
-        acc = {k: 0.0 for k in ("zero", "deposit", "overdensity", "fft", "bin+d2h+finalise")}
+        acc = {k: 0.0 for k in ("zero", "deposit", "overdensity", "fft", "bin+finalise+d2h")}
         for _ in range(reps):
             e0 = ev(); grid.zero_()
             e1 = ev(); MASL.MA(pos, grid, BOX, MAS)
             e2 = ev(); overdensity_(grid)
             e3 = ev(); dk = PKL.fft3d_r2c_device(grid)
-            e4 = ev(); raw = PKL.bin_fields([dk], [PKL.MAS_function(MAS)], grid_n, AXIS, want_phase=True)
-            PKL._finalize(raw, BOX, grid_n)
+            e4 = ev(); PKL.spectra([dk], [PKL.MAS_function(MAS)], grid_n, AXIS, BOX, want_phase=True)
             e5 = ev(); torch.cuda.synchronize()
             for k, (a, b) in zip(acc, ((e0, e1), (e1, e2), (e2, e3), (e3, e4), (e4, e5))):
                 acc[k] += a.elapsed_time(b) / reps
@@ -330,13 +331,13 @@ def run_ours(args):
             e.record()
             return e
         reps = 3
-        acc = {k: 0.0 for k in ("zero", "deposit+halo", "overdensity", "fft(yz,transpose,x)", "bin+allreduce+finalise")}
+        acc = {k: 0.0 for k in ("zero", "deposit+halo", "overdensity", "fft(yz,transpose,x)", "bin+allreduce+finalise+d2h")}
         for _ in range(reps):
             e0 = ev(); slab.zero_()
             e1 = ev(); ctx.MA(pos, slab, MAS, routed=True)
             e2 = ev(); ctx.overdensity_(slab)
             e3 = ev(); dk = ctx.fft(slab)
-            e4 = ev(); raw = ctx._raw([dk], [PKL.MAS_function(MAS)], AXIS, True); PKL._finalize(raw, BOX, grid_n)
+            e4 = ev(); ctx._spectra([dk], [PKL.MAS_function(MAS)], AXIS, True)
             e5 = ev(); torch.cuda.synchronize()
             for k, (a, b) in zip(acc, ((e0, e1), (e1, e2), (e2, e3), (e3, e4), (e4, e5))):
                 acc[k] += a.elapsed_time(b) / reps

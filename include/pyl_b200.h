@@ -177,6 +177,27 @@ int pyl_pk_bin(const float *const *delta_k, int fields, const int *mas_index, in
                int ky_lo, int nky, int axis, int want_phase, void *out, void *ws,
                size_t ws_bytes, pyl_stream_t stream);
 
+/* Finalisation of the accumulators IN PLACE (Pk_library.pyx:384-418 / :735-791): afterwards every word of `acc`
+ * is the float64 value the reference stores for that slot -- k3D = <k> kF, Pk3D = P_l (2l+1)/Nmodes (BoxSize/
+ * dims^2)^3, phase likewise, Pk1D with its perpendicular-area weight, Pk2D = P/Nmodes2D * units; counts are
+ * converted to float64 (counts_are_f64 != 0: they already are, e.g. after a float64 all-reduce).  The DC bins
+ * keep their slots (the reference drops bin 0 of the 3D and 1D arrays; the caller slices).  Operation order
+ * follows the reference's expressions, so results equal a host finalisation bit for bit.
+ * kpar/kper (DEVICE double [n2d] each, or both NULL) receive the bin-centre coordinates of the 2D array. */
+int pyl_pk_finalize(void *acc, int dims, int fields, double BoxSize, int counts_are_f64, double *kpar,
+                    double *kper, pyl_stream_t stream);
+
+/* Mirrored slab form (multi-GPU): the rank holds the rows |ky| in [ky_lo, ky_lo+ny_lo) of the half-range
+ * 0..dims/2 AND their mirrors N-ky, as (dims, nky, dims/2+1) complex64 with the ky axis ordered: first the
+ * ny_lo lower rows (ascending ky), then the mirrors that exist as separate modes (ky != 0, ky != Nyquist) in
+ * ascending order of their global index.  pyl_pk_mirrored_rows returns nky (and the global index of the first
+ * upper row).  Holding both signs of ky lets the kernel share geometry between the four modes (+-kx, +-ky, kz)
+ * exactly as on a whole grid, and walk along an axis that is not the line of sight. */
+int pyl_pk_mirrored_rows(int dims, int ky_lo, int ny_lo, int *first_upper);
+int pyl_pk_bin_mirrored(const float *const *delta_k, int fields, const int *mas_index, int dims,
+                        int ky_lo, int ny_lo, int axis, int want_phase, void *out, void *ws,
+                        size_t ws_bytes, pyl_stream_t stream);
+
 /* ---- 4. host-pointer entry points with the reference's exact C signature ------------ */
 /* Same argument list as MAS_c.h:3-10 (HOST pointers; `threads` is accepted and ignored).
  * They copy pos/W/number to the GPU, run pyl_deposit, and copy number back; a maintainer

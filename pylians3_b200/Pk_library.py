@@ -107,22 +107,25 @@ def FFT3Dr_f(a, threads=1):
     return out if D.is_cuda_tensor(a) else out.cpu().numpy()
 
 
-def bin_device(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=None):
+def bin_device(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=None, mirrored=False):
     """Run pyl_pk_bin on `len(dk_list)` (<= L.MAX_FIELDS) half-spectra; returns (int64 CUDA tensor
-    holding the raw accumulators, layout)."""
+    holding the raw accumulators, layout).  mirrored=True: the fields hold the |ky| rows [ky_lo, ky_lo+nky)
+    and their mirrors (pyl_pk_bin_mirrored, multi-GPU slabs)."""
     lib = L.load()
     F = len(dk_list)
     nky = dims if nky is None else nky
     dev = dk_list[0].device
     lay = L.pk_layout(dims, F)
     with torch.cuda.device(dev):
-        out = torch.empty(lay.total_words, dtype=torch.int64, device=dev)
+        # room behind the accumulators for kpar/kper (finalize_device)
+        out = torch.empty(lay.total_words + 2 * lay.n2d, dtype=torch.int64, device=dev)
         need = lib.pyl_pk_bin_workspace_bytes(dims, F)
         ws = D.workspace(need, dev, "pkbin")
         ptrs = (ctypes.c_void_p * F)(*[D.ptr(t) for t in dk_list])
         mi = (ctypes.c_int * F)(*[int(i) for i in mas_index])
-        st = lib.pyl_pk_bin(ptrs, F, mi, dims, ky_lo, nky, axis, 1 if want_phase else 0, D.ptr(out),
-                            D.ptr(ws), need, D.stream_ptr(dev))
+        fn = lib.pyl_pk_bin_mirrored if mirrored else lib.pyl_pk_bin
+        st = fn(ptrs, F, mi, dims, ky_lo, nky, axis, 1 if want_phase else 0, D.ptr(out), D.ptr(ws), need,
+                D.stream_ptr(dev))
     L.check(st, "pyl_pk_bin")
     return out, lay
 
@@ -148,7 +151,8 @@ def unpack_raw(words, lay):
                 Nm2D=cnt(lay.Nm2D, n2), Pk2D=dbl(lay.Pk2D, n2, F), PkX2D=dbl(lay.PkX2D, n2, X))
 
 
-def bin_fields(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=None, reduce_fn=None):
+def bin_fields(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=None, reduce_fn=None,
+               mirrored=False):
     """Raw accumulators for ANY number of fields.
 
     Up to L.MAX_FIELDS fields go through one launch.  More fields are covered by launches over
@@ -159,7 +163,7 @@ def bin_fields(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=No
 
     def run(idx):
         out, lay = bin_device([dk_list[i] for i in idx], [mas_index[i] for i in idx], dims, axis,
-                              want_phase and len(idx) == 1, ky_lo, nky)
+                              want_phase and len(idx) == 1, ky_lo, nky, mirrored)
         if reduce_fn is not None:
             out = reduce_fn(out, lay)
         return unpack_raw(D.to_host_numpy(out), lay)
@@ -200,6 +204,58 @@ def bin_fields(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=No
                             res[k][..., pair_id[g]] = r[k][..., lx]
                     lx += 1
     return res
+
+
+def finalize_device(out, lay, BoxSize, dims, counts_are_f64=False):
+    """Finalise the accumulators on the device (pyl_pk_finalize) and return the reference's attribute arrays
+    (same dict as `_finalize`).
+
+    `out` must have room for lay.total_words + 2*lay.n2d words (bin_device allocates that): kpar/kper are
+    written behind the accumulators.  The finished block crosses PCIe ONCE into a pinned host block
+    (_device.result_block) and the returned arrays are views of that block: they keep it out of circulation
+    until the caller drops them.  No multi-MB NumPy temporaries: at 1024^3 their page faults alone
+    cost several ms per call."""
+    dev = out.device
+    n2 = lay.n2d
+    with torch.cuda.device(dev):
+        f64 = out.view(torch.float64)
+        kp = f64[lay.total_words:lay.total_words + n2]
+        kq = f64[lay.total_words + n2:lay.total_words + 2 * n2]
+        L.check(L.load().pyl_pk_finalize(D.ptr(out), int(dims), int(lay.fields), float(BoxSize),
+                                         1 if counts_are_f64 else 0, D.ptr(kp), D.ptr(kq), D.stream_ptr(dev)),
+                "pyl_pk_finalize")
+        block, f = D.result_block(f64.numel())
+        block[:f64.numel()].copy_(f64, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    F, X = lay.fields, lay.xfields
+    n3, n1 = lay.kmax + 1, lay.kmax_par + 1
+    kF = frequencies(BoxSize, dims)[0]
+
+    def arr(off, *shape, skip=0):
+        return f[off:off + int(np.prod(shape))].reshape(shape)[skip:]
+
+    o = {}
+    Nm1 = arr(lay.Nm1D, n1, skip=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        o["k1D"] = ((Nm1 * np.arange(1, n1, dtype=np.float64)) / Nm1) * kF
+    o["Nmodes1D"] = Nm1
+    o["Pk1D"], o["PkX1D"] = arr(lay.Pk1D, n1, F, skip=1), arr(lay.PkX1D, n1, X, skip=1)
+    o["kpar"], o["kper"] = arr(lay.total_words, n2), arr(lay.total_words + n2, n2)
+    o["Nmodes2D"], o["Pk2D"], o["PkX2D"] = arr(lay.Nm2D, n2), arr(lay.Pk2D, n2, F), arr(lay.PkX2D, n2, X)
+    Nm3 = arr(lay.Nm3D, n3)
+    check_number_modes(Nm3, dims)
+    o["Nmodes3D"], o["k3D"] = Nm3[1:], arr(lay.k3D, n3, skip=1)
+    o["Pk"], o["XPk"] = arr(lay.Pk3D, n3, 3, F, skip=1), arr(lay.PkX3D, n3, 3, X, skip=1)
+    o["Pkphase"] = arr(lay.phase, n3, skip=1)
+    return o
+
+
+def spectra(dk_list, mas_index, dims, axis, BoxSize, want_phase=False):
+    """bin + finalise: device finalisation for up to L.MAX_FIELDS fields, host assembly beyond."""
+    if len(dk_list) <= L.MAX_FIELDS:
+        out, lay = bin_device(dk_list, mas_index, dims, axis, want_phase and len(dk_list) == 1)
+        return finalize_device(out, lay, BoxSize, dims)
+    return _finalize(bin_fields(dk_list, mas_index, dims, axis, want_phase), BoxSize, dims)
 
 
 # ---- host finalisation (vectorised restatement of :384-418 / :735-791) --------------------
@@ -272,10 +328,9 @@ class Pk:
         dims = delta_d.shape[0]
         delta_k = fft3d_r2c_device(delta_d)
         start2 = time.time()
-        raw = bin_fields([delta_k], [MAS_function(MAS)], dims, axis, want_phase=True)
+        o = spectra([delta_k], [MAS_function(MAS)], dims, axis, BoxSize, want_phase=True)
         if verbose:
             print("Time to complete loop = %.2f" % (time.time() - start2))
-        o = _finalize(raw, BoxSize, dims)
         self.k1D, self.Pk1D, self.Nmodes1D = o["k1D"], o["Pk1D"][:, 0], o["Nmodes1D"]
         self.kpar, self.kper = o["kpar"], o["kper"]
         self.Pk2D, self.Nmodes2D = o["Pk2D"][:, 0], o["Nmodes2D"]
@@ -310,10 +365,9 @@ class XPk:
             torch.cuda.synchronize(dev)
         print("Time FFTS = %.2f" % (time.time() - start))
         start2 = time.time()
-        raw = bin_fields(dk, [MAS_function(m) for m in MAS], dims, axis)
+        o = spectra(dk, [MAS_function(m) for m in MAS], dims, axis, BoxSize)
         del dk
         print("Time loop = %.2f" % (time.time() - start2))
-        o = _finalize(raw, BoxSize, dims)
         self.k1D, self.Nmodes1D = o["k1D"], o["Nmodes1D"]
         self.Pk1D, self.PkX1D = o["Pk1D"], o["PkX1D"]
         self.kpar, self.kper, self.Nmodes2D = o["kpar"], o["kper"], o["Nmodes2D"]

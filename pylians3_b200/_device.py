@@ -45,6 +45,8 @@ def workspace(nbytes, device, tag="ws"):
 
 def release_workspaces():
     _ws_cache.clear()
+    _pinned.clear()
+    del _result_pool[:]
 
 
 _pinned = {}
@@ -67,6 +69,29 @@ def to_host_numpy(t):
     view.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
     return view.numpy()
+
+
+_result_pool = []          # [pinned tensor, weakref to the ndarray handed out over it]
+
+
+def result_block(nwords):
+    """(pinned float64 tensor, float64 ndarray over the same memory) for one set of results.
+
+    Blocks are recycled: a block is free again once the ndarray handed out with it -- the `.base` of every view
+    the caller received -- has been garbage collected.  A steady-state loop therefore touches the same few
+    blocks (no page faults, no cudaHostAlloc per call), while every result the caller keeps stays valid."""
+    import weakref
+    nwords = int(nwords)
+    for entry in _result_pool:
+        t, ref = entry
+        if t.numel() >= nwords and (ref is None or ref() is None):
+            root = t.numpy()
+            entry[1] = weakref.ref(root)
+            return t, root
+    t = torch.empty(max(nwords, 1 << 16), dtype=torch.float64, pin_memory=True)
+    root = t.numpy()
+    _result_pool.append([t, weakref.ref(root)])
+    return t, root
 
 
 def to_device_f32(x, device, name):

@@ -60,6 +60,9 @@ PROTOTYPES = {
     "pyl_pk_layout": (_i, [_i, _i, ctypes.POINTER(PkLayout)]),
     "pyl_pk_bin_workspace_bytes": (_sz, [_i, _i]),
     "pyl_pk_bin": (_i, [ctypes.POINTER(_vp), _i, ctypes.POINTER(_i), _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "pyl_pk_finalize": (_i, [_vp, _i, _i, ctypes.c_double, _i, _vp, _vp, _vp]),
+    "pyl_pk_mirrored_rows": (_i, [_i, _i, _i, ctypes.POINTER(_i)]),
+    "pyl_pk_bin_mirrored": (_i, [ctypes.POINTER(_vp), _i, ctypes.POINTER(_i), _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "pyl_NGP": (_i, [_vp, _vp, _vp, _l, _i, _i, _f, _i]),
     "pyl_CIC": (_i, [_vp, _vp, _vp, _l, _i, _i, _f, _i]),
     "pyl_TSC": (_i, [_vp, _vp, _vp, _l, _i, _i, _f, _i]),

@@ -39,10 +39,14 @@ struct PkArgs {
     const float2 *dk[F];     // (N, nky, nz) complex64 each
     const double *win[F];    // MAS window per |k| index: (x/sin x)^p, x = pi*k/N, [m+1]
     int N, m, nz, even;
-    int ky_lo, nky;          // stored ky rows [ky_lo, ky_lo+nky)
+    int ky_lo, nky;          // stored ky rows: nky rows, the first ones are global ky = ky_lo, ky_lo+1, ...
+    int ny_lo, ky_up0;       // mirrored slab: rows [0,ny_lo) hold ky_lo.., rows [ny_lo,nky) hold global ky_up0..
+                             // (the mirrors N-ky of the lower rows, ascending); otherwise ny_lo = nky
     int walk_y;              // 1: walk along ky, other axis = kx;  0: walk along kx, other = ky
     int fold_other;          // 1: thread folds +-k_o (needs both rows stored)
-    int n_other;             // fold: m+1 values |k_o|; no fold: stored indices of the other axis
+    int n_other;             // fold: number of |k_o| values; no fold: stored indices of the other axis
+    int o_lo;                // fold: first |k_o| (0 unless the other axis is a mirrored ky window)
+    int w_lo, w_hi;          // walk range |k_w| in [w_lo, w_hi)
     int axis;                // line of sight
     int kmax_par1;           // kmax_par + 1
     int seg_len, nseg;       // walk range [0, m] cut into nseg segments of seg_len steps
@@ -96,16 +100,24 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
     int o_val[2], o_idx[2];
     bool o_ok[2];
     int a_abs;
+    // stored row of a global ky index (identity on a whole grid)
+    auto ystore = [&](int gy) -> int {
+        return (gy - A.ky_lo < A.ny_lo && gy >= A.ky_lo) ? gy - A.ky_lo : A.ny_lo + (gy - A.ky_up0);
+    };
     if (A.fold_other) {
-        a_abs = oi;
-        o_val[0] = oi; o_idx[0] = oi; o_ok[0] = true;
-        o_val[1] = -oi; o_idx[1] = N - oi;
-        o_ok[1] = (oi != 0) && !(even && oi == m);
+        a_abs = A.o_lo + oi;
+        o_val[0] = a_abs; o_idx[0] = a_abs; o_ok[0] = true;
+        o_val[1] = -a_abs; o_idx[1] = N - a_abs;
+        o_ok[1] = (a_abs != 0) && !(even && a_abs == m);
+        if (!A.walk_y) {                     // the other axis is y: translate to stored rows
+            o_idx[0] = ystore(o_idx[0]);
+            if (o_ok[1]) o_idx[1] = ystore(o_idx[1]);
+        }
     } else {
         const int gi = oi + (A.walk_y ? 0 : A.ky_lo);    // stored index -> global index
         const int v = (gi > m) ? gi - N : gi;
         a_abs = v < 0 ? -v : v;
-        o_val[0] = v; o_idx[0] = gi; o_ok[0] = true;
+        o_val[0] = v; o_idx[0] = A.walk_y ? gi : oi; o_ok[0] = true;
         o_val[1] = 0; o_idx[1] = 0; o_ok[1] = false;
     }
 
@@ -115,8 +127,8 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
     for (int f = 0; f < F; f++) win_oz[f] = A.win[f][a_abs] * A.win[f][kz];
 
     // ---- bin bookkeeping ----------------------------------------------------------------
-    const int s0 = seg * A.seg_len;
-    const int s1 = min(s0 + A.seg_len, m + 1);
+    const int s0 = A.w_lo + seg * A.seg_len;
+    const int s1 = min(s0 + A.seg_len, A.w_hi);
     const int base2 = a_abs * a_abs + kz * kz;
     // k_par by line of sight; the walk coordinate is x (walk_y==0) or y (walk_y==1)
     const int walk_axis = A.walk_y ? 1 : 0;
@@ -189,10 +201,11 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
 
     // ---- loads: the 2x2 sign combinations of (other, walk) at walk step s ----------------
     // slot c = 2*io + iw.  ok[c] carries existence AND the Hermitian-duplicate rule.
+    // o_index is a kx index (walk_y) or an already translated stored ky row (walk x)
     auto row_of = [&](int o_index, int w_index) -> long long {
         const int kxx = A.walk_y ? o_index : w_index;
-        const int kyy = A.walk_y ? w_index : o_index;
-        return ((long long)kxx * A.nky + (kyy - A.ky_lo)) * nz + kz;
+        const int yrow = A.walk_y ? ystore(w_index) : o_index;
+        return ((long long)kxx * A.nky + yrow) * nz + kz;
     };
     auto mode_ok = [&](int ov, int wv) -> bool {
         const int kx = A.walk_y ? ov : wv;
@@ -352,6 +365,80 @@ __global__ void pk_fold_replicas_kernel(unsigned long long *out, const unsigned 
     }
 }
 
+// ---- finalisation on the device (Pk_library.pyx:384-418 / :735-791): units, averages, (2l+1) factors ----------
+// In place on the accumulator buffer: every word becomes the float64 value the reference stores in the same
+// slot (counts become float64 too; the DC bins keep their slots and are dropped by the caller).  One thread per
+// bin; each expression is spelled with explicit-rounding intrinsics in the order of the reference's (and of
+// Pk_library._finalize's) NumPy expressions, so the result is bit-identical to the host finalisation.
+struct FinalizeArgs {
+    unsigned long long *acc;
+    double *kpar, *kper;     // optional: bin-centre coordinates of the 2D array (Pk_library.pyx:394-399)
+    int kmax_par1;
+    int F, X, n3, n1;
+    long long n2;
+    int counts_f64;
+    double kF, kN2, fact, twopi2;   // kN2, fact, twopi2 come from libm pow() like the Python-level expressions
+    long long o_k3D, o_Nm3D, o_Pk3D, o_PkX3D, o_phase, o_Nm1D, o_Pk1D, o_PkX1D, o_Nm2D, o_Pk2D, o_PkX2D;
+};
+
+__global__ void __launch_bounds__(256) pk_finalize_kernel(const FinalizeArgs A) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double *f = reinterpret_cast<double *>(A.acc);
+    auto count = [&](long long w) -> double {
+        return A.counts_f64 ? f[w] : (double)A.acc[w];
+    };
+    if (t < A.n3) {
+        const double Nm = count(A.o_Nm3D + t);
+        f[A.o_k3D + t] = __dmul_rn(__ddiv_rn(f[A.o_k3D + t], Nm), A.kF);
+        const double ell[3] = {1.0, 5.0, 9.0};
+        for (int l = 0; l < 3; l++) {
+            for (int c = 0; c < A.F; c++) {
+                const long long w = A.o_Pk3D + (t * 3 + l) * A.F + c;
+                f[w] = __dmul_rn(__ddiv_rn(__dmul_rn(f[w], ell[l]), Nm), A.fact);
+            }
+            for (int c = 0; c < A.X; c++) {
+                const long long w = A.o_PkX3D + (t * 3 + l) * A.X + c;
+                f[w] = __dmul_rn(__ddiv_rn(__dmul_rn(f[w], ell[l]), Nm), A.fact);
+            }
+        }
+        f[A.o_phase + t] = __dmul_rn(__ddiv_rn(f[A.o_phase + t], Nm), A.fact);
+        f[A.o_Nm3D + t] = Nm;
+    }
+    if (t < A.n1) {
+        const double Nm = count(A.o_Nm1D + t);
+        const double k1 = __dmul_rn(__ddiv_rn(__dmul_rn(Nm, (double)t), Nm), A.kF);
+        const double kmaxper = sqrt(__dsub_rn(A.kN2, __dmul_rn(k1, k1)));
+        const double w1 = __ddiv_rn(__dmul_rn(M_PI, __dmul_rn(kmaxper, kmaxper)), Nm);
+        const double twopi2 = A.twopi2;
+        for (int c = 0; c < A.F; c++) {
+            const long long w = A.o_Pk1D + t * A.F + c;
+            f[w] = __ddiv_rn(__dmul_rn(__dmul_rn(f[w], A.fact), w1), twopi2);
+        }
+        for (int c = 0; c < A.X; c++) {
+            const long long w = A.o_PkX1D + t * A.X + c;
+            f[w] = __ddiv_rn(__dmul_rn(__dmul_rn(f[w], A.fact), w1), twopi2);
+        }
+        f[A.o_Nm1D + t] = Nm;
+    }
+    if (t < A.n2) {
+        const double Nm = count(A.o_Nm2D + t);
+        for (int c = 0; c < A.F; c++) {
+            const long long w = A.o_Pk2D + t * A.F + c;
+            f[w] = __ddiv_rn(__dmul_rn(f[w], A.fact), Nm);
+        }
+        for (int c = 0; c < A.X; c++) {
+            const long long w = A.o_PkX2D + t * A.X + c;
+            f[w] = __ddiv_rn(__dmul_rn(f[w], A.fact), Nm);
+        }
+        f[A.o_Nm2D + t] = Nm;
+        if (A.kpar != nullptr) {
+            const long long kp = t % A.kmax_par1, kq = t / A.kmax_par1;
+            A.kpar[t] = __dmul_rn(0.5 * (double)(kp + kp + 1), A.kF);      // 0.5*(k_par + k_par+1)*kF
+            A.kper[t] = __dmul_rn(0.5 * (double)(kq + kq + 1), A.kF);
+        }
+    }
+}
+
 static void fill_layout(int dims, int F, pyl_pk_layout_t *L) {
     const int m = dims / 2;
     const int X = F * (F - 1) / 2;
@@ -384,9 +471,20 @@ static size_t bin_workspace(int dims, int F) {
     return tab + rep;
 }
 
+// rows N-ky of the lower rows ky in [ky_lo, ky_lo+ny_lo) that exist as separate modes (ky != 0, ky != Nyquist),
+// stored in ascending order of their global index; *first = global index of the first of them
+static int mirrored_upper_rows(int dims, int ky_lo, int ny_lo, int *first) {
+    const int m = dims / 2;
+    int lo = ky_lo, hi = ky_lo + ny_lo - 1;             // |ky| values with a mirror: lo..hi minus {0, Nyquist}
+    if (lo == 0) lo = 1;
+    if (dims % 2 == 0 && hi == m) hi = m - 1;
+    if (first) *first = dims - hi;
+    return hi >= lo ? hi - lo + 1 : 0;
+}
+
 template <int F>
 static int launch_bin(const float *const *delta_k, const int *mas_index, int dims, int ky_lo,
-                      int nky, int axis, int want_phase, void *out, void *ws, cudaStream_t stream) {
+                      int nky, int mirrored, int axis, int want_phase, void *out, void *ws, cudaStream_t stream) {
     pyl_pk_layout_t L;
     fill_layout(dims, F, &L);
     const int m = dims / 2, nz = m + 1;
@@ -411,15 +509,25 @@ static int launch_bin(const float *const *delta_k, const int *mas_index, int dim
         A.win[f] = tab + (size_t)f * nz;
     }
     A.N = dims; A.m = m; A.nz = nz; A.even = (dims % 2 == 0);
-    A.ky_lo = ky_lo; A.nky = nky;
-    const bool whole = (ky_lo == 0 && nky == dims);
+    A.ky_lo = ky_lo; A.nky = nky; A.ny_lo = nky; A.ky_up0 = 0;
+    A.o_lo = 0; A.w_lo = 0; A.w_hi = m + 1;
+    const bool whole = (ky_lo == 0 && nky == dims && !mirrored);
     if (whole) {
         // fold both in-plane axes; walk along y unless y is the line of sight
         A.fold_other = 1;
         A.walk_y = (axis == 1) ? 0 : 1;
         A.n_other = m + 1;
+    } else if (mirrored) {
+        // slab holding |ky| in [ky_lo, ky_lo+nky) AND the mirrored rows N-ky (pyl_pk_bin_mirrored; here `nky`
+        // counts the lower rows): the whole-grid scheme restricted to a |ky| window -- four-fold mode sharing,
+        // and the walk still avoids the line of sight (walk y over the window, or x when y is the line of sight)
+        A.ny_lo = nky;
+        A.nky = nky + mirrored_upper_rows(dims, ky_lo, nky, &A.ky_up0);
+        A.fold_other = 1;
+        if (axis == 1) { A.walk_y = 0; A.n_other = nky; A.o_lo = ky_lo; }
+        else { A.walk_y = 1; A.n_other = m + 1; A.w_lo = ky_lo; A.w_hi = ky_lo + nky; }
     } else {
-        // slab of ky rows (distributed transform): only kx is complete -> walk x, no ky fold
+        // contiguous window of ky rows without their mirrors: only kx is complete -> walk x, no ky fold
         A.fold_other = 0;
         A.walk_y = 0;
         A.n_other = nky;
@@ -432,11 +540,13 @@ static int launch_bin(const float *const *delta_k, const int *mas_index, int dim
     const long long warps_per_seg = (A.T + 31) / 32;
     const long long want_warps = (long long)sm_count() * 64;
     long long nseg = (want_warps + warps_per_seg - 1) / warps_per_seg;
-    const long long max_seg = (m + 1 + 7) / 8;          // at least 8 steps per segment
+    const int wlen = A.w_hi - A.w_lo;
+    const long long max_seg = (wlen + 7) / 8;           // at least 8 steps per segment
     if (nseg > max_seg) nseg = max_seg;
     if (nseg < 1) nseg = 1;
-    A.seg_len = (int)((m + 1 + nseg - 1) / nseg);
-    A.nseg = (m + 1 + A.seg_len - 1) / A.seg_len;
+    A.seg_len = (int)((wlen + nseg - 1) / nseg);
+    if (A.seg_len < 1) A.seg_len = 1;
+    A.nseg = (wlen + A.seg_len - 1) / A.seg_len;
 
     A.out = reinterpret_cast<unsigned long long *>(out);
     A.rep = rep; A.rep_words = rep_words;
@@ -444,7 +554,7 @@ static int launch_bin(const float *const *delta_k, const int *mas_index, int dim
     A.o_Nm1D = L.Nm1D; A.o_Pk1D = L.Pk1D; A.o_PkX1D = L.PkX1D;
     A.o_Nm2D = L.Nm2D; A.o_Pk2D = L.Pk2D; A.o_PkX2D = L.PkX2D;
 
-    if (A.T > 0) {
+    if (A.T > 0 && A.nseg > 0) {
         dim3 grid((unsigned)((A.T + PK_BLOCK - 1) / PK_BLOCK), (unsigned)A.nseg);
         if (want_phase) pk_bin_walk_kernel<F, true><<<grid, PK_BLOCK, 0, stream>>>(A);
         else pk_bin_walk_kernel<F, false><<<grid, PK_BLOCK, 0, stream>>>(A);
@@ -469,19 +579,46 @@ int pyl_pk_layout(int dims, int fields, pyl_pk_layout_t *layout) {
     return PYL_OK;
 }
 
+int pyl_pk_finalize(void *acc, int dims, int fields, double BoxSize, int counts_are_f64, double *kpar,
+                    double *kper, pyl_stream_t stream) {
+    PYL_REQUIRE(acc != nullptr, "pyl_pk_finalize: NULL buffer");
+    PYL_REQUIRE((kpar == nullptr) == (kper == nullptr), "pyl_pk_finalize: give both kpar and kper or neither");
+    PYL_REQUIRE(dims > 0 && fields >= 1 && BoxSize > 0.0, "pyl_pk_finalize: bad dims/fields/BoxSize");
+    pyl_pk_layout_t L;
+    fill_layout(dims, fields, &L);
+    FinalizeArgs A;
+    A.acc = reinterpret_cast<unsigned long long *>(acc);
+    A.kpar = kpar; A.kper = kper; A.kmax_par1 = L.kmax_par + 1;
+    A.F = L.fields; A.X = L.xfields;
+    A.n3 = L.kmax + 1; A.n1 = L.kmax_par + 1; A.n2 = L.n2d;
+    A.counts_f64 = counts_are_f64;
+    A.kF = 2.0 * M_PI / BoxSize;                                   // Pk_library.pyx:57
+    A.kN2 = pow((double)(dims / 2) * A.kF, 2.0);                   // kN**2, :59 and :389
+    A.fact = pow(BoxSize / ((double)dims * (double)dims), 3.0);    // (BoxSize/dims**2)**3, :385
+    A.twopi2 = pow(2.0 * M_PI, 2.0);                               // (2.0*np.pi)**2, :391
+    A.o_k3D = L.k3D; A.o_Nm3D = L.Nm3D; A.o_Pk3D = L.Pk3D; A.o_PkX3D = L.PkX3D; A.o_phase = L.phase;
+    A.o_Nm1D = L.Nm1D; A.o_Pk1D = L.Pk1D; A.o_PkX1D = L.PkX1D;
+    A.o_Nm2D = L.Nm2D; A.o_Pk2D = L.Pk2D; A.o_PkX2D = L.PkX2D;
+    long long n = A.n2 > A.n3 ? A.n2 : A.n3;
+    if (A.n1 > n) n = A.n1;
+    pk_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(A);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
 size_t pyl_pk_bin_workspace_bytes(int dims, int fields) {
     if (dims <= 0 || fields < 1 || fields > PYL_MAX_FIELDS) return 0;
     return bin_workspace(dims, fields);
 }
 
-int pyl_pk_bin(const float *const *delta_k, int fields, const int *mas_index, int dims,
-               int ky_lo, int nky, int axis, int want_phase, void *out, void *ws,
-               size_t ws_bytes, pyl_stream_t stream) {
+static int pk_bin_entry(const float *const *delta_k, int fields, const int *mas_index, int dims,
+                        int ky_lo, int nky, int mirrored, int axis, int want_phase, void *out, void *ws,
+                        size_t ws_bytes, pyl_stream_t stream) {
     PYL_REQUIRE(fields >= 1 && fields <= PYL_MAX_FIELDS, "pyl_pk_bin: fields must be 1..PYL_MAX_FIELDS");
     PYL_REQUIRE(dims > 0 && dims <= 8192, "pyl_pk_bin: dims must be in 1..8192");
     PYL_REQUIRE(axis >= 0 && axis <= 2, "pyl_pk_bin: axis must be 0, 1 or 2");
     PYL_REQUIRE(delta_k != nullptr && mas_index != nullptr && out != nullptr, "pyl_pk_bin: NULL pointer");
-    PYL_REQUIRE(ky_lo >= 0 && nky >= 0 && ky_lo + nky <= dims, "pyl_pk_bin: bad ky window");
+    PYL_REQUIRE(ky_lo >= 0 && nky >= 0 && ky_lo + nky <= (mirrored ? dims / 2 + 1 : dims), "pyl_pk_bin: bad ky window");
     for (int f = 0; f < fields; f++) {
         PYL_REQUIRE(delta_k[f] != nullptr || nky == 0, "pyl_pk_bin: NULL field pointer");
         PYL_REQUIRE(mas_index[f] >= 0 && mas_index[f] <= 4, "pyl_pk_bin: mas_index must be 0..4");
@@ -494,11 +631,28 @@ int pyl_pk_bin(const float *const *delta_k, int fields, const int *mas_index, in
     }
     cudaStream_t s = as_stream(stream);
     switch (fields) {
-        case 1: return launch_bin<1>(delta_k, mas_index, dims, ky_lo, nky, axis, want_phase, out, ws, s);
-        case 2: return launch_bin<2>(delta_k, mas_index, dims, ky_lo, nky, axis, 0, out, ws, s);
-        case 3: return launch_bin<3>(delta_k, mas_index, dims, ky_lo, nky, axis, 0, out, ws, s);
-        default: return launch_bin<4>(delta_k, mas_index, dims, ky_lo, nky, axis, 0, out, ws, s);
+        case 1: return launch_bin<1>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, want_phase, out, ws, s);
+        case 2: return launch_bin<2>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, 0, out, ws, s);
+        case 3: return launch_bin<3>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, 0, out, ws, s);
+        default: return launch_bin<4>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, 0, out, ws, s);
     }
+}
+
+int pyl_pk_bin(const float *const *delta_k, int fields, const int *mas_index, int dims,
+               int ky_lo, int nky, int axis, int want_phase, void *out, void *ws,
+               size_t ws_bytes, pyl_stream_t stream) {
+    return pk_bin_entry(delta_k, fields, mas_index, dims, ky_lo, nky, 0, axis, want_phase, out, ws, ws_bytes, stream);
+}
+
+int pyl_pk_mirrored_rows(int dims, int ky_lo, int ny_lo, int *first_upper) {
+    if (dims <= 0 || ky_lo < 0 || ny_lo < 0 || ky_lo + ny_lo > dims / 2 + 1) return -1;
+    return ny_lo + mirrored_upper_rows(dims, ky_lo, ny_lo, first_upper);
+}
+
+int pyl_pk_bin_mirrored(const float *const *delta_k, int fields, const int *mas_index, int dims,
+                        int ky_lo, int ny_lo, int axis, int want_phase, void *out, void *ws,
+                        size_t ws_bytes, pyl_stream_t stream) {
+    return pk_bin_entry(delta_k, fields, mas_index, dims, ky_lo, ny_lo, 1, axis, want_phase, out, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

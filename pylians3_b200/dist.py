@@ -43,6 +43,26 @@ def split_sizes(n, parts):
     return sizes, offs
 
 
+def mirrored_rows(dims, ky_lo, ny_lo):
+    """Global ky index of the rows a rank stores: the lower rows ky_lo..ky_lo+ny_lo-1, then their mirrors
+    dims-ky (those that are separate modes: ky != 0, ky != Nyquist) in ascending order -- the layout
+    pyl_pk_bin_mirrored expects (include/pyl_b200.h)."""
+    m = dims // 2
+    lower = list(range(ky_lo, ky_lo + ny_lo))
+    upper = sorted(dims - ky for ky in lower if ky != 0 and not (dims % 2 == 0 and ky == m))
+    return lower + upper
+
+
+def _row_runs(rows):
+    """Contiguous runs [a,b) of an ascending-by-pieces index list (at most two for mirrored rows)."""
+    runs, start = [], 0
+    for i in range(1, len(rows) + 1):
+        if i == len(rows) or rows[i] != rows[i - 1] + 1:
+            runs.append((rows[start], rows[i - 1] + 1))
+            start = i
+    return runs
+
+
 class DeviceOps:
     """The compute kernels of the path, bound to libpyl_b200.so (device pointers, current stream)."""
 
@@ -99,8 +119,9 @@ class DeviceOps:
         L.check(self.lib.pyl_fft_slab_x(D.ptr(cols), dims, nky, D.ptr(ws), need, self._s()), "pyl_fft_slab_x")
         return cols
 
-    def bin(self, dk_list, mas_index, dims, axis, want_phase, ky_lo, nky):
-        return PKL.bin_device(dk_list, mas_index, dims, axis, want_phase, ky_lo, nky)
+    def bin(self, dk_list, mas_index, dims, axis, want_phase, ky_lo, ny_lo):
+        """Bins the mirrored slab (rows as in mirrored_rows(dims, ky_lo, ny_lo))."""
+        return PKL.bin_device(dk_list, mas_index, dims, axis, want_phase, ky_lo, ny_lo, mirrored=True)
 
 
 class _Result:
@@ -124,15 +145,34 @@ class SlabContext:
         self.device = torch.device(device)
         self.ops = ops if ops is not None else DeviceOps(self.device)
         self.x_sizes, self.x_offs = split_sizes(self.dims, self.world)
-        self.ky_sizes, self.ky_offs = split_sizes(self.dims, self.world)
+        # ky is distributed in MIRRORED pairs: rank r owns |ky| in [ky_lo, ky_lo+ny_lo) of the half range
+        # 0..N/2 together with the rows N-ky, so that the bin kernel can share geometry between +-ky like on a
+        # whole grid (pyl_pk_bin_mirrored).  ky_rows[r] = global ky index of every row rank r stores, in order.
+        self.ylo_sizes, self.ylo_offs = split_sizes(self.dims // 2 + 1, self.world)
+        self.ky_rows = [mirrored_rows(self.dims, self.ylo_offs[r], self.ylo_sizes[r]) for r in range(self.world)]
         self.x_range = (self.x_offs[self.rank], self.x_offs[self.rank + 1])
-        self.ky_range = (self.ky_offs[self.rank], self.ky_offs[self.rank + 1])
+        self.ky_lo, self.ny_lo = self.ylo_offs[self.rank], self.ylo_sizes[self.rank]
         self.nx = self.x_sizes[self.rank]
-        self.nky = self.ky_sizes[self.rank]
+        self.nky = len(self.ky_rows[self.rank])
+        if min(self.ylo_sizes) < 1:
+            raise ValueError("more ranks than ky rows (dims=%d over %d ranks)" % (dims, self.world))
         if min(self.x_sizes) < 3:
             raise ValueError("slabs thinner than the PCS ghost width (dims=%d over %d ranks)" % (dims, self.world))
         self.dropped = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._plane_owner = None
+        self._scratch = {}
+
+    def _buf(self, name, shape, dtype):
+        """Persistent scratch buffer per (name, shape, dtype): the multi-GB work/transpose buffers are
+        allocated once per context instead of once per step (allocator churn showed up as several ms of
+        run-to-run noise in the transpose)."""
+        key = (name, tuple(shape), dtype)
+        b = self._scratch.get(key)
+        if b is None:
+            for k in [k for k in self._scratch if k[0] == name]:
+                del self._scratch[k]
+            b = self._scratch[key] = torch.empty(shape, dtype=dtype, device=self.device)
+        return b
 
     # ---- helpers ----------------------------------------------------------------------------------
     def new_slab(self):
@@ -201,13 +241,14 @@ class SlabContext:
         if ghosts == 0:
             deposit(slab)
             return
-        work = torch.zeros((self.nx + ghosts, self.dims, self.dims), dtype=torch.float32, device=self.device)
+        work = self._buf("work", (self.nx + ghosts, self.dims, self.dims), torch.float32)
+        work.zero_()
         deposit(work)
         halo_out = work[self.nx:]                        # planes x1 .. x1+ghosts-1 belong to the next rank
         if self.world == 1:
             halo_in = halo_out
         else:
-            halo_in = torch.empty_like(halo_out)
+            halo_in = self._buf("halo_in", halo_out.shape, torch.float32)
             nxt, prv = (self.rank + 1) % self.world, (self.rank - 1) % self.world
             ops = [dist.P2POp(dist.isend, halo_out, nxt, self.group), dist.P2POp(dist.irecv, halo_in, prv, self.group)]
             for req in dist.batch_isend_irecv(ops):
@@ -236,20 +277,24 @@ class SlabContext:
         a = self.ops.fft_yz(slab, N)                                   # (nx, N, nz)
         if P == 1:
             return self.ops.fft_x_(a, N)
-        send = torch.empty(self.nx * N * nz, dtype=a.dtype, device=slab.device)
+        send = self._buf("send", (self.nx * N * nz,), a.dtype)
         send_sizes, off = [], 0                                        # (complex64 on the GPU path)
-        for r in range(P):                                             # pack: ky chunk r of every local plane
-            k0, k1 = self.ky_offs[r], self.ky_offs[r + 1]
-            n = self.nx * (k1 - k0) * nz
-            send[off:off + n].view(self.nx, k1 - k0, nz).copy_(a[:, k0:k1, :])
+        for r in range(P):                                             # pack: the ky rows of rank r, every local plane
+            rows = self.ky_rows[r]
+            n = self.nx * len(rows) * nz
+            dst = send[off:off + n].view(self.nx, len(rows), nz)
+            j = 0
+            for k0, k1 in _row_runs(rows):
+                dst[:, j:j + (k1 - k0), :].copy_(a[:, k0:k1, :])
+                j += k1 - k0
             send_sizes.append(2 * n)
             off += n
         del a
         recv_sizes = [2 * self.x_sizes[s] * self.nky * nz for s in range(P)]
+        # a fresh buffer: the caller keeps the spectrum (XPk holds several at once)
         recv = torch.empty((N, self.nky, nz), dtype=send.dtype, device=slab.device)
         # blocks arrive ordered by source rank = ascending x: the receive buffer IS (N, nky, nz)
         self._all_to_all(torch.view_as_real(recv).view(-1), torch.view_as_real(send).view(-1), recv_sizes, send_sizes)
-        del send
         return self.ops.fft_x_(recv, N)
 
     # ---- spectra -----------------------------------------------------------------------------------
@@ -259,22 +304,30 @@ class SlabContext:
         f64 = out.view(torch.float64)
         for off, n in ((lay.Nm3D, lay.kmax + 1), (lay.Nm1D, lay.kmax_par + 1), (lay.Nm2D, lay.n2d)):
             f64[off:off + n] = out[off:off + n].to(torch.float64)
-        dist.all_reduce(f64, group=self.group)
+        dist.all_reduce(f64[:lay.total_words], group=self.group)     # (kpar/kper scratch behind it is not reduced)
         return f64
 
     def _raw(self, dk_list, mas_index, axis, want_phase):
-        out, lay = self.ops.bin(dk_list, mas_index, self.dims, axis, want_phase, self.ky_range[0], self.nky)
+        out, lay = self.ops.bin(dk_list, mas_index, self.dims, axis, want_phase, self.ky_lo, self.ny_lo)
         f64 = D.to_host_numpy(self._reduce(out, lay))
         words = f64.view(np.int64).copy()
         for off, n in ((lay.Nm3D, lay.kmax + 1), (lay.Nm1D, lay.kmax_par + 1), (lay.Nm2D, lay.n2d)):
             words[off:off + n] = np.rint(f64[off:off + n]).astype(np.int64)
         return PKL.unpack_raw(words, lay)
 
+    def _spectra(self, dk_list, mas_index, axis, want_phase):
+        """bin -> all-reduce -> finalisation.  On GPUs the finalisation runs on the device (pyl_pk_finalize)
+        and only the finished arrays cross PCIe; the CPU stand-ins of the tests finalise on the host."""
+        if self.device.type != "cuda":
+            return PKL._finalize(self._raw(dk_list, mas_index, axis, want_phase), self.BoxSize, self.dims)
+        out, lay = self.ops.bin(dk_list, mas_index, self.dims, axis, want_phase, self.ky_lo, self.ny_lo)
+        f64 = self._reduce(out, lay)
+        return PKL.finalize_device(f64.view(torch.int64), lay, self.BoxSize, self.dims, counts_are_f64=True)
+
     def Pk(self, slab, axis=2, MAS="CIC"):
         """Pk_library.Pk of the slab-distributed field; every rank gets the full result."""
         dk = self.fft(slab)
-        raw = self._raw([dk], [PKL.MAS_function(MAS)], axis, True)
-        o = PKL._finalize(raw, self.BoxSize, self.dims)
+        o = self._spectra([dk], [PKL.MAS_function(MAS)], axis, True)
         r = _Result()
         r.k1D, r.Pk1D, r.Nmodes1D = o["k1D"], o["Pk1D"][:, 0], o["Nmodes1D"]
         r.kpar, r.kper, r.Pk2D, r.Nmodes2D = o["kpar"], o["kper"], o["Pk2D"][:, 0], o["Nmodes2D"]
@@ -289,8 +342,7 @@ class SlabContext:
         if len(slabs) > L.MAX_FIELDS:
             raise ValueError("the distributed XPk bins at most %d fields per call" % L.MAX_FIELDS)
         dk = [self.fft(s) for s in slabs]
-        raw = self._raw(dk, [PKL.MAS_function(m) for m in MAS], axis, False)
-        o = PKL._finalize(raw, self.BoxSize, self.dims)
+        o = self._spectra(dk, [PKL.MAS_function(m) for m in MAS], axis, False)
         r = _Result()
         r.k1D, r.Nmodes1D, r.Pk1D, r.PkX1D = o["k1D"], o["Nmodes1D"], o["Pk1D"], o["PkX1D"]
         r.kpar, r.kper, r.Nmodes2D, r.Pk2D, r.PkX2D = o["kpar"], o["kper"], o["Nmodes2D"], o["Pk2D"], o["PkX2D"]

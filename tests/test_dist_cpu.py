@@ -26,15 +26,16 @@ def base_cell(mas, dist_):
     return np.floor(d64 - 2.0).astype(np.int64) + 1
 
 
-def numpy_bin(dk_list, mas_index, dims, axis, want_phase, ky_lo, nky, lay):
-    """Vectorised restatement of Pk_library.pyx:311-378 / :623-732 on a (dims, nky, nz) ky-window,
-    written into the accumulator layout of pyl_pk_layout_t."""
+def numpy_bin(dk_list, mas_index, dims, axis, want_phase, ky_lo, nky, lay, ky_rows=None):
+    """Vectorised restatement of Pk_library.pyx:311-378 / :623-732 on (dims, nky, nz) arrays holding the
+    global ky rows `ky_rows` (default: the window ky_lo..ky_lo+nky-1), written into the accumulator layout
+    of pyl_pk_layout_t."""
     N, m = dims, dims // 2
     nz = m + 1
     even = (N % 2 == 0)
     F = len(dk_list)
     kxx = np.arange(N)[:, None, None]
-    kyy = (np.arange(nky) + ky_lo)[None, :, None]
+    kyy = (np.arange(nky) + ky_lo if ky_rows is None else np.asarray(ky_rows))[None, :, None]
     kz = np.arange(nz)[None, None, :]
     kx = np.where(kxx > m, kxx - N, kxx)
     ky = np.where(kyy > m, kyy - N, kyy)
@@ -140,9 +141,11 @@ class NumpyOps:
         c[...] = np.fft.fft(c, axis=0)
         return cols
 
-    def bin(self, dk_list, mas_index, dims, axis, want_phase, ky_lo, nky):
+    def bin(self, dk_list, mas_index, dims, axis, want_phase, ky_lo, ny_lo):
+        from pylians3_b200.dist import mirrored_rows
         lay = self._lib.pk_layout(dims, len(dk_list))
-        out = numpy_bin([d.numpy() for d in dk_list], mas_index, dims, axis, want_phase, ky_lo, nky, lay)
+        rows = mirrored_rows(dims, ky_lo, ny_lo)
+        out = numpy_bin([d.numpy() for d in dk_list], mas_index, dims, axis, want_phase, 0, len(rows), lay, rows)
         return torch.from_numpy(out), lay
 
 
@@ -274,3 +277,27 @@ def test_split_sizes():
     from pylians3_b200.dist import split_sizes
     assert split_sizes(10, 3) == ([4, 3, 3], [0, 4, 7, 10])
     assert split_sizes(4096, 8)[0] == [512] * 8
+
+
+@pytest.mark.parametrize("dims,world", [(16, 2), (15, 2), (64, 8), (45, 4), (9, 5)])
+def test_mirrored_ky_rows_partition_every_row_once(dims, world):
+    """The mirrored ky distribution covers 0..dims-1 exactly once, keeps +-ky on one rank, and matches the
+    row count the C ABI reports."""
+    import ctypes
+    from pylians3_b200 import _lib
+    from pylians3_b200.dist import mirrored_rows, split_sizes, _row_runs
+    lib = _lib.load()
+    sizes, offs = split_sizes(dims // 2 + 1, world)
+    seen = []
+    for r in range(world):
+        rows = mirrored_rows(dims, offs[r], sizes[r])
+        first = ctypes.c_int(-1)
+        assert lib.pyl_pk_mirrored_rows(dims, offs[r], sizes[r], ctypes.byref(first)) == len(rows)
+        if len(rows) > sizes[r]:
+            assert first.value == rows[sizes[r]]
+        for ky in rows[:sizes[r]]:
+            if ky != 0 and not (dims % 2 == 0 and ky == dims // 2):
+                assert dims - ky in rows
+        assert len(_row_runs(rows)) <= 2
+        seen += rows
+    assert sorted(seen) == list(range(dims))

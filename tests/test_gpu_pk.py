@@ -236,6 +236,55 @@ def test_slab_windows_add_up_to_the_full_binning(env, oracle):
             assert np.max(np.abs(acc[k] - full[k])) < 1e-10 * scale, k
 
 
+@pytest.mark.parametrize("N,parts", [(40, 3), (33, 4), (64, 8), (18, 10)])
+def test_mirrored_slabs_add_up_to_the_full_binning(env, oracle, N, parts):
+    """The mirrored-ky slab form of the multi-GPU path (pyl_pk_bin_mirrored): every rank holds |ky| rows and
+    their mirrors; partial results sum to the single-GPU result -- counts exactly, sums to float64 round-off,
+    phase included -- for every line of sight, even/odd N, and slabs as thin as one row."""
+    torch, MASL, PKL, _ = env
+    from pylians3_b200.dist import mirrored_rows, split_sizes
+    fields, mas = make_fields(oracle, N, 1, 91 + N)
+    dk = [PKL.fft3d_r2c_device(torch.from_numpy(f).cuda()) for f in fields]
+    mi = [PKL.MAS_function(m) for m in mas]
+    sizes, offs = split_sizes(N // 2 + 1, parts)
+    for axis in (0, 1, 2):
+        full = PKL.bin_fields(dk, mi, N, axis, want_phase=True)
+        acc = None
+        for r in range(parts):
+            rows = torch.tensor(mirrored_rows(N, offs[r], sizes[r]), device="cuda")
+            part = PKL.bin_fields([t[:, rows, :].contiguous() for t in dk], mi, N, axis, want_phase=True,
+                                  ky_lo=offs[r], nky=sizes[r], mirrored=True)
+            acc = part if acc is None else {k: acc[k] + part[k] for k in acc}
+        for k in ("Nm3D", "Nm1D", "Nm2D", "k1D"):
+            assert np.array_equal(acc[k], full[k]), (axis, k)
+        for k in ("k3D", "Pk3D", "Pk1D", "Pk2D", "phase"):
+            scale = float(np.max(np.abs(full[k]))) or 1.0
+            assert np.max(np.abs(acc[k] - full[k])) < 1e-10 * scale, (axis, k)
+
+
+@pytest.mark.parametrize("N,F", [(48, 1), (33, 3), (16, 2)])
+def test_device_finalisation_equals_host_finalisation(env, oracle, N, F):
+    """pyl_pk_finalize (units, averages, (2l+1), 1D area weight on the device) against the vectorised host
+    restatement of Pk_library.pyx:384-418 / :735-791 on the same accumulators: same IEEE operations in the
+    same order -> 1e-15, same NaN pattern (empty 2D bins are 0/0 in the reference too)."""
+    torch, MASL, PKL, _ = env
+    fields, mas = make_fields(oracle, N, F, 300 + N)
+    dk = [PKL.fft3d_r2c_device(torch.from_numpy(f).cuda()) for f in fields]
+    mi = [PKL.MAS_function(m) for m in mas]
+    for axis in (0, 2):
+        # ONE run of the bin kernel (its float64 reductions are not ordered), finalised both ways
+        out, lay = PKL.bin_device(dk, mi, N, axis, F == 1)
+        host = PKL._finalize(PKL.unpack_raw(out.cpu().numpy(), lay), BOX, N)
+        dev = PKL.finalize_device(out, lay, BOX, N)
+        assert set(host) == set(dev)
+        for k in host:
+            a, b = np.asarray(dev[k], dtype=np.float64), np.asarray(host[k], dtype=np.float64)
+            assert a.shape == b.shape, k
+            assert np.array_equal(np.isnan(a), np.isnan(b)), k
+            ok = np.isnan(b) | (np.abs(a - b) <= 1e-15 * np.abs(b))
+            assert np.all(ok), (k, float(np.nanmax(np.abs(a - b))))
+
+
 def test_pk_full_size_properties(env):
     """BASELINE config 2 grid (512^3): exact mode count (Pk_library.pyx:87-99), exact scaling
     Pk(2*delta) = 4*Pk(delta), and shot noise of a uniform-random NGP field ~ L^3/Np."""
