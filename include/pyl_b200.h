@@ -136,6 +136,15 @@ int pyl_fft_slab_yz(const float *slab, float *slab_k, int dims, int nx, void *ws
                     pyl_stream_t stream);
 int pyl_fft_slab_x(float *cols_k, int dims, int nky, void *ws, size_t ws_bytes,
                    pyl_stream_t stream);
+/* Transpose of the distributed transform as one kernel over peer memory (multi-GPU, one node): every row
+ * (ix, ky, :) of the local (nx, dims, dims/2+1) complex64 output of stage 1 is stored directly into the receive
+ * buffer of the rank owning ky -- peer_recv[r] (HOST array of `nranks` DEVICE pointers, peer-mapped; shape
+ * (dims, nky_of_rank[r], dims/2+1)) at [x0+ix][ky_row[ky]][:].  ky_owner / ky_row: DEVICE int32 [dims];
+ * nky_of_rank: HOST int [nranks].  The caller synchronises the ranks before (buffers free) and after (rows
+ * landed).  Replaces "pack + NCCL all-to-all". */
+int pyl_transpose_scatter(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
+                          const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
+                          pyl_stream_t stream);
 /* release every cached cuFFT plan of the calling thread's current device */
 int pyl_fft_clear_plans(void);
 

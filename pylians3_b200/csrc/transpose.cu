@@ -1,0 +1,62 @@
+// K8: slab-FFT transpose as ONE kernel over peer memory (NVLink 5 / NVSwitch), replacing "pack into a send
+// buffer + NCCL all-to-all".
+//
+// After the batched 2D r2c over (y,z) every rank holds (nx_local, N, nz) complex64 for its own x-planes; the
+// 1D transform along x needs, on rank r, ALL x for the ky rows that rank owns (mirrored pairs, see
+// pyl_pk_bin_mirrored).  Each rank therefore writes row (ix, ky, :) straight into the receive buffer of the
+// rank owning ky, at [x0 + ix][stored row of ky][:] -- plain 8-byte stores to peer pointers (P2P mappings of
+// symmetric allocations), coalesced along kz.  No staging copy, no separate collective: the NVLink traffic is
+// issued by the same kernel that reads the FFT output.  The caller brackets the kernel with two device-side
+// barriers (receive buffers free / all rows landed).
+//
+// The reference has no counterpart (single process, FFTW on the whole grid, Pk_library.pyx:117-130).
+#include "common.cuh"
+
+namespace pyl {
+
+constexpr int TR_THREADS = 128;
+constexpr int TR_MAX_RANKS = 16;
+
+struct TransposeArgs {
+    const float2 *src;                 // (nx, N, nz)
+    float2 *peer[TR_MAX_RANKS];        // receive buffer of every rank: (N, nky[r], nz)
+    int nky[TR_MAX_RANKS];
+    const int *ky_owner;               // [N] rank owning global row ky
+    const int *ky_row;                 // [N] stored row index of ky on its owner
+    int N, nz, nx, x0;
+};
+
+__global__ void __launch_bounds__(TR_THREADS) transpose_scatter_kernel(const TransposeArgs A) {
+    const int ky = blockIdx.x, ix = blockIdx.y;
+    const int r = __ldg(A.ky_owner + ky), j = __ldg(A.ky_row + ky);
+    const float2 *src = A.src + ((int64_t)ix * A.N + ky) * A.nz;
+    float2 *dst = A.peer[r] + ((int64_t)(A.x0 + ix) * A.nky[r] + j) * A.nz;
+    for (int kz = threadIdx.x; kz < A.nz; kz += TR_THREADS) dst[kz] = __ldg(src + kz);
+}
+
+}  // namespace pyl
+
+using namespace pyl;
+
+extern "C" int pyl_transpose_scatter(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
+                                     const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
+                                     pyl_stream_t stream) {
+    PYL_REQUIRE(nranks >= 1 && nranks <= TR_MAX_RANKS, "pyl_transpose_scatter: 1..16 ranks");
+    PYL_REQUIRE(dims > 0 && nx >= 0 && x0 >= 0 && x0 + nx <= dims, "pyl_transpose_scatter: bad plane range");
+    if (nx == 0) return PYL_OK;
+    PYL_REQUIRE(slab_k != nullptr && peer_recv != nullptr && nky_of_rank != nullptr && ky_owner != nullptr &&
+                    ky_row != nullptr, "pyl_transpose_scatter: NULL pointer");
+    PYL_REQUIRE(nx <= 65535, "pyl_transpose_scatter: more than 65535 local planes");
+    TransposeArgs A;
+    A.src = reinterpret_cast<const float2 *>(slab_k);
+    for (int r = 0; r < nranks; r++) {
+        PYL_REQUIRE(peer_recv[r] != nullptr, "pyl_transpose_scatter: NULL peer buffer");
+        A.peer[r] = reinterpret_cast<float2 *>(peer_recv[r]);
+        A.nky[r] = nky_of_rank[r];
+    }
+    A.ky_owner = ky_owner; A.ky_row = ky_row;
+    A.N = dims; A.nz = dims / 2 + 1; A.nx = nx; A.x0 = x0;
+    transpose_scatter_kernel<<<dim3((unsigned)dims, (unsigned)nx), TR_THREADS, 0, as_stream(stream)>>>(A);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}

@@ -119,6 +119,14 @@ class DeviceOps:
         L.check(self.lib.pyl_fft_slab_x(D.ptr(cols), dims, nky, D.ptr(ws), need, self._s()), "pyl_fft_slab_x")
         return cols
 
+    def transpose_scatter(self, a, peer_ptrs, nky_of_rank, ky_owner, ky_row, dims, x0):
+        """Rows of the local (nx, dims, nz) stage-1 output -> receive buffers of their owner ranks (peer stores)."""
+        P = len(peer_ptrs)
+        ptrs = (ctypes.c_void_p * P)(*[int(p) for p in peer_ptrs])
+        nky = (ctypes.c_int * P)(*[int(n) for n in nky_of_rank])
+        L.check(self.lib.pyl_transpose_scatter(D.ptr(a), ptrs, nky, D.ptr(ky_owner), D.ptr(ky_row), dims,
+                                               a.shape[0], int(x0), P, self._s()), "pyl_transpose_scatter")
+
     def bin(self, dk_list, mas_index, dims, axis, want_phase, ky_lo, ny_lo):
         """Bins the mirrored slab (rows as in mirrored_rows(dims, ky_lo, ny_lo))."""
         return PKL.bin_device(dk_list, mas_index, dims, axis, want_phase, ky_lo, ny_lo, mirrored=True)
@@ -161,6 +169,44 @@ class SlabContext:
         self.dropped = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._plane_owner = None
         self._scratch = {}
+        # transpose over peer memory (one kernel storing into the owners' receive buffers) where symmetric
+        # memory is available: CUDA, one node.  PYL_TRANSPOSE=nccl keeps the pack + all-to-all path.
+        self._peer = None
+        self._peer_slots = {}
+        import os
+        if self.device.type == "cuda" and self.world > 1 and os.environ.get("PYL_TRANSPOSE", "peer") == "peer":
+            self._peer = self._setup_peer()
+
+    def _setup_peer(self):
+        try:
+            import torch.distributed._symmetric_memory as symm
+            grp = self.group if self.group is not None else dist.group.WORLD
+            try:
+                symm.enable_symm_mem_for_group(grp.group_name)
+            except Exception:
+                pass
+            owner = torch.empty(self.dims, dtype=torch.int32)
+            row = torch.empty(self.dims, dtype=torch.int32)
+            for r, rows in enumerate(self.ky_rows):
+                idx = torch.tensor(rows, dtype=torch.long)
+                owner[idx] = r
+                row[idx] = torch.arange(len(rows), dtype=torch.int32)
+            return {"symm": symm, "group": grp, "owner": owner.to(self.device), "row": row.to(self.device),
+                    "nky": [len(r) for r in self.ky_rows]}
+        except Exception as e:                                   # symmetric memory unusable: NCCL all-to-all
+            print("pylians3_b200.dist: peer-memory transpose unavailable (%s); using NCCL all-to-all" % e)
+            return None
+
+    def _peer_slot(self, slot):
+        """Symmetric receive buffer number `slot` (one per field that must stay alive at the same time)."""
+        s = self._peer_slots.get(slot)
+        if s is None:
+            symm = self._peer["symm"]
+            n = self.dims * max(self._peer["nky"]) * self.nz
+            buf = symm.empty(n, dtype=torch.complex64, device=self.device)
+            hdl = symm.rendezvous(buf, self._peer["group"])
+            s = self._peer_slots[slot] = (buf, hdl, [int(p) for p in hdl.buffer_ptrs])
+        return s
 
     def _buf(self, name, shape, dtype):
         """Persistent scratch buffer per (name, shape, dtype): the multi-GB work/transpose buffers are
@@ -272,11 +318,21 @@ class SlabContext:
         return slab
 
     # ---- distributed r2c: (nx_local, N, N) real -> (N, nky_local, nz) complex ---------------------
-    def fft(self, slab):
+    def fft(self, slab, slot=0):
+        """(nx_local, N, N) real -> (N, nky_local, nz) complex.  With the peer-memory transpose the result lives
+        in symmetric receive buffer `slot` and stays valid until the next fft() with the same slot."""
         N, nz, P = self.dims, self.nz, self.world
         a = self.ops.fft_yz(slab, N)                                   # (nx, N, nz)
         if P == 1:
             return self.ops.fft_x_(a, N)
+        if self._peer is not None:
+            buf, hdl, ptrs = self._peer_slot(slot)
+            hdl.barrier(channel=0)                                     # every rank is done with this slot
+            self.ops.transpose_scatter(a, ptrs, self._peer["nky"], self._peer["owner"], self._peer["row"], N,
+                                       self.x_range[0])
+            hdl.barrier(channel=0)                                     # every row has landed
+            del a
+            return self.ops.fft_x_(buf[:N * self.nky * nz].view(N, self.nky, nz), N)
         send = self._buf("send", (self.nx * N * nz,), a.dtype)
         send_sizes, off = [], 0                                        # (complex64 on the GPU path)
         for r in range(P):                                             # pack: the ky rows of rank r, every local plane
@@ -341,7 +397,7 @@ class SlabContext:
             raise TypeError("MAS must be a list with one scheme per field")
         if len(slabs) > L.MAX_FIELDS:
             raise ValueError("the distributed XPk bins at most %d fields per call" % L.MAX_FIELDS)
-        dk = [self.fft(s) for s in slabs]
+        dk = [self.fft(s, slot=i) for i, s in enumerate(slabs)]
         o = self._spectra(dk, [PKL.MAS_function(m) for m in MAS], axis, False)
         r = _Result()
         r.k1D, r.Nmodes1D, r.Pk1D, r.PkX1D = o["k1D"], o["Nmodes1D"], o["Pk1D"], o["PkX1D"]

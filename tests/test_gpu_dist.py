@@ -21,8 +21,9 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, N, q):
+def _worker(rank, world, port, N, q, transpose="peer"):
     try:
+        os.environ["PYL_TRANSPOSE"] = transpose
         import torch
         import torch.distributed as dist
         sys.path.insert(0, ROOT)
@@ -35,6 +36,7 @@ def _worker(rank, world, port, N, q):
         from pylians3_b200 import dist as PD
         from oracle import cpu as O
         ctx = PD.SlabContext(N, BOX)
+        assert (ctx._peer is not None) == (transpose == "peer"), "peer-memory transpose not active"
         pos, W = make_particles(77, 4 * N ** 3, True)
         mine = slice(rank, None, world)
         x0, x1 = ctx.x_range
@@ -79,8 +81,11 @@ def _worker(rank, world, port, N, q):
         q.put((rank, "fail", traceback.format_exc()))
 
 
-@pytest.mark.parametrize("world,N", [(2, 64), (2, 45), (4, 64), (4, 45), (8, 64)])
-def test_multi_gpu_slab_pipeline(oracle, world, N):
+@pytest.mark.parametrize("world,N,transpose", [(2, 64, "peer"), (2, 45, "peer"), (2, 45, "nccl"), (4, 64, "peer"),
+                                               (4, 45, "peer"), (8, 64, "peer")])
+def test_multi_gpu_slab_pipeline(oracle, world, N, transpose):
+    """transpose="peer": the slab-FFT transpose is one kernel storing into the owners' symmetric receive buffers
+    over NVLink (pyl_transpose_scatter); "nccl": pack + all_to_all_single."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
@@ -88,7 +93,7 @@ def test_multi_gpu_slab_pipeline(oracle, world, N):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, N, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, q, transpose)) for r in range(world)]
     for p in procs:
         p.start()
     out = [q.get(timeout=600) for _ in procs]
