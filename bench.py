@@ -33,6 +33,10 @@ MAS = "CIC"
 AXIS = 0
 # weak-scaling ladder: ~512^3 particles and cells per GPU, FFT-friendly sizes (2^a 5^b)
 GRID_FOR_GPUS = {1: 512, 2: 640, 4: 800, 8: 1024}
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one MA(CIC) call at 512^3/512^3 from the
+# `ncu --set full` capture summarised in profiles/r1_tiled_deposit_cic_final.md: tile_count 0.54 GB +
+# tile_scatter 3.90 GB + tile_deposit 3.21 GB
+NCU_DEPOSIT_TRAFFIC = {("CIC", 512): 7.65e9}
 
 
 def measured_peak_hbm():
@@ -373,7 +377,10 @@ def run_ours(args):
         alg_bytes = npart * 12 + 8 * grid_n ** 3          # positions once + grid RMW once
         achieved = alg_bytes / (ma_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "deposit (%s, %s)" % (MAS, "pyl_deposit"), "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": NCU_DEPOSIT_TRAFFIC.get((MAS, grid_n)),
+                    "traffic_source": "profiles/r1_tiled_deposit_cic_final.md (ncu --set full, per MA call)",
+                    "kernels": "tile_count + tile_scatter + tile_deposit (one pyl_deposit call)",
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": ma_ms, "share_of_step": ma_ms / ms_step}
     pk = pk_holder["pk"]

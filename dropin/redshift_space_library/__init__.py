@@ -1,0 +1,11 @@
+"""`import redshift_space_library as RSL` resolving to the B200-native implementation.
+
+Put this directory (dropin/) on PYTHONPATH ahead of the Pylians3 install; see INTEGRATION.md."""
+import os as _os
+import sys as _sys
+
+_root = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+if _root not in _sys.path:
+    _sys.path.insert(0, _root)
+from pylians3_b200.redshift_space_library import *  # noqa: E402,F401,F403
+from pylians3_b200.redshift_space_library import pos_redshift_space  # noqa: E402,F401

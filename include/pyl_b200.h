@@ -12,6 +12,7 @@
  *                                             FLOAT BoxSize, int threads)
  *   library/MAS_library/MAS_library.pyx:72-80 MA()'s dispatch to NGP/CIC/TSC/PCS(+W)
  *   library/MAS_library/MAS_library.pyx:558-599 CIC_interp(density, BoxSize, pos, den)
+ *   library/redshift_space_library/redshift_space_library.pyx:29-46 pos_redshift_space(...)
  *   library/Pk_library/Pk_library.pyx:117-130 FFT3Dr_f(a, threads)
  *   library/Pk_library/Pk_library.pyx:311-378 Pk.__init__ hot loop   (no native ABI exists)
  *   library/Pk_library/Pk_library.pyx:623-732 XPk.__init__ hot loop  (no native ABI exists)
@@ -104,6 +105,11 @@ int pyl_stencil_base_plane(int mas, const float *pos, int64_t particles, int dim
  * Replaces MAS_library.pyx:558-599 (CIC_interp). */
 int pyl_cic_interp(const float *density, int dims, float BoxSize, const float *pos, int64_t particles,
                    float *den, pyl_stream_t stream);
+
+/* Real -> redshift space IN PLACE: pos[i][axis] += vel[i][axis]*(1+redshift)/Hubble, wrapped into [0,BoxSize].
+ * pos, vel: DEVICE float32 [particles][3].  Replaces redshift_space_library.pyx:29-46 (pos_redshift_space). */
+int pyl_pos_redshift_space(float *pos, const float *vel, int64_t particles, float BoxSize, float Hubble,
+                           float redshift, int axis, pyl_stream_t stream);
 
 /* x[i] /= divisor, IEEE float32 division: the 2D renormalisation `number2 /= 2.0|3.0|4.0`
  * of MAS_library.pyx:90-107 */

@@ -9,6 +9,8 @@ git-ignored but still travels to the GPU box):
 
   oracle/_ref/MAS_library/MAS_library*.so  <- library/MAS_library/MAS_library.pyx + MAS_c.c
   oracle/_ref/Pk_library/Pk_library*.so    <- library/Pk_library/Pk_library.pyx
+  oracle/_ref/redshift_space_library/redshift_space_library*.so
+                                           <- library/redshift_space_library/redshift_space_library.pyx
   oracle/_ref/omp/MAS_library*.so          <- same MAS sources, with -fopenmp at compile
                                               time (NON-default build: the reference's
                                               setup.py:22 typo drops -fopenmp)
@@ -66,7 +68,8 @@ def build(force=False):
     mas_so = os.path.join(OUT, "MAS_library", "MAS_library" + suf)
     pk_so = os.path.join(OUT, "Pk_library", "Pk_library" + suf)
     omp_so = os.path.join(OUT, "omp", "MAS_library" + suf)
-    have = all(os.path.exists(p) for p in (mas_so, pk_so, omp_so))
+    rsd_so = os.path.join(OUT, "redshift_space_library", "redshift_space_library" + suf)
+    have = all(os.path.exists(p) for p in (mas_so, pk_so, omp_so, rsd_so))
     if have and not force:
         return True
     if not available():
@@ -81,6 +84,10 @@ def build(force=False):
     _compile([mas_c, os.path.join(mas_dir, "MAS_c.c")], mas_so, [mas_dir])
     _compile([mas_c, os.path.join(mas_dir, "MAS_c.c")], omp_so, [mas_dir], extra=["-fopenmp"])
     _compile([pk_c], pk_so, [pk_dir])
+    rsd_dir = os.path.join(REF, "library", "redshift_space_library")
+    rsd_c = os.path.join(gen, "redshift_space_library.c")
+    _cythonize(os.path.join(rsd_dir, "redshift_space_library.pyx"), rsd_c, rsd_dir)
+    _compile([rsd_c], rsd_so, [rsd_dir])
     shutil.rmtree(gen, ignore_errors=True)   # generated C is large; keep only the .so files
     return True
 

@@ -34,6 +34,9 @@ def lib():
         L.oracle_ma.restype = None
         L.oracle_cic_interp.argtypes = [fp, ctypes.c_int, ctypes.c_float, fp, ctypes.c_long, fp]
         L.oracle_cic_interp.restype = None
+        L.oracle_pos_redshift_space.argtypes = [fp, fp, ctypes.c_long, ctypes.c_float, ctypes.c_float,
+                                                ctypes.c_float, ctypes.c_int]
+        L.oracle_pos_redshift_space.restype = None
         L.oracle_pk_bin.argtypes = [fp, ctypes.c_int, ctypes.c_int, ip, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_int, ctypes.c_int] + [dp] * 12
         L.oracle_pk_bin.restype = None
@@ -71,6 +74,14 @@ def CIC_interp(density, BoxSize, pos, den):
     assert den.dtype == np.float32 and den.flags.c_contiguous
     pos = np.ascontiguousarray(pos, dtype=np.float32)
     lib().oracle_cic_interp(_fp(density), density.shape[0], np.float32(BoxSize), _fp(pos), pos.shape[0], _fp(den))
+
+
+def pos_redshift_space(pos, vel, BoxSize, Hubble, redshift, axis):
+    """redshift_space_library.pyx:29-46: pos[:,axis] += (1+z)/H * vel[:,axis], wrapped into the box, IN PLACE."""
+    assert pos.dtype == np.float32 and pos.flags.c_contiguous and pos.shape[1] == 3
+    assert vel.dtype == np.float32 and vel.flags.c_contiguous and vel.shape == pos.shape
+    lib().oracle_pos_redshift_space(_fp(pos), _fp(vel), pos.shape[0], np.float32(BoxSize), np.float32(Hubble),
+                                    np.float32(redshift), int(axis))
 
 
 def frequencies(BoxSize, dims):

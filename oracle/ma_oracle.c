@@ -17,6 +17,7 @@
  *   2D mode    : library/MAS_library/MAS_library.pyx:84-110 (third axis pinned to cell 0
  *                with unit weight, so each particle lands 1/2/3/4 times in the plane)
  *   CIC_interp : library/MAS_library/MAS_library.pyx:558-599 (grid -> particle gather)
+ *   pos_redshift_space : library/redshift_space_library/redshift_space_library.pyx:29-46
  *
  * The serial particle order of the reference is kept, so float32 accumulation order is the
  * same as the reference's.
@@ -149,5 +150,21 @@ void oracle_cic_interp(const float *density, int dims, float BoxSize, const floa
                  DEN(iu[0], id[1], id[2]) * u[0] * d[1] * d[2] + DEN(iu[0], id[1], iu[2]) * u[0] * d[1] * u[2] +
                  DEN(iu[0], iu[1], id[2]) * u[0] * u[1] * d[2] + DEN(iu[0], iu[1], iu[2]) * u[0] * u[1] * u[2];
 #undef DEN
+    }
+}
+
+/* Real -> redshift space along one axis, library/redshift_space_library/redshift_space_library.pyx:29-46:
+ * factor = (float)((1.0 + z)/H) ; pos = pos + vel*factor (ONE rounding: the reference binary, built with
+ * -O3 -ffast-math for an FMA-capable target, contracts it into a fused multiply-add -- checked against the
+ * compiled reference) ; while pos < 0: pos += BoxSize ; if pos > BoxSize: pos = fmodf(pos, BoxSize). */
+void oracle_pos_redshift_space(float *pos, const float *vel, long particles, float BoxSize, float Hubble,
+                               float redshift, int axis)
+{
+    const float factor = (float)((1.0 + (double)redshift) / (double)Hubble);
+    for (long i = 0; i < particles; i++) {
+        float p = fmaf(vel[i * 3 + axis], factor, pos[i * 3 + axis]);
+        while (p < 0.0f) p += BoxSize;
+        if (p > BoxSize) p = fmodf(p, BoxSize);
+        pos[i * 3 + axis] = p;
     }
 }

@@ -45,6 +45,16 @@ def ref_MASL(omp=False):
     return _cache[key]
 
 
+def ref_RSL():
+    """The reference's redshift_space_library extension (pos_redshift_space)."""
+    if "RSL" not in _cache:
+        path = _find("redshift_space_library", "redshift_space_library")
+        if path is None:
+            raise ImportError("oracle/_ref not built: run `python oracle/build_ref.py` where /root/reference exists")
+        _cache["RSL"] = _load("ref.redshift_space_library", path)
+    return _cache["RSL"]
+
+
 def ref_PKL():
     """The reference's Pk_library extension (Pk, XPk, ...), FFT through the pyfftw shim."""
     if "PKL" not in _cache:

@@ -45,6 +45,7 @@ PROTOTYPES = {
     "pyl_deposit_slab": (_i, [_i, _vp, _vp, _vp, _i64, _i, _f, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "pyl_stencil_base_plane": (_i, [_i, _vp, _i64, _i, _f, _vp, _vp]),
     "pyl_cic_interp": (_i, [_vp, _i, _f, _vp, _i64, _vp, _vp]),
+    "pyl_pos_redshift_space": (_i, [_vp, _vp, _i64, _f, _f, _f, _i, _vp]),
     "pyl_divide_inplace": (_i, [_vp, _i64, _f, _vp]),
     "pyl_scale_inplace": (_i, [_vp, _i64, _f, _vp]),
     "pyl_affine_inplace": (_i, [_vp, _i64, _f, _f, _vp]),

@@ -51,3 +51,34 @@ extern "C" int pyl_cic_interp(const float *density, int dims, float BoxSize, con
     PYL_LAUNCH_CHECK();
     return PYL_OK;
 }
+
+// ---- real -> redshift space along one axis ------------------------------------------------------------------
+// Replaces library/redshift_space_library/redshift_space_library.pyx:29-46 (the step before MA in
+// Pk_library/Pk_snapshot.py:60-64 and MAS_gadget.py): pos[:,axis] += vel[:,axis]*(1+z)/H, wrapped into the box,
+// in place.  The reference binary fuses the multiply-add (one rounding), hence fmaf.
+namespace pyl {
+__global__ void __launch_bounds__(256) redshift_space_kernel(float *__restrict__ pos, const float *__restrict__ vel,
+                                                             int64_t particles, float BoxSize, float factor,
+                                                             int axis) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= particles) return;
+    float p = fmaf(__ldg(vel + i * 3 + axis), factor, pos[i * 3 + axis]);
+    if (isfinite(p)) {                       // (the reference would loop forever on -inf; leave non-finite as is)
+        while (p < 0.0f) p = __fadd_rn(p, BoxSize);
+        if (p > BoxSize) p = fmodf(p, BoxSize);
+    }
+    pos[i * 3 + axis] = p;
+}
+}  // namespace pyl
+
+extern "C" int pyl_pos_redshift_space(float *pos, const float *vel, int64_t particles, float BoxSize, float Hubble,
+                                      float redshift, int axis, pyl_stream_t stream) {
+    PYL_REQUIRE(particles >= 0 && BoxSize > 0.0f && axis >= 0 && axis <= 2, "pyl_pos_redshift_space: bad arguments");
+    if (particles == 0) return PYL_OK;
+    PYL_REQUIRE(pos != nullptr && vel != nullptr, "pyl_pos_redshift_space: NULL pointer");
+    const float factor = (float)((1.0 + (double)redshift) / (double)Hubble);   // :37, double expression -> float
+    redshift_space_kernel<<<(unsigned)((particles + 255) / 256), 256, 0, as_stream(stream)>>>(pos, vel, particles,
+                                                                                            BoxSize, factor, axis);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}

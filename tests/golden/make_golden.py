@@ -9,6 +9,7 @@ The fixtures are small on purpose (a few hundred kB) and are committed; the GPU 
 Reference entry points exercised:
   MAS_library.MA            library/MAS_library/MAS_library.pyx:57-112
   MAS_library.CIC_interp    library/MAS_library/MAS_library.pyx:558-599
+  redshift_space_library.pos_redshift_space  library/redshift_space_library/redshift_space_library.pyx:29-46
   Pk_library.Pk             library/Pk_library/Pk_library.pyx:263-420
   Pk_library.XPk            library/Pk_library/Pk_library.pyx:529-793
 (the FFT inside Pk/XPk goes through oracle/pyfftw_shim -> scipy pocketfft, float32)
@@ -79,6 +80,19 @@ def main():
         den = np.zeros(len(pos), np.float32)
         M.CIC_interp(field, BOX, pos, den)
         out["interp_N%d_pos" % N], out["interp_N%d_field" % N], out["interp_N%d_den" % N] = pos, field, den
+    # pos_redshift_space (redshift_space_library.pyx:29-46): ordinary velocities plus a few that cross the box
+    # several times in both directions (the "neutrino" case the reference comments on)
+    R = ref_loader.ref_RSL()
+    rng = np.random.default_rng(555)
+    pos = rng.random((4000, 3), dtype=np.float32) * np.float32(BOX)
+    pos[:len(EDGE)] = EDGE
+    vel = (rng.standard_normal((4000, 3)) * 2500.0).astype(np.float32)
+    vel[:40] *= 400.0
+    out["rsd_pos"], out["rsd_vel"] = pos, vel
+    for axis in (0, 1, 2):
+        p = pos.copy()
+        R.pos_redshift_space(p, vel, BOX, 171.5, 0.5, axis)
+        out["rsd_out_a%d" % axis] = p
     np.savez_compressed(os.path.join(HERE, "ma_golden.npz"), **out)
 
     # ---- Pk / XPk
