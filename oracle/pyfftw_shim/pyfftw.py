@@ -6,8 +6,15 @@ and `FFTW(a_in, a_out, axes, flags, direction, threads)` called as `plan(a_in, a
 pyfftw / FFTW3 are not installed in this image (unpinned dependency, reference setup.py:137),
 so the compiled reference's *own* deconvolution + binning code is driven through this shim,
 which performs the transform with scipy's pocketfft (native single precision for float32
-input, like FFTW's float interface).  FFTW's backward transforms are unnormalised, so the
-shim multiplies irfftn by the number of real-space points.
+input, like FFTW's float interface).
+
+Backward transforms: pyfftw's `FFTW.__call__(input_array, output_array, normalise_idft=True)`
+scales an inverse transform by 1/N by default, and the reference calls the plan with the two
+arrays only (Pk_library.pyx:149-163) -- so IFFT3Dr_f returns the NORMALISED inverse.  The
+reference's own arithmetic confirms it: Xi (Pk_library.pyx:2221, 2276) multiplies the inverse
+transform of |delta_k|^2 by one further 1/dims^3, which is the correlation function only if
+the inverse already carried its 1/dims^3.  scipy's irfftn/ifftn are normalised the same way,
+so the shim returns them unscaled.
 """
 import numpy as np
 import scipy.fft as _sfft
@@ -36,8 +43,8 @@ class FFTW:
         else:
             if self.real_out:
                 s = [a_out.shape[ax] for ax in self.axes]
-                a_out[...] = _sfft.irfftn(a_in, s=s, axes=self.axes, workers=w) * float(np.prod(s))
+                a_out[...] = _sfft.irfftn(a_in, s=s, axes=self.axes, workers=w)
             else:
                 s = [a_out.shape[ax] for ax in self.axes]
-                a_out[...] = _sfft.ifftn(a_in, axes=self.axes, workers=w) * float(np.prod(s))
+                a_out[...] = _sfft.ifftn(a_in, axes=self.axes, workers=w)
         return a_out

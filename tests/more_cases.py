@@ -1,0 +1,91 @@
+"""Shared driver for the sibling estimators (Pk_plane ... XXi): run every entry point of an implementation
+`impl` (a namespace with the reference's names: the CPU oracle `oracle.cpu_more`, or the CUDA product
+`pylians3_b200.Pk_library`) on the seeded inputs of tests/golden/make_golden_more.py and return the results
+under the golden file's keys."""
+import contextlib
+import importlib.util
+import io
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BOX = 1000.0
+_spec = importlib.util.spec_from_file_location("make_golden_more", os.path.join(HERE, "golden", "make_golden_more.py"))
+_gen = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_gen)
+inputs = _gen.inputs
+SIZES = _gen.SIZES
+
+
+def run_all(impl, N, I=None):
+    I = inputs(N) if I is None else I
+    t = "N%d_" % N
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = impl.Pk_plane(I["img1"], BOX, "CIC", 1, False)
+        out.update({t + "plane_k": r.k, t + "plane_Pk": r.Pk, t + "plane_Nm": r.Nmodes})
+        r = impl.XPk_plane(I["img1"], I["img2"], BOX, "CIC", "PCS", 1)
+        out.update({t + "xplane_k": r.k, t + "xplane_Pk": r.Pk, t + "xplane_XPk": r.XPk, t + "xplane_Nm": r.Nmodes,
+                    t + "xplane_r": r.r})
+        for axis in (0, 1, 2):
+            a = t + "imag_a%d_" % axis
+            r = impl.XPk_imag([I["f1"], I["f2"], I["f3"]], BOX, axis, ["CIC", "NGP", "PCS"], 1)
+            for n in ("k3D", "Nmodes3D", "Pk", "XPk", "k1D", "Nmodes1D", "Pk1D", "PkX1D", "Nmodes2D", "Pk2D", "PkX2D"):
+                out[a + n] = np.asarray(getattr(r, n))
+            r = impl.XPk_2D(I["f1"], I["f2"], BOX, axis, "TSC", "CIC", 1)
+            for i, n in enumerate(("kpar", "kper", "Pk1", "Pk2", "PkX", "Nm")):
+                out[t + "x2d_a%d_%s" % (axis, n)] = np.asarray(r[i])
+            r = impl.Xi(I["d1"], BOX, "CIC", axis, 1)
+            out.update({t + "xi_a%d_r" % axis: r.r3D, t + "xi_a%d_xi" % axis: r.xi, t + "xi_a%d_Nm" % axis: r.Nmodes3D})
+        r = impl.XXi(I["d1"], I["d2"], BOX, ["CIC", "PCS"], 2, 1)
+        out.update({t + "xxi_r": r.r3D, t + "xxi_xi": r.xi, t + "xxi_Nm": r.Nmodes3D})
+        r = impl.Pk_theta(I["Vx1"], I["Vy1"], I["Vz1"], BOX, 2, "CIC", 1)
+        out.update({t + "theta_k": r[0], t + "theta_Pk": r[1], t + "theta_Nm": r[2]})
+        V = [I[n].copy() for n in ("Vx1", "Vy1", "Vz1")]
+        r = impl.XPk_dv(I["d1"], V[0], V[1], V[2], BOX, 2, "TSC", 1)
+        for i, n in enumerate(("k", "Pk1", "Pk2", "PkX", "Nm")):
+            out[t + "dv_" + n] = np.asarray(r[i])
+        out[t + "dv_Vx_after"] = V[0]
+        V = [I[n].copy() for n in ("Vx1", "Vy1", "Vz1", "Vx2", "Vy2", "Vz2")]
+        r = impl.XPk_vv(I["d1"], V[0], V[1], V[2], I["d2"], V[3], V[4], V[5], BOX, 2, "PCS", 1)
+        for i, n in enumerate(("k", "Pk1", "Pk2", "PkX", "Nm")):
+            out[t + "vv_" + n] = np.asarray(r[i])
+        out[t + "cmas"] = np.asarray(impl.correct_MAS(I["d1"].copy(), BOX, "PCS", 1))
+        r = impl.expected_Pk(I["k_in"], I["Pk_in"], BOX, N, 300)
+        out.update({t + "exp_k": np.asarray(r[0]), t + "exp_Pk": np.asarray(r[1]), t + "exp_Nm": np.asarray(r[2])})
+    return out
+
+
+def compare(got, ref, tol, exact_counts=True, ktol=1e-12):
+    """Every key of `got` against `ref`.  Counts (…Nm, …Nmodes*) bit-exact; wavenumbers / radii to `ktol`;
+    everything else to `tol` relative to max(|value|, 1e-6 * the array's largest |value|) -- cross terms and
+    high multipoles are sums of signed terms, so a per-element relative bar is meaningless where they cancel."""
+    bad = []
+    for key, g in got.items():
+        r = np.asarray(ref[key], dtype=np.float64)
+        g = np.asarray(g, dtype=np.float64)
+        if g.shape != r.shape:
+            bad.append((key, "shape", g.shape, r.shape))
+            continue
+        name = key.split("_")[-1]
+        if name in ("Nm", "Nmodes3D", "Nmodes1D", "Nmodes2D"):
+            if not np.array_equal(g, r):
+                bad.append((key, "counts differ"))
+            continue
+        nan_g, nan_r = np.isnan(g), np.isnan(r)
+        if not np.array_equal(nan_g, nan_r):
+            bad.append((key, "NaN pattern"))
+            continue
+        if r.size == 0 or nan_r.all():
+            continue
+        t = ktol if name in ("k", "k3D", "k1D", "kpar", "kper", "r") and "xplane_r" not in key else tol
+        if "exp_k" in key:
+            t = max(t, 1e-6)          # float32 k in the reference
+        scale = np.nanmax(np.abs(r))
+        den = np.maximum(np.abs(r), 1e-6 * scale if t > 1e-10 else 0.0)
+        den = np.where(den == 0, 1.0, den)
+        e = float(np.nanmax(np.abs(g - r) / den))
+        if not e < t:
+            bad.append((key, e, t))
+    return bad

@@ -1,0 +1,35 @@
+"""CPU: pin the oracle's restatement of the sibling estimators (oracle/cpu_more.py over pk_oracle.c) against
+tests/golden/pk_more_golden.npz, the outputs of the compiled, unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+
+import more_cases as MC
+from conftest import GOLDEN
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return dict(np.load(os.path.join(GOLDEN, "pk_more_golden.npz")))
+
+
+@pytest.mark.parametrize("N", MC.SIZES)
+def test_sibling_oracle_matches_reference(oracle, golden, N):
+    from oracle import cpu_more
+    got = MC.run_all(cpu_more, N)
+    assert set(got) == {k for k in golden if k.startswith("N%d_" % N)}
+    # same transform (pocketfft) on both sides: only float64 association / float32 FMA contraction differ
+    bad = MC.compare(got, golden, tol=2e-6)
+    assert not bad, bad
+
+
+def test_inverse_transform_is_normalised(oracle, golden):
+    """correct_MAS with MAS=None is FFT -> IFFT: the reference returns the field itself, which pins the
+    normalised inverse the oracle (and the product) must use (see oracle/pyfftw_shim)."""
+    from oracle import cpu_more
+    I = MC.inputs(12)
+    back = cpu_more.correct_MAS(I["d1"].copy(), MC.BOX, "None", 1)
+    assert np.max(np.abs(back - I["d1"])) < 1e-5 * np.abs(I["d1"]).max()
+    # and the reference's deconvolved field is of the same order as the input, not dims^3 larger
+    assert np.abs(golden["N12_cmas"]).max() < 10 * np.abs(I["d1"]).max()
