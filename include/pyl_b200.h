@@ -16,6 +16,11 @@
  *   library/Pk_library/Pk_library.pyx:117-130 FFT3Dr_f(a, threads)
  *   library/Pk_library/Pk_library.pyx:311-378 Pk.__init__ hot loop   (no native ABI exists)
  *   library/Pk_library/Pk_library.pyx:623-732 XPk.__init__ hot loop  (no native ABI exists)
+ *   library/Pk_library/Pk_library.pyx:149-163 IFFT3Dr_f(a, threads)
+ *   library/Pk_library/Pk_library.pyx:470-499, 905-1016, 1151-1200, 1273-1316, 1386-1432, 1515-1568,
+ *       1909-1929, 2004-2037, 2198-2267, 2335-2412   the loops of Pk_plane, XPk_imag, XPk_plane, Pk_theta,
+ *       XPk_dv, XPk_vv, correct_MAS, expected_Pk, Xi, XXi (section 5; no native ABI exists)
+ *   library/smoothing_library/smoothing_library.pyx:227-232 field_smoothing's mode loop
  *
  * Ownership: all device pointers are BORROWED.  The device-pointer entry points never
  * allocate: scratch memory is passed in (`ws`, sized by the matching *_workspace_bytes
@@ -151,6 +156,13 @@ int pyl_fft_slab_x(float *cols_k, int dims, int nky, void *ws, size_t ws_bytes,
 int pyl_transpose_scatter(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
                           const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
                           pyl_stream_t stream);
+/* Unnormalised inverse c2r, (dims,dims,dims/2+1) complex64 -> (dims,dims,dims) float32, out of place; cuFFT may
+ * OVERWRITE delta_k.  The reference's IFFT3Dr_f (Pk_library.pyx:149-163) returns the NORMALISED inverse (pyfftw
+ * scales inverse transforms by 1/N^3 by default): callers follow with pyl_scale_inplace(delta, N^3, 1/N^3) or
+ * pass that factor to the consumer (pyl_shell_bin's `scale`). */
+size_t pyl_fft_c2r_workspace_bytes(int dims);
+int pyl_fft_c2r(float *delta_k /* interleaved re,im */, float *delta, int dims, void *ws, size_t ws_bytes,
+                pyl_stream_t stream);
 /* release every cached cuFFT plan of the calling thread's current device */
 int pyl_fft_clear_plans(void);
 
@@ -183,11 +195,15 @@ size_t pyl_pk_bin_workspace_bytes(int dims, int fields);
  *              deconvolution, :351-352, is an internal temporary).
  *   mas_index: HOST array, per field 0..4 = None,NGP,CIC,TSC,PCS (Pk_library.pyx:72-78)
  *   axis     : line of sight 0|1|2
- *   want_phase: accumulate Pkphase of field 0 (Pk only; Pk_library.pyx:358,377)
+ *   want_phase: flag word.  PYL_PK_PHASE: accumulate Pkphase of field 0 (Pk only; Pk_library.pyx:358,377).
+ *              PYL_PK_CROSS_IMAG: the cross terms are imag_i*real_j - real_i*imag_j (XPk_imag,
+ *              Pk_library.pyx:1000-1001) instead of real_i*real_j + imag_i*imag_j (XPk, :716-717)
  *   out      : DEVICE buffer of layout.total_words 8-byte words; zeroed by the call
  * Applies the Hermitian-duplicate skip rule (:324-327), the float32 window factor (:351)
  * and the float64 accumulation of the reference. */
 #define PYL_MAX_FIELDS 4
+#define PYL_PK_PHASE 1
+#define PYL_PK_CROSS_IMAG 2
 int pyl_pk_bin(const float *const *delta_k, int fields, const int *mas_index, int dims,
                int ky_lo, int nky, int axis, int want_phase, void *out, void *ws,
                size_t ws_bytes, pyl_stream_t stream);
@@ -212,6 +228,62 @@ int pyl_pk_mirrored_rows(int dims, int ky_lo, int ny_lo, int *first_upper);
 int pyl_pk_bin_mirrored(const float *const *delta_k, int fields, const int *mas_index, int dims,
                         int ky_lo, int ny_lo, int axis, int want_phase, void *out, void *ws,
                         size_t ws_bytes, pyl_stream_t stream);
+
+/* ---- 5. sibling estimators of Pk_library on |k| shells, and half-spectrum passes ------- */
+/* One kernel family reduces every independent mode (or every real-space cell) into bins of one fundamental
+ * frequency, k_index = (int)|k|, with a per-mode functional selected by `kind`:
+ *   kind            replaces (Pk_library.pyx)  fields (DEVICE, in this order)              values per bin
+ *   PYL_SHELL_THETA    Pk_theta    :1273-1316  Vx_k, Vy_k, Vz_k                             |i k.V|^2
+ *   PYL_SHELL_DV       XPk_dv      :1386-1432  delta_k, Vx_k, Vy_k, Vz_k                    |d|^2, |k.V|^2, cross
+ *   PYL_SHELL_VV       XPk_vv      :1515-1568  Vx1_k, Vy1_k, Vz1_k, Vx2_k, Vy2_k, Vz2_k     |k.V1|^2, |k.V2|^2, cross
+ *   PYL_SHELL_EXPECTED expected_Pk :2004-2037  none (interpolation table)                   P_interp(k)
+ *   PYL_SHELL_PLANE    Pk_plane    :470-499    one (dims, dims/2+1) image transform         |d|^2
+ *   PYL_SHELL_XPLANE   XPk_plane   :1151-1200  two image transforms (mas_index[0], [1])     |d1|^2, |d2|^2, cross
+ *   PYL_SHELL_XI       Xi / XXi    :2233-2267  one REAL (dims,dims,dims) float32 grid       xi*L_0, xi*L_2, xi*L_4
+ * Complex fields are (dims,dims,dims/2+1) complex64 half-spectra (not modified); k.V is formed in float32 and
+ * the window factor is a float32 product exactly as in the reference; all sums are float64.
+ * `out` (DEVICE, zeroed by the call) receives (2 + values) * bins 8-byte words:
+ *   sum_k[bins] (float64)   Nmodes[bins] (uint64)   value_j[bins] (float64), j = 0..values-1
+ * RAW sums, DC bin included; units and averaging stay with the caller (they are O(bins)).
+ * `scale` multiplies the grid values of PYL_SHELL_XI (float32 product: the 1/dims^3 of the normalised inverse
+ * transform); ignored otherwise.  `axis` is the line of sight of the PYL_SHELL_XI multipoles. */
+#define PYL_SHELL_THETA 0
+#define PYL_SHELL_DV 1
+#define PYL_SHELL_VV 2
+#define PYL_SHELL_EXPECTED 3
+#define PYL_SHELL_PLANE 4
+#define PYL_SHELL_XPLANE 5
+#define PYL_SHELL_XI 6
+/* expected_Pk's log-spaced interpolation table (Pk_library.pyx:1983-1993), DEVICE float32 arrays of n entries */
+typedef struct pyl_shell_table {
+    const float *k;
+    const float *P;
+    int32_t n;
+    float kF;          /* fundamental frequency, float32 like the reference's `cdef float kF` */
+    double log10_kmin; /* log10(k_in[0]) */
+    double deltak;     /* float32 spacing in log10 k, promoted */
+} pyl_shell_table_t;
+int pyl_shell_layout(int kind, int dims, int *bins, int *values);
+size_t pyl_shell_bin_workspace_bytes(int kind, int dims);
+int pyl_shell_bin(int kind, const float *const *fields, int nfields, const int *mas_index, int dims, int axis,
+                  float scale, const pyl_shell_table_t *table, void *out, void *ws, size_t ws_bytes,
+                  pyl_stream_t stream);
+
+/* Elementwise passes over a (dims,dims,dims/2+1) complex64 half-spectrum, IN PLACE on a_k / delta_k:
+ *   pyl_modes_deconvolve  correct_MAS's loop (Pk_library.pyx:1909-1929): multiply by the float32 window.  The
+ *       reference corrects only the modes it counts as independent, leaving their Hermitian duplicates on the
+ *       kz = 0 / Nyquist planes untouched; its c2r transform then sees the Hermitian part of those planes, i.e.
+ *       (1 + w)/2 on both members of a pair.  That factor is applied explicitly here (planes stay Hermitian).
+ *   pyl_modes_power       Xi / XXi's loop (:2198-2218, :2335-2362): a_k <- (re_a*re_b + im_a*im_b, 0) of the
+ *       deconvolved modes in float32; b_k NULL = auto-correlation.  b_k is not modified. */
+size_t pyl_modes_workspace_bytes(int dims);
+int pyl_modes_deconvolve(float *delta_k, int dims, int mas_index, void *ws, size_t ws_bytes, pyl_stream_t stream);
+int pyl_modes_power(float *a_k, const float *b_k, int dims, int mas_a, int mas_b, void *ws, size_t ws_bytes,
+                    pyl_stream_t stream);
+/* a_k[i] *= b_k[i], complex64 (smoothing_library.pyx:227-232, field_k * filter_k) */
+int pyl_cmul_inplace(float *a_k, const float *b_k, int64_t n_complex, pyl_stream_t stream);
+/* v[i] *= (1 + delta[i]), float32: the momentum fields of XPk_dv / XPk_vv (Pk_library.pyx:1367, :1491-1492) */
+int pyl_mul_one_plus(float *v, const float *delta, int64_t n, pyl_stream_t stream);
 
 /* ---- 4. host-pointer entry points with the reference's exact C signature ------------ */
 /* Same argument list as MAS_c.h:3-10 (HOST pointers; `threads` is accepted and ignored).

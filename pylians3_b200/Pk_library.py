@@ -107,10 +107,10 @@ def FFT3Dr_f(a, threads=1):
     return out if D.is_cuda_tensor(a) else out.cpu().numpy()
 
 
-def bin_device(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=None, mirrored=False):
+def bin_device(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=None, mirrored=False, flags=0):
     """Run pyl_pk_bin on `len(dk_list)` (<= L.MAX_FIELDS) half-spectra; returns (int64 CUDA tensor
     holding the raw accumulators, layout).  mirrored=True: the fields hold the |ky| rows [ky_lo, ky_lo+nky)
-    and their mirrors (pyl_pk_bin_mirrored, multi-GPU slabs)."""
+    and their mirrors (pyl_pk_bin_mirrored, multi-GPU slabs).  flags: extra PYL_PK_* bits (L.PK_CROSS_IMAG)."""
     lib = L.load()
     F = len(dk_list)
     nky = dims if nky is None else nky
@@ -124,7 +124,7 @@ def bin_device(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=No
         ptrs = (ctypes.c_void_p * F)(*[D.ptr(t) for t in dk_list])
         mi = (ctypes.c_int * F)(*[int(i) for i in mas_index])
         fn = lib.pyl_pk_bin_mirrored if mirrored else lib.pyl_pk_bin
-        st = fn(ptrs, F, mi, dims, ky_lo, nky, axis, 1 if want_phase else 0, D.ptr(out), D.ptr(ws), need,
+        st = fn(ptrs, F, mi, dims, ky_lo, nky, axis, (L.PK_PHASE if want_phase else 0) | int(flags), D.ptr(out), D.ptr(ws), need,
                 D.stream_ptr(dev))
     L.check(st, "pyl_pk_bin")
     return out, lay
@@ -375,3 +375,11 @@ class XPk:
         self.k3D, self.Nmodes3D = o["k3D"], o["Nmodes3D"]
         self.Pk, self.XPk = o["Pk"], o["XPk"]
         print("Time taken = %.2f seconds" % (time.time() - start))
+
+
+# ---- sibling estimators on the same machinery (Pk_plane, XPk_imag, XPk_plane, Pk_theta, XPk_dv, XPk_vv, XPk_2D,
+# correct_MAS, expected_Pk, Xi, XXi, ...): defined in _pk_more.py, exported here under the reference's names
+from . import _pk_more  # noqa: E402
+from ._pk_more import *  # noqa: E402,F401,F403
+
+__all__ += [n for n in _pk_more.__all__ if n != "field_smoothing"]

@@ -24,6 +24,16 @@ class PylError(RuntimeError):
                                                     (" -- " + detail) if detail else ""))
 
 
+SHELL_KINDS = {"theta": 0, "dv": 1, "vv": 2, "expected": 3, "plane": 4, "xplane": 5, "xi": 6}
+PK_PHASE, PK_CROSS_IMAG = 1, 2
+
+
+class ShellTable(ctypes.Structure):
+    """Mirror of pyl_shell_table_t."""
+    _fields_ = [("k", ctypes.c_void_p), ("P", ctypes.c_void_p), ("n", ctypes.c_int32), ("kF", ctypes.c_float),
+                ("log10_kmin", ctypes.c_double), ("deltak", ctypes.c_double)]
+
+
 class PkLayout(ctypes.Structure):
     """Mirror of pyl_pk_layout_t."""
     _fields_ = [(n, ctypes.c_int32) for n in ("dims", "fields", "xfields", "kmax_par", "kmax_per", "kmax")] + \
@@ -65,6 +75,16 @@ PROTOTYPES = {
     "pyl_pk_finalize": (_i, [_vp, _i, _i, ctypes.c_double, _i, _vp, _vp, _vp]),
     "pyl_pk_mirrored_rows": (_i, [_i, _i, _i, ctypes.POINTER(_i)]),
     "pyl_pk_bin_mirrored": (_i, [ctypes.POINTER(_vp), _i, ctypes.POINTER(_i), _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "pyl_fft_c2r_workspace_bytes": (_sz, [_i]),
+    "pyl_fft_c2r": (_i, [_vp, _vp, _i, _vp, _sz, _vp]),
+    "pyl_shell_layout": (_i, [_i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "pyl_shell_bin_workspace_bytes": (_sz, [_i, _i]),
+    "pyl_shell_bin": (_i, [_i, ctypes.POINTER(_vp), _i, ctypes.POINTER(_i), _i, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "pyl_modes_workspace_bytes": (_sz, [_i]),
+    "pyl_modes_deconvolve": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
+    "pyl_modes_power": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "pyl_cmul_inplace": (_i, [_vp, _vp, _i64, _vp]),
+    "pyl_mul_one_plus": (_i, [_vp, _vp, _i64, _vp]),
     "pyl_NGP": (_i, [_vp, _vp, _vp, _l, _i, _i, _f, _i]),
     "pyl_CIC": (_i, [_vp, _vp, _vp, _l, _i, _i, _f, _i]),
     "pyl_TSC": (_i, [_vp, _vp, _vp, _l, _i, _i, _f, _i]),

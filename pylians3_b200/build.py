@@ -13,9 +13,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "libpyl_b200.so")
-SOURCES = ["common.cu", "deposit.cu", "deposit_atomic.cu", "deposit_tiled.cu", "deposit_sorted.cu", "interp.cu", "fft.cu", "transpose.cu", "pk_bin.cu",
+SOURCES = ["common.cu", "deposit.cu", "deposit_atomic.cu", "deposit_tiled.cu", "deposit_sorted.cu", "interp.cu", "fft.cu", "transpose.cu", "pk_bin.cu", "pk_shell.cu",
            "hostapi.cu"]
-HEADERS = ["common.cuh", "stencil.cuh", os.path.join(ROOT, "include", "pyl_b200.h")]
+HEADERS = ["common.cuh", "stencil.cuh", "shell_body.cuh", "deposit_point.cuh", os.path.join(ROOT, "include", "pyl_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CUDA_LIB = "/usr/local/cuda/lib64"
 

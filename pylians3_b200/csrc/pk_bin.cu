@@ -48,6 +48,7 @@ struct PkArgs {
     int o_lo;                // fold: first |k_o| (0 unless the other axis is a mirrored ky window)
     int w_lo, w_hi;          // walk range |k_w| in [w_lo, w_hi)
     int axis;                // line of sight
+    int cross_imag;          // cross term: 0 = re_i re_j + im_i im_j (XPk), 1 = im_i re_j - re_i im_j (XPk_imag)
     int kmax_par1;           // kmax_par + 1
     int seg_len, nseg;       // walk range [0, m] cut into nseg segments of seg_len steps
     long long T;             // threads per segment = n_other * nz
@@ -293,7 +294,11 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
 #pragma unroll
                     for (int i = 0; i < F; i++)
 #pragma unroll
-                        for (int j = i + 1; j < F; j++) { DX[x] += re[i] * re[j] + im[i] * im[j]; x++; }
+                        for (int j = i + 1; j < F; j++) {
+                            // Pk_library.pyx:716-717 (XPk) or :1000-1001 (XPk_imag)
+                            DX[x] += A.cross_imag ? im[i] * re[j] - re[i] * im[j] : re[i] * re[j] + im[i] * im[j];
+                            x++;
+                        }
                 }
             }
 
@@ -484,7 +489,8 @@ static int mirrored_upper_rows(int dims, int ky_lo, int ny_lo, int *first) {
 
 template <int F>
 static int launch_bin(const float *const *delta_k, const int *mas_index, int dims, int ky_lo,
-                      int nky, int mirrored, int axis, int want_phase, void *out, void *ws, cudaStream_t stream) {
+                      int nky, int mirrored, int axis, int flags, void *out, void *ws, cudaStream_t stream) {
+    const int want_phase = flags & PYL_PK_PHASE;
     pyl_pk_layout_t L;
     fill_layout(dims, F, &L);
     const int m = dims / 2, nz = m + 1;
@@ -533,6 +539,7 @@ static int launch_bin(const float *const *delta_k, const int *mas_index, int dim
         A.n_other = nky;
     }
     A.axis = axis;
+    A.cross_imag = (flags & PYL_PK_CROSS_IMAG) ? 1 : 0;
     A.kmax_par1 = L.kmax_par + 1;
     A.T = (long long)A.n_other * nz;
 
@@ -612,8 +619,9 @@ size_t pyl_pk_bin_workspace_bytes(int dims, int fields) {
 }
 
 static int pk_bin_entry(const float *const *delta_k, int fields, const int *mas_index, int dims,
-                        int ky_lo, int nky, int mirrored, int axis, int want_phase, void *out, void *ws,
+                        int ky_lo, int nky, int mirrored, int axis, int flags, void *out, void *ws,
                         size_t ws_bytes, pyl_stream_t stream) {
+    const int want_phase = flags & PYL_PK_PHASE;
     PYL_REQUIRE(fields >= 1 && fields <= PYL_MAX_FIELDS, "pyl_pk_bin: fields must be 1..PYL_MAX_FIELDS");
     PYL_REQUIRE(dims > 0 && dims <= 8192, "pyl_pk_bin: dims must be in 1..8192");
     PYL_REQUIRE(axis >= 0 && axis <= 2, "pyl_pk_bin: axis must be 0, 1 or 2");
@@ -631,10 +639,10 @@ static int pk_bin_entry(const float *const *delta_k, int fields, const int *mas_
     }
     cudaStream_t s = as_stream(stream);
     switch (fields) {
-        case 1: return launch_bin<1>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, want_phase, out, ws, s);
-        case 2: return launch_bin<2>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, 0, out, ws, s);
-        case 3: return launch_bin<3>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, 0, out, ws, s);
-        default: return launch_bin<4>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, 0, out, ws, s);
+        case 1: return launch_bin<1>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, flags, out, ws, s);
+        case 2: return launch_bin<2>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, flags & ~PYL_PK_PHASE, out, ws, s);
+        case 3: return launch_bin<3>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, flags & ~PYL_PK_PHASE, out, ws, s);
+        default: return launch_bin<4>(delta_k, mas_index, dims, ky_lo, nky, mirrored, axis, flags & ~PYL_PK_PHASE, out, ws, s);
     }
 }
 

@@ -57,6 +57,29 @@ def run_all(impl, N, I=None):
     return out
 
 
+_PAIRS = [(0, 1), (0, 2), (1, 2)]
+
+
+def _cross_floor(key, ref):
+    """Natural scale sqrt(P_i P_j) of a cross quantity, from the reference's auto spectra (None for other keys).
+    A cross sum is a sum of signed terms: where it cancels, its round-off is set by the autos, not by itself."""
+    pre, name = key.rsplit("_", 1)
+    with np.errstate(invalid="ignore"):
+        if name == "PkX" and (pre.endswith("dv") or pre.endswith("vv") or "x2d" in pre):
+            return np.sqrt(np.abs(ref[pre + "_Pk1"] * ref[pre + "_Pk2"]))
+        if key.endswith("xplane_XPk"):
+            P = ref[pre + "_Pk"]
+            return np.sqrt(np.abs(P[:, 0] * P[:, 1]))
+        if "imag" in pre and name in ("XPk", "PkX1D", "PkX2D"):
+            P = ref[pre + "_" + {"XPk": "Pk", "PkX1D": "Pk1D", "PkX2D": "Pk2D"}[name]]
+            if name == "XPk":
+                mono = P[:, 0, :]
+                fl = np.stack([np.sqrt(np.abs(mono[:, i] * mono[:, j])) for i, j in _PAIRS], axis=-1)
+                return fl[:, None, :] * np.array([1.0, 5.0, 9.0])[None, :, None]
+            return np.stack([np.sqrt(np.abs(P[:, i] * P[:, j])) for i, j in _PAIRS], axis=-1)
+    return None
+
+
 def compare(got, ref, tol, exact_counts=True, ktol=1e-12):
     """Every key of `got` against `ref`.  Counts (…Nm, …Nmodes*) bit-exact; wavenumbers / radii to `ktol`;
     everything else to `tol` relative to max(|value|, 1e-6 * the array's largest |value|) -- cross terms and
@@ -84,6 +107,13 @@ def compare(got, ref, tol, exact_counts=True, ktol=1e-12):
             t = max(t, 1e-6)          # float32 k in the reference
         scale = np.nanmax(np.abs(r))
         den = np.maximum(np.abs(r), 1e-6 * scale if t > 1e-10 else 0.0)
+        fl = _cross_floor(key, ref)
+        if fl is not None:
+            den = np.maximum(den, 0.1 * np.nan_to_num(fl))
+        if name == "cmas":
+            den = np.full_like(r, scale)                 # a real-space field: error relative to its amplitude
+        if "xplane_r" in key:
+            den = np.maximum(den, 0.1)                   # correlation coefficient: |r| <= 1
         den = np.where(den == 0, 1.0, den)
         e = float(np.nanmax(np.abs(g - r) / den))
         if not e < t:

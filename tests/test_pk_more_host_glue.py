@@ -1,0 +1,106 @@
+"""CPU: the product's Python layer for the sibling estimators (pylians3_b200/_pk_more.py: argument handling, call
+sequence, unit conversions) driven end to end WITHOUT a GPU.  The device primitives it calls are monkeypatched with
+test doubles: transforms by pocketfft, and -- for the kernels -- the real per-thread bodies of shell_body.cuh run
+serially by tests/harness/shell_host.cpp.  Results are held to the golden outputs of the compiled reference.
+The product itself has no such path: without the patches every entry point raises (no CUDA device)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import scipy.fft as sfft
+
+import more_cases as MC
+from conftest import GOLDEN
+from test_shell_bodies_host import harness, run_shell  # noqa: F401  (fixture + helper)
+
+
+@pytest.fixture()
+def fake_device(monkeypatch, harness):  # noqa: F811
+    from pylians3_b200 import _pk_more as PM, Pk_library as P, _device as D
+
+    def as_np(x, dev=None, name=None):
+        assert x.dtype == np.float32
+        return np.ascontiguousarray(x)
+
+    def shell_bin(kind, fields, mas_index, dims, axis=2, scale=1.0, table=None):
+        if table is not None:
+            tk, tP, kF32, lk, dk = table
+            table = (tk, tP, float(kF32), lk, dk)
+        r = run_shell(harness, kind, fields, mas_index, dims, axis=axis, scale=scale, table=table)
+        return dict(ksum=r["ksum"], Nm=r["Nm"], vals=r["vals"])
+
+    def modes(op, a_k, b_k, dims, mas_a, mas_b):
+        harness.harness_modes(0 if op == "deconvolve" else 1, a_k.ctypes.data, None if b_k is None else b_k.ctypes.data,
+                              dims, mas_a, mas_b if b_k is not None else mas_a)
+
+    def c2r(ak, normalise=True):
+        n = ak.shape[0]
+        out = sfft.irfftn(ak, s=(n, n, n), axes=(0, 1, 2)).astype(np.float32)
+        return out if normalise else (out * np.float32(n ** 3)).astype(np.float32)
+
+    def momentum(V, delta_d, dev, names):
+        for v in V:
+            v *= (np.float32(1.0) + delta_d)
+        return list(V)
+
+    class FakeTorchTable:                      # expected_Pk ships its table through torch.from_numpy(...).to(dev)
+        pass
+
+    monkeypatch.setattr(D, "require_cuda", lambda: None)
+    monkeypatch.setattr(D, "pick_device", lambda *a: None)
+    monkeypatch.setattr(PM, "_cube", as_np)
+    monkeypatch.setattr(PM, "_as_image", as_np)
+    monkeypatch.setattr(P, "fft3d_r2c_device", lambda d: np.ascontiguousarray(sfft.rfftn(d, axes=(0, 1, 2)).astype(np.complex64)))
+    monkeypatch.setattr(PM, "fft2d_r2c_device", lambda d: np.ascontiguousarray(sfft.rfftn(d, axes=(0, 1)).astype(np.complex64)))
+    monkeypatch.setattr(PM, "ifft3d_c2r_device", c2r)
+    monkeypatch.setattr(PM, "shell_bin", shell_bin)
+    monkeypatch.setattr(PM, "_modes", modes)
+    monkeypatch.setattr(PM, "_momentum_", momentum)
+    monkeypatch.setattr(D, "is_cuda_tensor", lambda x: True)          # "device in -> device out": keep arrays as they are
+
+    class _T:                                                          # torch.from_numpy(x).to(dev) -> x ; torch.device(...)
+        @staticmethod
+        def from_numpy(x):
+            class W:
+                def to(self, dev):
+                    return x
+            return W()
+
+        @staticmethod
+        def device(*a):
+            return None
+
+        class cuda:
+            @staticmethod
+            def current_device():
+                return 0
+    monkeypatch.setattr(PM, "torch", _T)
+    return PM
+
+
+@pytest.mark.parametrize("N", MC.SIZES)
+def test_python_layer_against_reference_golden(fake_device, N):
+    PM = fake_device
+    golden = dict(np.load(os.path.join(GOLDEN, "pk_more_golden.npz")))
+
+    class Impl:                                 # the entry points whose kernels can run on the host harness
+        Pk_plane, XPk_plane, Pk_theta, XPk_dv, XPk_vv = PM.Pk_plane, PM.XPk_plane, PM.Pk_theta, PM.XPk_dv, PM.XPk_vv
+        correct_MAS, expected_Pk, Xi, XXi = PM.correct_MAS, PM.expected_Pk, PM.Xi, PM.XXi
+
+        class _Skip:
+            def __getattr__(self, n):
+                return np.zeros(0)
+
+        @staticmethod
+        def XPk_imag(*a, **k):
+            return Impl._Skip()
+
+        @staticmethod
+        def XPk_2D(*a, **k):
+            return [np.zeros(0)] * 6
+
+    got = MC.run_all(Impl, N)
+    got = {k: v for k, v in got.items() if "imag" not in k and "x2d" not in k}
+    bad = MC.compare(got, golden, tol=1e-5)     # float32 transforms differ in association (scaled c2r)
+    assert not bad, bad
