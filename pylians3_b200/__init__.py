@@ -12,5 +12,5 @@ without a CUDA device, the entry points raise.
 """
 __version__ = "0.1.0"
 
-from . import MAS_library, Pk_library, redshift_space_library  # noqa: E402,F401
+from . import MAS_library, Pk_library, redshift_space_library, smoothing_library  # noqa: E402,F401
 from .field import overdensity_  # noqa: E402,F401

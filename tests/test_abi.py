@@ -131,3 +131,51 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("# oracle", ""), f
+
+
+@pytest.mark.parametrize("dims", [16, 15, 512, 4096])
+def test_shell_layout_matches_frequencies(lib, oracle, dims):
+    """pyl_shell_layout: bins = kmax+1 of frequencies (3D kinds) / frequencies_2D (images), values per kind."""
+    from pylians3_b200 import _lib, Pk_library as PKL
+    from oracle import cpu_more
+    nvals = {"theta": 1, "dv": 3, "vv": 3, "expected": 1, "plane": 1, "xplane": 3, "xi": 3}
+    for kind, kid in _lib.SHELL_KINDS.items():
+        b, v = ctypes.c_int(0), ctypes.c_int(0)
+        assert lib.pyl_shell_layout(kid, dims, ctypes.byref(b), ctypes.byref(v)) == 0
+        kmax = (cpu_more.frequencies_2D if kind in ("plane", "xplane") else oracle.frequencies)(BOX, dims)[4]
+        assert (b.value, v.value) == (kmax + 1, nvals[kind]), kind
+        assert lib.pyl_shell_bin_workspace_bytes(kid, dims) >= 8 * 8 * (2 + v.value) * b.value
+    assert PKL.frequencies_2D(BOX, dims) == cpu_more.frequencies_2D(BOX, dims)
+    assert lib.pyl_shell_layout(9, dims, None, None) == -1
+
+
+def test_sibling_argument_errors(lib):
+    # wrong field count for the kind, NULL output, missing table, missing workspace: status codes, no crash
+    one = (ctypes.c_void_p * 1)(ctypes.c_void_p(16))
+    mi = (ctypes.c_int * 2)(2, 2)
+    assert lib.pyl_shell_bin(0, one, 1, mi, 16, 2, 1.0, None, ctypes.c_void_p(16), None, 0, None) == -1
+    three = (ctypes.c_void_p * 3)(16, 16, 16)
+    assert lib.pyl_shell_bin(0, three, 3, mi, 16, 2, 1.0, None, None, None, 0, None) == -1
+    assert lib.pyl_shell_bin(0, three, 3, mi, 16, 2, 1.0, None, ctypes.c_void_p(16), None, 0, None) == -4
+    assert lib.pyl_shell_bin(3, one, 0, None, 16, 2, 1.0, None, ctypes.c_void_p(16), None, 0, None) == -1
+    assert lib.pyl_modes_deconvolve(None, 16, 2, None, 0, None) == -1
+    assert lib.pyl_modes_deconvolve(ctypes.c_void_p(16), 16, 7, None, 0, None) == -1
+    assert lib.pyl_modes_power(ctypes.c_void_p(16), None, 16, 2, 2, None, 0, None) == -4
+    assert lib.pyl_fft_c2r(None, None, 16, None, 0, None) == -1
+    assert lib.pyl_cmul_inplace(None, None, 10, None) == -1 and lib.pyl_cmul_inplace(None, None, 0, None) == 0
+    assert lib.pyl_mul_one_plus(None, None, 10, None) == -1
+
+
+def test_sibling_python_errors_match_reference(capsys):
+    """Host-side argument checks happen before any device work is attempted (messages of Pk_library.pyx:1119,
+    1773, 1975, 1980, 2323 and smoothing_library.pyx:223)."""
+    from pylians3_b200 import Pk_library as PKL, smoothing_library as SL, _device
+    if _device.torch.cuda.is_available():
+        pytest.skip("checked on the CPU tier")
+    k = np.logspace(-3, 1, 50).astype(np.float32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PKL.Pk_theta(np.zeros((4, 4, 4), np.float32), np.zeros((4, 4, 4), np.float32), np.zeros((4, 4, 4), np.float32), 1.0)
+    for name in ("Pk_plane", "XPk_plane", "XPk_imag", "XPk_2D", "Pk_theta", "XPk_dv", "XPk_vv", "correct_MAS",
+                 "expected_Pk", "Xi", "XXi", "IFFT3Dr_f", "FFT2Dr_f", "frequencies_2D", "check_number_modes_2D"):
+        assert hasattr(PKL, name), name
+    assert callable(SL.field_smoothing)
