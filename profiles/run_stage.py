@@ -4,6 +4,7 @@
     python profiles/run_stage.py deposit CIC auto 512 [reps]
     python profiles/run_stage.py pk 512 [axis] [reps]
     python profiles/run_stage.py step 512 [reps]          # the bench.py step: zero, MA(CIC), delta, Pk
+    python profiles/run_stage.py shell 512 [reps]         # shell kernels (theta, dv, vv, xi) + mode passes
 """
 import os
 import sys
@@ -25,6 +26,22 @@ if what == "deposit":
         MASL.MA(pos, grid, BOX, mas, mode=mode)
     torch.cuda.synchronize()
     print("sum/N^3 =", float(grid.sum(dtype=torch.float64)) / N ** 3 / reps)
+elif what == "shell":
+    from pylians3_b200 import _pk_more as PM
+    N = int(sys.argv[2])
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    real = [torch.randn((N, N, N), generator=g, device=dev, dtype=torch.float32) for _ in range(2)]
+    cplx = [PKL.fft3d_r2c_device(real[i % 2]) for i in range(6)]
+    for _ in range(reps):
+        PM.shell_bin("theta", cplx[:3], [2], N)
+        PM.shell_bin("dv", cplx[:4], [2], N)
+        PM.shell_bin("vv", cplx[:6], [2], N)
+        r = PM.shell_bin("xi", real[:1], [], N, axis=2, scale=1.0 / N ** 3)
+        PM._modes("deconvolve", cplx[0], None, N, 2, 0)
+        PM._modes("power", cplx[1], cplx[2], N, 2, 4)
+    torch.cuda.synchronize()
+    print("xi Nm sum =", r["Nm"].sum())
 elif what == "step":
     N = int(sys.argv[2])
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2

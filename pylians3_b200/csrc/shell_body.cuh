@@ -16,10 +16,10 @@
 // threads and segments, the Hermitian-duplicate rule, the index arithmetic and every per-mode functional are
 // checked against the CPU restatement of the reference in the GPU-less authoring container.  That harness is test infrastructure only.
 //
-// Decomposition: thread t owns (ix, iz) = (t / nzs, t % nzs) -- lanes run along the contiguous last axis, so a
-// warp's loads are 256-byte row segments -- and walks iy over its segment [seg*seg_len, (seg+1)*seg_len).  k^2
-// changes slowly along the walk (piecewise monotonic in iy), so the sums of the current bin live in registers
-// and reach memory only when the bin changes.
+// Decomposition: thread t owns (|kx|, |kz|) -- lanes run along the contiguous last axis, so a warp's loads are
+// 256-byte row segments -- and walks |ky| over its segment of [0, N/2], handling the sign combinations that share
+// |k| together (see shell_thread).  k^2 grows monotonically along the walk, so the sums of the current bin live
+// in registers and reach memory only when the bin changes.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -121,34 +121,91 @@ PYL_HD void shell_kdotv(const float2 *V, float fac, int kx, int ky, int kz, floa
     dim = shell_fma(fz, shell_fmul(V[2].y, fac), shell_fma(fy, shell_fmul(V[1].y, fac), shell_fmul(fx, shell_fmul(V[0].y, fac))));
 }
 
+// The per-mode functional of one loaded mode/cell with signed wavenumbers (kx, ky, kz); adds into v[].
+template <int KIND>
+PYL_HD void shell_mode(const ShellArgs &A, const ShellLoad<KIND> &L, int kx, int ky, int kz, float fac, float fac1,
+                       double k, int k2, double *v) {
+    if (KIND == SK_XI) {
+        const int kpar = (A.axis == 0) ? kx : (A.axis == 1 ? ky : kz);
+        const double mu = (k2 == 0) ? 0.0 : (double)kpar / k;
+        const double mu2 = mu * mu;
+        const double x = (double)shell_fmul(L.r, A.scale);
+        v[0] += x;
+        v[1] += (x * (3.0 * mu2 - 1.0) / 2.0);
+        v[2] += (x * (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0);
+    } else if (KIND == SK_PLANE) {
+        const double re = (double)shell_fmul(L.c[0].x, fac), im = (double)shell_fmul(L.c[0].y, fac);
+        v[0] += re * re + im * im;
+    } else if (KIND == SK_XPLANE) {
+        const double r0 = (double)shell_fmul(L.c[0].x, fac), i0 = (double)shell_fmul(L.c[0].y, fac);
+        const double r1 = (double)shell_fmul(L.c[1].x, fac1), i1 = (double)shell_fmul(L.c[1].y, fac1);
+        v[0] += r0 * r0 + i0 * i0;
+        v[1] += r1 * r1 + i1 * i1;
+        v[2] += r0 * r1 + i0 * i1;
+    } else if (KIND == SK_THETA) {
+        float dre, dim;
+        shell_kdotv(&L.c[0], fac, kx, ky, kz, dre, dim);
+        const double re = -(double)dim, im = (double)dre;          // theta = i k.V (:1303-1309)
+        v[0] += re * re + im * im;
+    } else if (KIND == SK_DV || KIND == SK_VV) {
+        double r1, i1, r2, i2;
+        float dre, dim;
+        if (KIND == SK_DV) {
+            r1 = (double)shell_fmul(L.c[0].x, fac); i1 = (double)shell_fmul(L.c[0].y, fac);
+            shell_kdotv(&L.c[1], fac, kx, ky, kz, dre, dim);
+            r2 = (double)dim; i2 = -(double)dre;                   // :1419-1425
+        } else {
+            shell_kdotv(&L.c[0], fac, kx, ky, kz, dre, dim);
+            r1 = (double)dim; i1 = -(double)dre;                   // :1549-1554
+            shell_kdotv(&L.c[KIND == SK_VV ? 3 : 0], fac, kx, ky, kz, dre, dim);
+            r2 = (double)dim; i2 = -(double)dre;                   // :1556-1561
+        }
+        v[0] += r1 * r1 + i1 * i1;
+        v[1] += r2 * r2 + i2 * i2;
+        v[2] += r1 * r2 + i1 * i2;
+    }
+}
+
 // The body.  Sink: add(word, double) and count(word, unsigned long long) accumulate into the block the caller chose.
+//
+// FOLD: thread t owns (|kx|, |kz|) = (a, iz) and walks s = |ky| over its segment of [0, m].  The sign combinations
+// (+-kx, +-ky[, +-kz for the real grid of SK_XI]) that exist as separate stored elements share |k|, hence the bin,
+// the (even) window factor and mu^2: they are loaded together, their functionals (which see the SIGNED wavenumbers)
+// are summed into the same registers, and the duplicate-mode rule is applied per mode, so counts stay exact.
+// k^2 = a^2 + iz^2 + s^2 grows monotonically along the walk: a bin is flushed once per thread and the flush is
+// shared by 4 (8) modes -- the red.global rate, not the loads, bounded the unfolded form of this kernel
+// (measured: Xi binning 2.56 ms at 512^3 unfolded).
 template <int KIND, class Sink>
 PYL_HD void shell_thread(const ShellArgs &A, long long t, int seg, Sink &sink) {
     constexpr int NV = (KIND == SK_THETA || KIND == SK_EXPECTED || KIND == SK_PLANE) ? 1 : 3;
-    const int N = A.N, m = A.m;
+    constexpr int NZ = (KIND == SK_XI) ? 2 : 1;
+    const int N = A.N, m = A.m, nzh = A.m + 1;
     const bool even = A.even != 0;
-    const int ix = (int)(t / A.nzs);
-    const int iz = (int)(t - (long long)ix * A.nzs);
-    const int kx = (A.nx == 1) ? 0 : (ix > m ? ix - N : ix);
-    const int kz = iz > m ? iz - N : iz;
-    bool yskip = false;                       // drop ky < 0 on this column
-    if (A.hermitian) {
-        const bool zspecial = (kz == 0) || (kz == m && even);
-        if (zspecial && kx < 0) return;
-        yskip = zspecial && (kx == 0 || (kx == m && even));
-    }
-    const int y0 = seg * A.seg_len;
-    const int y1 = (y0 + A.seg_len < N) ? y0 + A.seg_len : N;
-    if (y0 >= y1) return;
+    const int a = (A.nx == 1) ? 0 : (int)(t / nzh);
+    const int iz = (int)(t - (long long)(t / nzh) * nzh);
+    const int s0 = seg * A.seg_len;
+    const int s1 = (s0 + A.seg_len < nzh) ? s0 + A.seg_len : nzh;
+    if (s0 >= s1) return;
 
-    const int ax = kx < 0 ? -kx : kx, az = kz < 0 ? -kz : kz;
+    const bool has_nx = (A.nx != 1) && a != 0 && !(even && a == m);        // -a is a separate stored row
+    const bool has_nz = (NZ == 2) && iz != 0 && !(even && iz == m);
+    const bool zspecial = A.hermitian && (iz == 0 || (iz == m && even));
+    const bool xself = (a == 0) || (a == m && even);
+    // duplicate-mode rule (Pk_library.pyx:324-327): on the special planes drop kx < 0, and ky < 0 where kx is 0 / Nyquist
+    const bool use_nx = has_nx && !zspecial;
+    const bool drop_ny = zspecial && xself;
+
     double cx0 = 1.0, cz0 = 1.0, cx1 = 1.0, cz1 = 1.0;
     if (KIND != SK_XI && KIND != SK_EXPECTED) {
-        cx0 = A.win[0][ax]; cz0 = A.win[0][az];
-        if (KIND == SK_XPLANE) { cx1 = A.win[1][ax]; cz1 = A.win[1][az]; }
+        cx0 = A.win[0][a]; cz0 = A.win[0][iz];
+        if (KIND == SK_XPLANE) { cx1 = A.win[1][a]; cz1 = A.win[1][iz]; }
     }
-    const int base2 = kx * kx + kz * kz;
-    const long long row0 = (long long)ix * N;
+    const int base2 = a * a + iz * iz;
+    const int ixs[2] = {a, N - a};
+    const int izs[2] = {iz, N - iz};
+    const int kxs[2] = {a, -a};
+    const int kzs[2] = {iz, -iz};
+    const int nxv = use_nx ? 2 : 1, nzv = has_nz ? 2 : 1;
 
     int cur = -1;
     unsigned int cnt = 0;
@@ -168,95 +225,74 @@ PYL_HD void shell_thread(const ShellArgs &A, long long t, int seg, Sink &sink) {
         for (int j = 0; j < NV; j++) v[j] = 0.0;
     };
 
-    ShellLoad<KIND> now, nxt;
-    shell_fetch<KIND>(A, (row0 + y0) * A.nzs + iz, now);
-    for (int iy = y0; iy < y1; iy++) {
-        if (iy + 1 < y1) shell_fetch<KIND>(A, (row0 + iy + 1) * A.nzs + iz, nxt);   // prefetch the next step
-        const int ky = iy > m ? iy - N : iy;
-        if (!(yskip && ky < 0)) {
-            const int k2 = base2 + ky * ky;
-            const double k = sqrt((double)k2);
-            int kidx = (int)k;
-            if (KIND == SK_EXPECTED) {
-                // `cdef float k` in the reference (Pk_library.pyx:1961,2021-2028)
-                float kf = (float)k;
-                kidx = (int)kf;
-                if (kf != 0.0f) {
-                    if (kidx != cur) { flush(); cur = kidx; }
-                    kf = shell_fmul(kf, A.kF);
-                    int i = (int)((log10((double)kf) - A.log10_kmin) / A.deltak);
-                    i = i < 0 ? 0 : (i > A.tab_n - 2 ? A.tab_n - 2 : i);     // the reference reads out of bounds here
-                    const float k0 = A.tab_k[i], k1 = A.tab_k[i + 1], p0 = A.tab_P[i], p1 = A.tab_P[i + 1];
-                    const float Pi = shell_fmul((p1 - p0) / (k1 - k0), kf - k0) + p0;
-                    cnt += 1; ksum += (double)kf; v[0] += (double)Pi;
-                }
-            } else {
-                if (kidx != cur) { flush(); cur = kidx; }
-                cnt += 1; ksum += k;
-                const int ay = ky < 0 ? -ky : ky;
-                if (KIND == SK_XI) {
-                    const int kpar = (A.axis == 0) ? kx : (A.axis == 1 ? ky : kz);
-                    const double mu = (k2 == 0) ? 0.0 : (double)kpar / k;
-                    const double mu2 = mu * mu;
-                    const double x = (double)shell_fmul(now.r, A.scale);
-                    v[0] += x;
-                    v[1] += (x * (3.0 * mu2 - 1.0) / 2.0);
-                    v[2] += (x * (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) / 8.0);
-                } else {
-                    // window factor: product in float64 in the reference's order, rounded to float32 (:351, :488)
-                    const float fac = (float)(cx0 * A.win[0][ay] * cz0);
-                    if (KIND == SK_PLANE) {
-                        const double re = (double)shell_fmul(now.c[0].x, fac), im = (double)shell_fmul(now.c[0].y, fac);
-                        v[0] += re * re + im * im;
-                    } else if (KIND == SK_XPLANE) {
-                        const float fac1 = (float)(cx1 * A.win[1][ay] * cz1);
-                        const double r0 = (double)shell_fmul(now.c[0].x, fac), i0 = (double)shell_fmul(now.c[0].y, fac);
-                        const double r1 = (double)shell_fmul(now.c[1].x, fac1), i1 = (double)shell_fmul(now.c[1].y, fac1);
-                        v[0] += r0 * r0 + i0 * i0;
-                        v[1] += r1 * r1 + i1 * i1;
-                        v[2] += r0 * r1 + i0 * i1;
-                    } else if (KIND == SK_THETA) {
-                        float dre, dim;
-                        shell_kdotv(&now.c[0], fac, kx, ky, kz, dre, dim);
-                        const double re = -(double)dim, im = (double)dre;          // theta = i k.V (:1303-1309)
-                        v[0] += re * re + im * im;
-                    } else {
-                        double r1, i1, r2, i2;
-                        float dre, dim;
-                        if (KIND == SK_DV) {
-                            r1 = (double)shell_fmul(now.c[0].x, fac); i1 = (double)shell_fmul(now.c[0].y, fac);
-                            shell_kdotv(&now.c[1], fac, kx, ky, kz, dre, dim);
-                            r2 = (double)dim; i2 = -(double)dre;                   // :1419-1425
-                        } else {
-                            shell_kdotv(&now.c[0], fac, kx, ky, kz, dre, dim);
-                            r1 = (double)dim; i1 = -(double)dre;                   // :1549-1554
-                            shell_kdotv(&now.c[3], fac, kx, ky, kz, dre, dim);
-                            r2 = (double)dim; i2 = -(double)dre;                   // :1556-1561
-                        }
-                        v[0] += r1 * r1 + i1 * i1;
-                        v[1] += r2 * r2 + i2 * i2;
-                        v[2] += r1 * r2 + i1 * i2;
-                    }
-                }
-            }
+    for (int s = s0; s < s1; s++) {
+        const bool use_ny = s != 0 && !(even && s == m) && !drop_ny;
+        const int nyv = use_ny ? 2 : 1;
+        const int iys[2] = {s, N - s};
+        // all loads of the step first (independent, in flight together), then the arithmetic
+        ShellLoad<KIND> L[2][2][NZ];
+        if (KIND != SK_EXPECTED) {
+#pragma unroll
+            for (int jx = 0; jx < 2; jx++)
+#pragma unroll
+                for (int jy = 0; jy < 2; jy++)
+#pragma unroll
+                    for (int jz = 0; jz < NZ; jz++)
+                        if (jx < nxv && jy < nyv && jz < nzv)
+                            shell_fetch<KIND>(A, ((long long)ixs[jx] * N + iys[jy]) * A.nzs + izs[jz], L[jx][jy][jz]);
         }
-        now = nxt;
+        const int mult = nxv * nyv * nzv;
+        const int k2 = base2 + s * s;
+        const double k = sqrt((double)k2);
+        int kidx = (int)k;
+        if (KIND == SK_EXPECTED) {
+            // `cdef float k` in the reference (Pk_library.pyx:1961,2021-2028); the DC mode is skipped (:2025)
+            float kf = (float)k;
+            kidx = (int)kf;
+            if (kf != 0.0f) {
+                if (kidx != cur) { flush(); cur = kidx; }
+                kf = shell_fmul(kf, A.kF);
+                int i = (int)((log10((double)kf) - A.log10_kmin) / A.deltak);
+                i = i < 0 ? 0 : (i > A.tab_n - 2 ? A.tab_n - 2 : i);     // the reference reads out of bounds here
+                const float k0 = A.tab_k[i], k1 = A.tab_k[i + 1], p0 = A.tab_P[i], p1 = A.tab_P[i + 1];
+                const float Pi = shell_fmul((p1 - p0) / (k1 - k0), kf - k0) + p0;
+                cnt += mult; ksum += (double)mult * (double)kf; v[0] += (double)mult * (double)Pi;
+            }
+            continue;
+        }
+        if (kidx != cur) { flush(); cur = kidx; }
+        cnt += mult; ksum += (double)mult * k;
+        // window factor: product in float64 in the reference's order, rounded to float32 (:351, :488)
+        float fac = 1.0f, fac1 = 1.0f;
+        if (KIND != SK_XI) {
+            fac = (float)(cx0 * A.win[0][s] * cz0);
+            if (KIND == SK_XPLANE) fac1 = (float)(cx1 * A.win[1][s] * cz1);
+        }
+#pragma unroll
+        for (int jx = 0; jx < 2; jx++)
+#pragma unroll
+            for (int jy = 0; jy < 2; jy++)
+#pragma unroll
+                for (int jz = 0; jz < NZ; jz++)
+                    if (jx < nxv && jy < nyv && jz < nzv)
+                        shell_mode<KIND>(A, L[jx][jy][jz], kxs[jx], jy ? -s : s, kzs[jz], fac, fac1, k, k2, v);
     }
     flush();
 }
 
 // launch geometry shared by the device launcher and the host harness
 PYL_HD void shell_geometry(ShellArgs &A, int sms) {
-    A.T = (long long)A.nx * A.nzs;
+    const int walk = A.m + 1;                            // |ky| = 0..m
+    A.T = (long long)(A.nx == 1 ? 1 : A.m + 1) * (A.m + 1);
     const long long warps_per_seg = (A.T + 31) / 32;
     const long long want_warps = (long long)sms * 64;
     long long nseg = (want_warps + warps_per_seg - 1) / warps_per_seg;
-    const long long max_seg = (A.N + 7) / 8;            // at least 8 walk steps per segment
+    const long long max_seg = (walk + 7) / 8;            // at least 8 walk steps per segment
     if (nseg > max_seg) nseg = max_seg;
     if (nseg < 1) nseg = 1;
-    A.seg_len = (int)((A.N + nseg - 1) / nseg);
+    A.seg_len = (int)((walk + nseg - 1) / nseg);
     if (A.seg_len < 1) A.seg_len = 1;
-    A.nseg = (A.N + A.seg_len - 1) / A.seg_len;
+    A.nseg = (walk + A.seg_len - 1) / A.seg_len;
 }
 
 // ---- elementwise passes over a (N, N, N/2+1) half-spectrum ---------------------------------------------------
