@@ -26,6 +26,7 @@
 //
 // Counts are uint64, everything else float64, exactly as wide as the reference's accumulators.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -33,6 +34,7 @@ namespace pyl {
 
 constexpr int PK_BLOCK = 128;
 constexpr int PK_NREP = 8;
+constexpr int PK_MINB_DEFAULT = 0;      // see pk_bin_walk_kernel's MINB; overridden by PYL_PKBIN_MINB (experiments)
 
 template <int F>
 struct PkArgs {
@@ -84,8 +86,11 @@ __device__ __forceinline__ double phase_sq(float re, float im) {
     return (double)(a * a);
 }
 
-template <int F, bool PHASE>
-__global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A) {
+// MINB: minimum resident CTAs per SM asked of ptxas (0 = no constraint).  The kernel is latency-bound on its row
+// loads (profiles/r1_pkbin.md: 80 registers -> 24 warps/SM, issue slots 31% busy); MINB = 8 caps it at 64
+// registers for 32 warps/SM.
+template <int F, bool PHASE, int MINB>
+__global__ void __launch_bounds__(PK_BLOCK, MINB > 0 ? MINB : 1) pk_bin_walk_kernel(const PkArgs<F> A) {
     constexpr int X = F * (F - 1) / 2;
     const int seg = blockIdx.y;
     const long long t = (long long)blockIdx.x * PK_BLOCK + threadIdx.x;
@@ -563,8 +568,18 @@ static int launch_bin(const float *const *delta_k, const int *mas_index, int dim
 
     if (A.T > 0 && A.nseg > 0) {
         dim3 grid((unsigned)((A.T + PK_BLOCK - 1) / PK_BLOCK), (unsigned)A.nseg);
-        if (want_phase) pk_bin_walk_kernel<F, true><<<grid, PK_BLOCK, 0, stream>>>(A);
-        else pk_bin_walk_kernel<F, false><<<grid, PK_BLOCK, 0, stream>>>(A);
+        // single field: the 64-register build (see MINB); several fields keep ptxas' own allocation
+        static const int minb = []() { const char *e = getenv("PYL_PKBIN_MINB"); return e ? atoi(e) : PK_MINB_DEFAULT; }();
+        if (F == 1 && minb >= 8) {
+            if (want_phase) pk_bin_walk_kernel<F, true, 8><<<grid, PK_BLOCK, 0, stream>>>(A);
+            else pk_bin_walk_kernel<F, false, 8><<<grid, PK_BLOCK, 0, stream>>>(A);
+        } else if (F == 1 && minb >= 6) {
+            if (want_phase) pk_bin_walk_kernel<F, true, 6><<<grid, PK_BLOCK, 0, stream>>>(A);
+            else pk_bin_walk_kernel<F, false, 6><<<grid, PK_BLOCK, 0, stream>>>(A);
+        } else {
+            if (want_phase) pk_bin_walk_kernel<F, true, 0><<<grid, PK_BLOCK, 0, stream>>>(A);
+            else pk_bin_walk_kernel<F, false, 0><<<grid, PK_BLOCK, 0, stream>>>(A);
+        }
         PYL_LAUNCH_CHECK();
     }
     pk_fold_replicas_kernel<<<(unsigned)((rep_words + 255) / 256), 256, 0, stream>>>(
