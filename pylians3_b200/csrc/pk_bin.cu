@@ -26,7 +26,6 @@
 //
 // Counts are uint64, everything else float64, exactly as wide as the reference's accumulators.
 #include <math.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -34,7 +33,6 @@ namespace pyl {
 
 constexpr int PK_BLOCK = 128;
 constexpr int PK_NREP = 8;
-constexpr int PK_MINB_DEFAULT = 0;      // see pk_bin_walk_kernel's MINB; overridden by PYL_PKBIN_MINB (experiments)
 
 template <int F>
 struct PkArgs {
@@ -86,11 +84,11 @@ __device__ __forceinline__ double phase_sq(float re, float im) {
     return (double)(a * a);
 }
 
-// MINB: minimum resident CTAs per SM asked of ptxas (0 = no constraint).  The kernel is latency-bound on its row
-// loads (profiles/r1_pkbin.md: 80 registers -> 24 warps/SM, issue slots 31% busy); MINB = 8 caps it at 64
-// registers for 32 warps/SM.
-template <int F, bool PHASE, int MINB>
-__global__ void __launch_bounds__(PK_BLOCK, MINB > 0 ? MINB : 1) pk_bin_walk_kernel(const PkArgs<F> A) {
+// Register cap: tried and dropped.  Built with __launch_bounds__(128, 8) (64 registers, 32 warps/SM instead of 24)
+// the kernel ran in the same 0.89 ms at 512^3 -- it is not bound by occupancy but by the LSU/L2 path of its
+// red.global flushes and table loads (profiles/r1_pkbin_hotlines.md).
+template <int F, bool PHASE>
+__global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A) {
     constexpr int X = F * (F - 1) / 2;
     const int seg = blockIdx.y;
     const long long t = (long long)blockIdx.x * PK_BLOCK + threadIdx.x;
@@ -245,13 +243,26 @@ __global__ void __launch_bounds__(PK_BLOCK, MINB > 0 ? MINB : 1) pk_bin_walk_ker
 
     float2 cur_v[4][F];
     unsigned cur_ok = 0;
-    if (s0 < s1) fetch(s0, cur_v, cur_ok);
+    double cur_w[F];                       // window factor of the walk coordinate, fetched one step ahead like the rows
+    if (s0 < s1) {
+        fetch(s0, cur_v, cur_ok);
+#pragma unroll
+        for (int f = 0; f < F; f++) cur_w[f] = A.win[f][s0];
+    }
 
     for (int s = s0; s < s1; s++) {
-        // software prefetch of the next step while this one is reduced
+        // software prefetch of the next step while this one is reduced (the table load, issued at its point of
+        // use, was 14% of the kernel's stall samples: profiles/r1_pkbin_hotlines.md)
         float2 nxt_v[4][F];
         unsigned nxt_ok = 0;
-        if (s + 1 < s1) fetch(s + 1, nxt_v, nxt_ok);
+        double nxt_w[F];
+#pragma unroll
+        for (int f = 0; f < F; f++) nxt_w[f] = cur_w[f];
+        if (s + 1 < s1) {
+            fetch(s + 1, nxt_v, nxt_ok);
+#pragma unroll
+            for (int f = 0; f < F; f++) nxt_w[f] = A.win[f][s + 1];
+        }
 
         // ---- geometry of this step (shared by the folded modes) -------------------------
         const int ss = s * s;
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(PK_BLOCK, MINB > 0 ? MINB : 1) pk_bin_walk_ker
             float fac[F];
 #pragma unroll
             for (int f = 0; f < F; f++)   // product in float64, rounded to float32 (:351)
-                fac[f] = __double2float_rn(win_oz[f] * A.win[f][s]);
+                fac[f] = __double2float_rn(win_oz[f] * cur_w[f]);
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 if (cur_ok & (1u << c)) {
@@ -336,6 +347,8 @@ __global__ void __launch_bounds__(PK_BLOCK, MINB > 0 ? MINB : 1) pk_bin_walk_ker
         }
 
         cur_ok = nxt_ok;
+#pragma unroll
+        for (int f = 0; f < F; f++) cur_w[f] = nxt_w[f];
 #pragma unroll
         for (int c = 0; c < 4; c++)
 #pragma unroll
@@ -568,18 +581,8 @@ static int launch_bin(const float *const *delta_k, const int *mas_index, int dim
 
     if (A.T > 0 && A.nseg > 0) {
         dim3 grid((unsigned)((A.T + PK_BLOCK - 1) / PK_BLOCK), (unsigned)A.nseg);
-        // single field: the 64-register build (see MINB); several fields keep ptxas' own allocation
-        static const int minb = []() { const char *e = getenv("PYL_PKBIN_MINB"); return e ? atoi(e) : PK_MINB_DEFAULT; }();
-        if (F == 1 && minb >= 8) {
-            if (want_phase) pk_bin_walk_kernel<F, true, 8><<<grid, PK_BLOCK, 0, stream>>>(A);
-            else pk_bin_walk_kernel<F, false, 8><<<grid, PK_BLOCK, 0, stream>>>(A);
-        } else if (F == 1 && minb >= 6) {
-            if (want_phase) pk_bin_walk_kernel<F, true, 6><<<grid, PK_BLOCK, 0, stream>>>(A);
-            else pk_bin_walk_kernel<F, false, 6><<<grid, PK_BLOCK, 0, stream>>>(A);
-        } else {
-            if (want_phase) pk_bin_walk_kernel<F, true, 0><<<grid, PK_BLOCK, 0, stream>>>(A);
-            else pk_bin_walk_kernel<F, false, 0><<<grid, PK_BLOCK, 0, stream>>>(A);
-        }
+        if (want_phase) pk_bin_walk_kernel<F, true><<<grid, PK_BLOCK, 0, stream>>>(A);
+        else pk_bin_walk_kernel<F, false><<<grid, PK_BLOCK, 0, stream>>>(A);
         PYL_LAUNCH_CHECK();
     }
     pk_fold_replicas_kernel<<<(unsigned)((rep_words + 255) / 256), 256, 0, stream>>>(
