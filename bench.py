@@ -337,6 +337,7 @@ def run_ours(args):
         reps = 3
         acc = {k: 0.0 for k in ("zero", "deposit+halo", "overdensity", "fft(yz,transpose,x)", "bin+allreduce+finalise+d2h")}
         for _ in range(reps):
+            barrier()                      # ranks start each repetition together: no inter-rank skew in the stage times
             e0 = ev(); slab.zero_()
             e1 = ev(); ctx.MA(pos, slab, MAS, routed=True)
             e2 = ev(); ctx.overdensity_(slab)
