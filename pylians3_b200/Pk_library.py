@@ -152,7 +152,7 @@ def unpack_raw(words, lay):
 
 
 def bin_fields(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=None, reduce_fn=None,
-               mirrored=False):
+               mirrored=False, flags=0):
     """Raw accumulators for ANY number of fields.
 
     Up to L.MAX_FIELDS fields go through one launch.  More fields are covered by launches over
@@ -163,7 +163,7 @@ def bin_fields(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=No
 
     def run(idx):
         out, lay = bin_device([dk_list[i] for i in idx], [mas_index[i] for i in idx], dims, axis,
-                              want_phase and len(idx) == 1, ky_lo, nky, mirrored)
+                              want_phase and len(idx) == 1, ky_lo, nky, mirrored, flags)
         if reduce_fn is not None:
             out = reduce_fn(out, lay)
         return unpack_raw(D.to_host_numpy(out), lay)
@@ -250,12 +250,12 @@ def finalize_device(out, lay, BoxSize, dims, counts_are_f64=False):
     return o
 
 
-def spectra(dk_list, mas_index, dims, axis, BoxSize, want_phase=False):
+def spectra(dk_list, mas_index, dims, axis, BoxSize, want_phase=False, flags=0):
     """bin + finalise: device finalisation for up to L.MAX_FIELDS fields, host assembly beyond."""
     if len(dk_list) <= L.MAX_FIELDS:
-        out, lay = bin_device(dk_list, mas_index, dims, axis, want_phase and len(dk_list) == 1)
+        out, lay = bin_device(dk_list, mas_index, dims, axis, want_phase and len(dk_list) == 1, flags=flags)
         return finalize_device(out, lay, BoxSize, dims)
-    return _finalize(bin_fields(dk_list, mas_index, dims, axis, want_phase), BoxSize, dims)
+    return _finalize(bin_fields(dk_list, mas_index, dims, axis, want_phase, flags=flags), BoxSize, dims)
 
 
 # ---- host finalisation (vectorised restatement of :384-418 / :735-791) --------------------

@@ -233,14 +233,11 @@ class XPk_imag:
                 reference_exit("Fields have different grid sizes!!!")
         if MAS is None or len(MAS) != fields:
             raise TypeError("MAS must be a list with one scheme per field")
-        if fields > L.MAX_FIELDS:
-            raise ValueError("XPk_imag handles up to %d fields per call" % L.MAX_FIELDS)
         dev = D.pick_device(*delta)
         dk = [_P.fft3d_r2c_device(_cube(d, dev, "delta[%d]" % i)) for i, d in enumerate(delta)]
         print("Time FFTS = %.2f" % (time.time() - start))
         start2 = time.time()
-        out, lay = _P.bin_device(dk, [_P.MAS_function(m) for m in MAS], dims, axis, flags=L.PK_CROSS_IMAG)
-        o = _P.finalize_device(out, lay, BoxSize, dims)
+        o = _P.spectra(dk, [_P.MAS_function(m) for m in MAS], dims, axis, BoxSize, flags=L.PK_CROSS_IMAG)
         del dk
         print("Time loop = %.2f" % (time.time() - start2))
         self.k1D, self.Nmodes1D, self.Pk1D, self.PkX1D = o["k1D"], o["Nmodes1D"], o["Pk1D"], o["PkX1D"]

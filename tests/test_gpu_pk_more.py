@@ -214,3 +214,25 @@ def test_properties_at_size(env):
     p = quiet(PKL.Pk_plane, img, MC.BOX, "None", 1, False)
     assert int(p.Nmodes.sum()) == (M * M - 4) // 2 + 4 - 1
     assert abs(np.mean(p.Pk[p.Nmodes > 1000]) / (MC.BOX ** 2 / M ** 2) - 1.0) < 0.02
+
+
+@pytest.mark.parametrize("N,F", [(20, 6), (15, 5)])
+def test_xpk_imag_more_fields_than_one_launch(env, oracle, N, F):
+    """More than PYL_MAX_FIELDS fields: block decomposition over launches, pairs in the reference's order, and
+    the antisymmetric cross term keeps its sign (i < j)."""
+    torch, PKL, PM = env
+    from oracle import cpu_more
+    rng = np.random.default_rng(N * F)
+    base = rng.standard_normal((N, N, N)).astype(np.float32)
+    fields = [(np.roll(base, i, axis=i % 3) + 0.5 * rng.standard_normal((N, N, N))).astype(np.float32) for i in range(F)]
+    mas = (["CIC", "PCS", "NGP", "TSC", "None", "CIC"])[:F]
+    got = quiet(PKL.XPk_imag, fields, MC.BOX, 1, mas, 1)
+    ref = quiet(cpu_more.XPk_imag, fields, MC.BOX, 1, mas, 1)
+    X = F * (F - 1) // 2
+    assert got.XPk.shape == ref.XPk.shape == (ref.k3D.size, 3, X)
+    assert np.array_equal(got.Nmodes3D, ref.Nmodes3D) and np.array_equal(got.Nmodes2D, ref.Nmodes2D)
+    pairs = [(i, j) for i in range(F) for j in range(i + 1, F)]
+    for x, (i, j) in enumerate(pairs):
+        scale = np.sqrt(np.abs(ref.Pk[:, 0, i] * ref.Pk[:, 0, j]))
+        assert np.max(np.abs(got.XPk[:, 0, x] - ref.XPk[:, 0, x]) / np.maximum(np.abs(ref.XPk[:, 0, x]), 0.1 * scale)) < TOL * 3
+    assert np.max(np.abs(got.Pk[:, 0, :] / ref.Pk[:, 0, :] - 1)) < TOL

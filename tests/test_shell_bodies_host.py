@@ -71,7 +71,7 @@ def z(n):
 
 # sms = 1 -> one segment (a thread walks the whole ky axis); 148 -> the B200 geometry; 4000 -> 8-step segments
 @pytest.mark.parametrize("sms", [1, 148, 4000])
-@pytest.mark.parametrize("N", [12, 9, 32])
+@pytest.mark.parametrize("N", [2, 3, 4, 5, 12, 9, 32])
 def test_velocity_kinds(harness, oracle, N, sms):
     from oracle import cpu as C, cpu_more as M
     import ctypes as ct
@@ -96,7 +96,7 @@ def test_velocity_kinds(harness, oracle, N, sms):
 
 
 @pytest.mark.parametrize("sms", [1, 148])
-@pytest.mark.parametrize("N", [12, 9, 64])
+@pytest.mark.parametrize("N", [2, 3, 4, 5, 12, 9, 64])
 def test_plane_kinds(harness, oracle, N, sms):
     from oracle import cpu as C, cpu_more as M
     rng = np.random.default_rng(100 + N)
@@ -116,7 +116,7 @@ def test_plane_kinds(harness, oracle, N, sms):
 
 
 @pytest.mark.parametrize("sms", [1, 148])
-@pytest.mark.parametrize("N,axis", [(12, 0), (9, 1), (20, 2)])
+@pytest.mark.parametrize("N,axis", [(2, 0), (3, 1), (4, 2), (5, 0), (12, 0), (9, 1), (20, 2)])
 def test_xi_kind(harness, oracle, N, axis, sms):
     from oracle import cpu as C, cpu_more as M
     rng = np.random.default_rng(200 + N)
