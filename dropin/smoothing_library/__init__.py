@@ -1,4 +1,4 @@
-"""`import smoothing_library as SL` resolving to the B200-native `field_smoothing`.
+"""`import smoothing_library as SL` resolving to the B200-native implementation.
 
 Put this directory (dropin/) on PYTHONPATH ahead of the Pylians3 install; see INTEGRATION.md."""
 import os as _os
@@ -7,4 +7,4 @@ import sys as _sys
 _root = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 if _root not in _sys.path:
     _sys.path.insert(0, _root)
-from pylians3_b200.smoothing_library import field_smoothing  # noqa: E402,F401
+from pylians3_b200.smoothing_library import *  # noqa: E402,F401,F403

@@ -20,7 +20,9 @@
  *   library/Pk_library/Pk_library.pyx:470-499, 905-1016, 1151-1200, 1273-1316, 1386-1432, 1515-1568,
  *       1909-1929, 2004-2037, 2198-2267, 2335-2412   the loops of Pk_plane, XPk_imag, XPk_plane, Pk_theta,
  *       XPk_dv, XPk_vv, correct_MAS, expected_Pk, Xi, XXi (section 5; no native ABI exists)
- *   library/smoothing_library/smoothing_library.pyx:227-232 field_smoothing's mode loop
+ *   library/smoothing_library/smoothing_library.pyx:227-232 field_smoothing's mode loop; :37-114, :141-203 the
+ *       filter loops of FT_filter / FT_filter_2D; :255-258 field_smoothing_2D's loop
+ *   library/Pk_library/Pk_library.pyx:213-226 IFFT2Dr_f(a, threads)
  *
  * Ownership: all device pointers are BORROWED.  The device-pointer entry points never
  * allocate: scratch memory is passed in (`ws`, sized by the matching *_workspace_bytes
@@ -163,6 +165,9 @@ int pyl_transpose_scatter(const float *slab_k, void *const *peer_recv, const int
 size_t pyl_fft_c2r_workspace_bytes(int dims);
 int pyl_fft_c2r(float *delta_k /* interleaved re,im */, float *delta, int dims, void *ws, size_t ws_bytes,
                 pyl_stream_t stream);
+/* Same for one (dims,dims/2+1) complex64 image -> (dims,dims) float32 (IFFT2Dr_f, Pk_library.pyx:213-226). */
+size_t pyl_fft2d_c2r_workspace_bytes(int dims);
+int pyl_fft2d_c2r(float *image_k, float *image, int dims, void *ws, size_t ws_bytes, pyl_stream_t stream);
 /* release every cached cuFFT plan of the calling thread's current device */
 int pyl_fft_clear_plans(void);
 
@@ -282,6 +287,16 @@ int pyl_modes_power(float *a_k, const float *b_k, int dims, int mas_a, int mas_b
                     pyl_stream_t stream);
 /* a_k[i] *= b_k[i], complex64 (smoothing_library.pyx:227-232, field_k * filter_k) */
 int pyl_cmul_inplace(float *a_k, const float *b_k, int64_t n_complex, pyl_stream_t stream);
+/* Smoothing filters placed on a grid (smoothing_library.pyx:37-100 FT_filter, :141-191 FT_filter_2D), axes = 3 | 2:
+ *   kind 0 Top-Hat   : out = float32 (dims,)*axes, 1 where d2 <= R2 (d2 = squared distance in cells, periodic)
+ *   kind 1 Gaussian  : out = float32 (dims,)*axes, exp(-d2 / (2 R2)) evaluated in double
+ *   kind 2 Top-Hat-k : out = complex64 (dims,)*(axes-1) x (dims/2+1), 1 where kmin <= kF*sqrt(d2) < kmax, DC kept
+ * R2, kF, kmin, kmax are float32 like the reference's C locals.  Normalisation (sum -> pyl_sum_f64, division ->
+ * pyl_divide_by_f64) and the transforms are separate calls. */
+int pyl_filter_fill(int kind, void *out, int dims, int axes, float R2, float kF, float kmin, float kmax,
+                    pyl_stream_t stream);
+/* x[i] = float(double(x[i]) / divisor[0]), divisor a DEVICE double (smoothing_library.pyx:110-114) */
+int pyl_divide_by_f64(float *x, int64_t n, const double *divisor, pyl_stream_t stream);
 /* v[i] *= (1 + delta[i]), float32: the momentum fields of XPk_dv / XPk_vv (Pk_library.pyx:1367, :1491-1492) */
 int pyl_mul_one_plus(float *v, const float *delta, int64_t n, pyl_stream_t stream);
 

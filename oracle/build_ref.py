@@ -11,6 +11,9 @@ git-ignored but still travels to the GPU box):
   oracle/_ref/Pk_library/Pk_library*.so    <- library/Pk_library/Pk_library.pyx
   oracle/_ref/redshift_space_library/redshift_space_library*.so
                                            <- library/redshift_space_library/redshift_space_library.pyx
+  oracle/_ref/smoothing_library/smoothing_library*.so
+                                           <- library/smoothing_library/smoothing_library.pyx (built with -fopenmp:
+                                              its loops are `prange`; it imports Pk_library at run time)
   oracle/_ref/omp/MAS_library*.so          <- same MAS sources, with -fopenmp at compile
                                               time (NON-default build: the reference's
                                               setup.py:22 typo drops -fopenmp)
@@ -69,7 +72,8 @@ def build(force=False):
     pk_so = os.path.join(OUT, "Pk_library", "Pk_library" + suf)
     omp_so = os.path.join(OUT, "omp", "MAS_library" + suf)
     rsd_so = os.path.join(OUT, "redshift_space_library", "redshift_space_library" + suf)
-    have = all(os.path.exists(p) for p in (mas_so, pk_so, omp_so, rsd_so))
+    sm_so = os.path.join(OUT, "smoothing_library", "smoothing_library" + suf)
+    have = all(os.path.exists(p) for p in (mas_so, pk_so, omp_so, rsd_so, sm_so))
     if have and not force:
         return True
     if not available():
@@ -88,6 +92,10 @@ def build(force=False):
     rsd_c = os.path.join(gen, "redshift_space_library.c")
     _cythonize(os.path.join(rsd_dir, "redshift_space_library.pyx"), rsd_c, rsd_dir)
     _compile([rsd_c], rsd_so, [rsd_dir])
+    sm_dir = os.path.join(REF, "library", "smoothing_library")
+    sm_c = os.path.join(gen, "smoothing_library.c")
+    _cythonize(os.path.join(sm_dir, "smoothing_library.pyx"), sm_c, sm_dir)
+    _compile([sm_c], sm_so, [sm_dir], extra=["-fopenmp"])
     shutil.rmtree(gen, ignore_errors=True)   # generated C is large; keep only the .so files
     return True
 

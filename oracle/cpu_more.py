@@ -322,3 +322,63 @@ def field_smoothing(field, filter_k, threads=1):
     fk = _c.fft3d_r2c(field, threads)
     fk = (fk * np.asarray(filter_k, dtype=np.complex64)).astype(np.complex64)
     return ifft3d_c2r(fk, dims, threads)
+
+
+# ---- smoothing_library: filters (smoothing_library.pyx:20-120, 123-209) and the 2D smoothing (:243-262) -------
+def _signed(n):
+    i = np.arange(n)
+    return np.where(i > n // 2, i - n, i)
+
+
+def _ft_filter(BoxSize, R, dims, Filter, kmin, kmax, nd):
+    """Common body of FT_filter / FT_filter_2D.  C-typed locals of the reference: BoxSize, R, kmin, kmax,
+    R_grid, R2, kF, k, factor are `float`; d2 is `int`; normalization is `double`."""
+    if Filter not in ["Top-Hat", "Gaussian", "Top-Hat-k"]:
+        raise Exception("Filter %s not implemented!" % Filter)
+    f32 = np.float32
+    BoxSize, R, kmin, kmax = f32(BoxSize), f32(R), f32(kmin), f32(kmax)
+    middle = dims // 2
+    R_grid = f32(f32(R * f32(dims)) / BoxSize)                  # (R*dims/BoxSize), float arithmetic
+    R2 = f32(R_grid * R_grid)
+    kF = f32(2.0 * np.pi / float(BoxSize))
+    s = _signed(dims)
+    if nd == 3:
+        d2 = s[:, None, None] ** 2 + s[None, :, None] ** 2 + s[None, None, :] ** 2
+        d2h = s[:, None, None] ** 2 + s[None, :, None] ** 2 + np.arange(middle + 1)[None, None, :] ** 2
+    else:
+        d2 = s[:, None] ** 2 + s[None, :] ** 2
+        d2h = s[:, None] ** 2 + np.arange(middle + 1)[None, :] ** 2
+    if Filter == "Top-Hat":
+        field = np.where(d2.astype(f32) <= R2, f32(1.0), f32(0.0)).astype(f32)          # `d2<=R2`: int vs float
+        normalization = float(np.sum(field, dtype=np.float64))
+    elif Filter == "Gaussian":
+        field = np.exp(-d2.astype(np.float64) / (2.0 * float(R2))).astype(f32)          # double exp, float store
+        normalization = float(np.sum(field, dtype=np.float64))
+    else:
+        k = (float(kF) * np.sqrt(d2h.astype(np.float64))).astype(f32)                   # `cdef float k`
+        field_k = np.where((k >= kmin) & (k < kmax), 1.0, 0.0).astype(np.complex64)
+        field_k[(0,) * nd] = 1.0                                                        # "dont mess with DC mode"
+        field = _sfft.irfftn(field_k, s=(dims,) * nd, axes=tuple(range(nd))).astype(f32)
+        normalization = float(np.sum(field, dtype=np.float64))
+    field = (field.astype(np.float64) / normalization).astype(f32)                      # float / double
+    return _sfft.rfftn(field, axes=tuple(range(nd))).astype(np.complex64)
+
+
+def FT_filter(BoxSize, R, dims, Filter, threads=1, kmin=0, kmax=0):
+    """smoothing_library.pyx:20-120."""
+    return _ft_filter(BoxSize, R, dims, Filter, kmin, kmax, 3)
+
+
+def FT_filter_2D(BoxSize, R, grid, Filter, threads=1, kmin=0, kmax=0):
+    """smoothing_library.pyx:123-209."""
+    return _ft_filter(BoxSize, R, grid, Filter, kmin, kmax, 2)
+
+
+def field_smoothing_2D(field, filter_k, threads=1):
+    """smoothing_library.pyx:243-262."""
+    grid = field.shape[0]
+    if field.shape[0] != filter_k.shape[0]:
+        raise Exception("field and filter have different grids!!!")
+    fk = fft2d_r2c(field, threads)
+    fk = (fk * np.asarray(filter_k, dtype=np.complex64)).astype(np.complex64)
+    return _sfft.irfftn(fk, s=(grid, grid), axes=(0, 1), workers=threads).astype(np.float32)

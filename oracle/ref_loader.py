@@ -70,3 +70,23 @@ def ref_PKL():
                 sys.path.remove(shim)
         _cache["PKL"] = _load("ref.Pk_library", path)
     return _cache["PKL"]
+
+
+def ref_SL():
+    """The reference's smoothing_library extension (FT_filter, field_smoothing, 2D variants).  It does
+    `import Pk_library as PKL` at import time (smoothing_library.pyx:9): the compiled reference Pk_library is
+    registered under that bare name for the duration of the import."""
+    if "SL" not in _cache:
+        path = _find("smoothing_library", "smoothing_library")
+        if path is None:
+            raise ImportError("oracle/_ref not built: run `python oracle/build_ref.py` where /root/reference exists")
+        saved = sys.modules.get("Pk_library")
+        sys.modules["Pk_library"] = ref_PKL()
+        try:
+            _cache["SL"] = _load("ref.smoothing_library", path)
+        finally:
+            if saved is None:
+                del sys.modules["Pk_library"]
+            else:
+                sys.modules["Pk_library"] = saved
+    return _cache["SL"]

@@ -85,6 +85,10 @@ PROTOTYPES = {
     "pyl_modes_power": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "pyl_cmul_inplace": (_i, [_vp, _vp, _i64, _vp]),
     "pyl_mul_one_plus": (_i, [_vp, _vp, _i64, _vp]),
+    "pyl_filter_fill": (_i, [_i, _vp, _i, _i, _f, _f, _f, _f, _vp]),
+    "pyl_divide_by_f64": (_i, [_vp, _i64, _vp, _vp]),
+    "pyl_fft2d_c2r_workspace_bytes": (_sz, [_i]),
+    "pyl_fft2d_c2r": (_i, [_vp, _vp, _i, _vp, _sz, _vp]),
     "pyl_NGP": (_i, [_vp, _vp, _vp, _l, _i, _i, _f, _i]),
     "pyl_CIC": (_i, [_vp, _vp, _vp, _l, _i, _i, _f, _i]),
     "pyl_TSC": (_i, [_vp, _vp, _vp, _l, _i, _i, _f, _i]),

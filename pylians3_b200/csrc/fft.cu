@@ -13,7 +13,7 @@
 
 namespace pyl {
 
-enum PlanKind { PLAN_R2C_3D = 0, PLAN_R2C_YZ = 1, PLAN_C2C_X = 2, PLAN_C2R_3D = 3 };
+enum PlanKind { PLAN_R2C_3D = 0, PLAN_R2C_YZ = 1, PLAN_C2C_X = 2, PLAN_C2R_3D = 3, PLAN_C2R_2D = 4 };
 
 struct Plan {
     cufftHandle handle = 0;
@@ -73,6 +73,9 @@ static int get_plan(PlanKind kind, int dims, int extent, Plan *out) {
             long long n[3] = {N, N, N};
             r = cufftMakePlanMany64(p.handle, 3, n, nullptr, 1, N * N * nz, nullptr, 1, N * N * N,
                                     CUFFT_C2R, 1, &p.work);
+        } else if (kind == PLAN_C2R_2D) {
+            long long n[2] = {N, N};
+            r = cufftMakePlanMany64(p.handle, 2, n, nullptr, 1, N * nz, nullptr, 1, N * N, CUFFT_C2R, 1, &p.work);
         } else if (kind == PLAN_R2C_YZ) {
             long long n[2] = {N, N};
             r = cufftMakePlanMany64(p.handle, 2, n, nullptr, 1, N * N, nullptr, 1, N * nz, CUFFT_R2C,
@@ -152,6 +155,26 @@ int pyl_fft_c2r(float *delta_k, float *delta, int dims, void *ws, size_t ws_byte
     st = bind(p, ws, ws_bytes, as_stream(stream));
     if (st != PYL_OK) return st;
     PYL_CUFFT_CHECK(cufftExecC2R(p.handle, reinterpret_cast<cufftComplex *>(delta_k), delta));
+    return PYL_OK;
+}
+
+size_t pyl_fft2d_c2r_workspace_bytes(int dims) {
+    if (dims <= 0) return 0;
+    Plan p;
+    if (get_plan(PLAN_C2R_2D, dims, 0, &p) != PYL_OK) return (size_t)-1;
+    return p.work;
+}
+
+int pyl_fft2d_c2r(float *image_k, float *image, int dims, void *ws, size_t ws_bytes, pyl_stream_t stream) {
+    PYL_REQUIRE(dims > 0, "pyl_fft2d_c2r: dims must be positive");
+    PYL_REQUIRE(image != nullptr && image_k != nullptr, "pyl_fft2d_c2r: NULL pointer");
+    PYL_REQUIRE((void *)image != (void *)image_k, "pyl_fft2d_c2r: transform is out of place");
+    Plan p;
+    int st = get_plan(PLAN_C2R_2D, dims, 0, &p);
+    if (st != PYL_OK) return st;
+    st = bind(p, ws, ws_bytes, as_stream(stream));
+    if (st != PYL_OK) return st;
+    PYL_CUFFT_CHECK(cufftExecC2R(p.handle, reinterpret_cast<cufftComplex *>(image_k), image));
     return PYL_OK;
 }
 

@@ -79,6 +79,21 @@ __global__ void __launch_bounds__(256) mul_one_plus_kernel(float *__restrict__ v
         v[i] = __fmul_rn(v[i], __fadd_rn(1.0f, __ldg(d + i)));
 }
 
+template <int KIND>
+__global__ void __launch_bounds__(256) filter_kernel(const FilterArgs A) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < A.total; e += stride) filter_element<KIND>(A, e);
+}
+
+// x[i] = float(double(x[i]) / d[0]) : `field[i,j,l] = field[i,j,l]/normalization` with a double normalisation
+// (smoothing_library.pyx:110-114)
+__global__ void __launch_bounds__(256) divide_by_f64_kernel(float *__restrict__ x, long long n, const double *__restrict__ d) {
+    const double div = d[0];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        x[i] = __double2float_rn(__ddiv_rn((double)x[i], div));
+}
+
 static int shell_bins(int kind, int dims) {
     const double m = (double)(dims / 2);
     const bool plane = (kind == SK_PLANE || kind == SK_XPLANE);
@@ -233,6 +248,35 @@ int pyl_cmul_inplace(float *a_k, const float *b_k, int64_t n_complex, pyl_stream
     PYL_REQUIRE(a_k != nullptr && b_k != nullptr, "pyl_cmul_inplace: NULL pointer");
     cmul_kernel<<<grid_for(n_complex, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<float2 *>(a_k),
                                                                          reinterpret_cast<const float2 *>(b_k), n_complex);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
+int pyl_filter_fill(int kind, void *out, int dims, int axes, float R2, float kF, float kmin, float kmax,
+                    pyl_stream_t stream) {
+    PYL_REQUIRE(kind >= FK_TOPHAT && kind <= FK_TOPHAT_K, "pyl_filter_fill: kind must be 0 (Top-Hat), 1 (Gaussian) or 2 (Top-Hat-k)");
+    PYL_REQUIRE(out != nullptr && dims > 0 && (axes == 2 || axes == 3), "pyl_filter_fill: bad output, dims or axes");
+    FilterArgs A;
+    A.real = reinterpret_cast<float *>(out);
+    A.cplx = reinterpret_cast<float2 *>(out);
+    A.N = dims; A.m = dims / 2; A.axes = axes;
+    A.R2 = R2; A.kF = kF; A.kmin = kmin; A.kmax = kmax;
+    const long long last = (kind == FK_TOPHAT_K) ? dims / 2 + 1 : dims;
+    A.total = (axes == 3 ? (long long)dims * dims : (long long)dims) * last;
+    const unsigned g = grid_for(A.total, 256);
+    cudaStream_t s = as_stream(stream);
+    if (kind == FK_TOPHAT) filter_kernel<FK_TOPHAT><<<g, 256, 0, s>>>(A);
+    else if (kind == FK_GAUSSIAN) filter_kernel<FK_GAUSSIAN><<<g, 256, 0, s>>>(A);
+    else filter_kernel<FK_TOPHAT_K><<<g, 256, 0, s>>>(A);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
+int pyl_divide_by_f64(float *x, int64_t n, const double *divisor, pyl_stream_t stream) {
+    PYL_REQUIRE(n >= 0, "pyl_divide_by_f64: negative size");
+    if (n == 0) return PYL_OK;
+    PYL_REQUIRE(x != nullptr && divisor != nullptr, "pyl_divide_by_f64: NULL pointer");
+    divide_by_f64_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, n, divisor);
     PYL_LAUNCH_CHECK();
     return PYL_OK;
 }

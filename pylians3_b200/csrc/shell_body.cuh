@@ -347,4 +347,40 @@ PYL_HD void mode_element(const ModeArgs &A, long long e) {
     A.a[e] = v;
 }
 
+// ---- smoothing filters placed on a grid (smoothing_library.pyx:37-100 / :141-191) --------------------------------
+enum FilterKind { FK_TOPHAT = 0, FK_GAUSSIAN = 1, FK_TOPHAT_K = 2 };
+
+struct FilterArgs {
+    float *real;             // FK_TOPHAT / FK_GAUSSIAN: (N,)*axes float32
+    float2 *cplx;            // FK_TOPHAT_K: (N,)*(axes-1) x (N/2+1) complex64
+    int N, m, axes;
+    float R2, kF, kmin, kmax;       // `cdef float` in the reference
+    long long total;
+};
+
+// element e of the filter grid.  d2 is an int, `d2 <= R2` compares it as a float, the Gaussian is a double exp
+// stored as float, k = kF*sqrt(d2) is a float (the reference's C types).
+template <int KIND>
+PYL_HD void filter_element(const FilterArgs &A, long long e) {
+    const int N = A.N, m = A.m;
+    const int nlast = (KIND == FK_TOPHAT_K) ? m + 1 : N;
+    const int il = (int)(e % nlast);
+    long long q = e / nlast;
+    const int ij = (int)(q % N);
+    const int ii = (A.axes == 3) ? (int)(q / N) : 0;
+    const int l1 = il > m ? il - N : il, j1 = ij > m ? ij - N : ij, i1 = ii > m ? ii - N : ii;
+    const int d2 = i1 * i1 + j1 * j1 + l1 * l1;
+    if (KIND == FK_TOPHAT) {
+        A.real[e] = ((float)d2 <= A.R2) ? 1.0f : 0.0f;
+    } else if (KIND == FK_GAUSSIAN) {
+        A.real[e] = (float)exp(-(double)d2 / (2.0 * (double)A.R2));
+    } else {
+        const float k = (float)((double)A.kF * sqrt((double)d2));
+        float2 v;
+        v.x = (e == 0 || (k >= A.kmin && k < A.kmax)) ? 1.0f : 0.0f;       // the DC mode is always kept
+        v.y = 0.0f;
+        A.cplx[e] = v;
+    }
+}
+
 }  // namespace pyl

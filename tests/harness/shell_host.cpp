@@ -95,4 +95,20 @@ int harness_modes(int op, float *a, const float *b, int dims, int mas_a, int mas
     return 0;
 }
 
+int harness_filter(int kind, void *out, int dims, int axes, float R2, float kF, float kmin, float kmax) {
+    FilterArgs A;
+    A.real = reinterpret_cast<float *>(out);
+    A.cplx = reinterpret_cast<float2 *>(out);
+    A.N = dims; A.m = dims / 2; A.axes = axes;
+    A.R2 = R2; A.kF = kF; A.kmin = kmin; A.kmax = kmax;
+    const long long last = (kind == FK_TOPHAT_K) ? dims / 2 + 1 : dims;
+    A.total = (axes == 3 ? (long long)dims * dims : (long long)dims) * last;
+    for (long long e = 0; e < A.total; e++) {
+        if (kind == FK_TOPHAT) filter_element<FK_TOPHAT>(A, e);
+        else if (kind == FK_GAUSSIAN) filter_element<FK_GAUSSIAN>(A, e);
+        else filter_element<FK_TOPHAT_K>(A, e);
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -16,6 +16,36 @@ _gen = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(_gen)
 inputs = _gen.inputs
 SIZES = _gen.SIZES
+FILTERS = _gen.FILTERS
+
+
+def run_smoothing(sl, N, I=None):
+    """The smoothing_library entry points of `sl` under the golden file's keys."""
+    I = inputs(N) if I is None else I
+    t = "N%d_" % N
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        for name, (F, R, kmin, kmax) in FILTERS.items():
+            out[t + "sm_f3_" + name] = np.asarray(sl.FT_filter(BOX, R, N, F, 2, kmin, kmax))
+            out[t + "sm_f2_" + name] = np.asarray(sl.FT_filter_2D(BOX, R, N, F, 2, kmin, kmax))
+        out[t + "sm_s3"] = np.asarray(sl.field_smoothing(I["d1"], out[t + "sm_f3_gauss"], 2))
+        out[t + "sm_s2"] = np.asarray(sl.field_smoothing_2D(I["img1"], out[t + "sm_f2_tophat"], 2))
+    return out
+
+
+def compare_smoothing(got, ref, tol):
+    """Filters and smoothed fields: complex / real arrays, error relative to the array's largest amplitude."""
+    bad = []
+    for key, g in got.items():
+        r = np.asarray(ref[key])
+        g = np.asarray(g)
+        if g.shape != r.shape or g.dtype != r.dtype:
+            bad.append((key, "shape/dtype", g.shape, g.dtype, r.shape, r.dtype))
+            continue
+        e = float(np.max(np.abs(g - r)) / np.max(np.abs(r)))
+        if not e < tol:
+            bad.append((key, e, tol))
+    return bad
 
 
 def run_all(impl, N, I=None):

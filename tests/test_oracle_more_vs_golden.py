@@ -18,9 +18,19 @@ def golden():
 def test_sibling_oracle_matches_reference(oracle, golden, N):
     from oracle import cpu_more
     got = MC.run_all(cpu_more, N)
-    assert set(got) == {k for k in golden if k.startswith("N%d_" % N)}
+    assert set(got) == {k for k in golden if k.startswith("N%d_" % N) and "_sm_" not in k}
     # same transform (pocketfft) on both sides: only float64 association / float32 FMA contraction differ
     bad = MC.compare(got, golden, tol=2e-6)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("N", MC.SIZES)
+def test_smoothing_oracle_matches_reference(oracle, golden, N):
+    """smoothing_library: FT_filter / FT_filter_2D for the three filters, field_smoothing and its 2D form."""
+    from oracle import cpu_more
+    got = MC.run_smoothing(cpu_more, N)
+    assert set(got) == {k for k in golden if k.startswith("N%d_sm_" % N)}
+    bad = MC.compare_smoothing(got, golden, tol=1e-6)
     assert not bad, bad
 
 

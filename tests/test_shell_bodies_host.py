@@ -36,6 +36,7 @@ def harness():
                                 ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
                                 ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_void_p]
     L.harness_shell_bins.restype = ctypes.c_int
+    L.harness_filter.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_float] * 4
     L.harness_modes.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return L
 
@@ -170,3 +171,26 @@ def test_mode_passes(harness, oracle, N):
     xg, xr = M.ifft3d_c2r(g, N), M.ifft3d_c2r(r, N)
     assert np.max(np.abs(xg - xr)) < 2e-6 * np.abs(xr).max()
     assert np.max(np.abs(xr - d1)) > 0.05 * np.abs(d1).max()          # the deconvolution did something
+
+
+@pytest.mark.parametrize("N", [2, 3, 12, 9])
+@pytest.mark.parametrize("nd", [3, 2])
+def test_filter_bodies(harness, oracle, N, nd):
+    """filter_element (Top-Hat, Gaussian, Top-Hat-k) -> normalise -> transform == the oracle's FT_filter."""
+    from oracle import cpu_more as M
+    import scipy.fft as sfft
+    f32 = np.float32
+    for name, (F, R, kmin, kmax) in MC.FILTERS.items():
+        R_grid = f32(f32(f32(R) * f32(N)) / f32(MC.BOX))
+        R2, kF = f32(R_grid * R_grid), f32(2.0 * np.pi / MC.BOX)
+        kind = {"Top-Hat": 0, "Gaussian": 1, "Top-Hat-k": 2}[F]
+        if kind == 2:
+            out = np.zeros((N,) * (nd - 1) + (N // 2 + 1,), np.complex64)
+        else:
+            out = np.zeros((N,) * nd, np.float32)
+        harness.harness_filter(kind, out.ctypes.data, N, nd, R2, kF, f32(kmin), f32(kmax))
+        field = sfft.irfftn(out, s=(N,) * nd, axes=tuple(range(nd))).astype(f32) if kind == 2 else out
+        field = (field.astype(np.float64) / float(np.sum(field, dtype=np.float64))).astype(f32)
+        got = sfft.rfftn(field, axes=tuple(range(nd))).astype(np.complex64)
+        ref = (M.FT_filter if nd == 3 else M.FT_filter_2D)(MC.BOX, R, N, F, 1, kmin, kmax)
+        assert np.max(np.abs(got - ref)) < 1e-6 * np.max(np.abs(ref)), (name, nd)
