@@ -110,7 +110,7 @@ def _cross_floor(key, ref):
     return None
 
 
-def compare(got, ref, tol, exact_counts=True, ktol=1e-12, fft_eps=0.0):
+def compare(got, ref, tol, ktol=1e-12, fft_eps=0.0):
     """Every key of `got` against `ref`: |got - ref| <= tol * den + fft_eps * sqrt(den * peak).
 
     Counts (...Nm, ...Nmodes*) bit-exact; wavenumbers / radii to `ktol`.  For everything else `den` is the

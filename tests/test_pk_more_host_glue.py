@@ -3,7 +3,6 @@ sequence, unit conversions) driven end to end WITHOUT a GPU.  The device primiti
 test doubles: transforms by pocketfft, and -- for the kernels -- the real per-thread bodies of shell_body.cuh run
 serially by tests/harness/shell_host.cpp.  Results are held to the golden outputs of the compiled reference.
 The product itself has no such path: without the patches every entry point raises (no CUDA device)."""
-import ctypes
 import os
 
 import numpy as np
@@ -51,9 +50,6 @@ def fake_device(request, monkeypatch, harness):  # noqa: F811
         for v in V:
             v *= (np.float32(1.0) + delta_d)
         return list(V)
-
-    class FakeTorchTable:                      # expected_Pk ships its table through torch.from_numpy(...).to(dev)
-        pass
 
     monkeypatch.setattr(D, "require_cuda", lambda: None)
     monkeypatch.setattr(D, "pick_device", lambda *a: None)

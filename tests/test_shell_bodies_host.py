@@ -75,7 +75,6 @@ def z(n):
 @pytest.mark.parametrize("N", [2, 3, 4, 5, 12, 9, 32])
 def test_velocity_kinds(harness, oracle, N, sms):
     from oracle import cpu as C, cpu_more as M
-    import ctypes as ct
     rng = np.random.default_rng(N)
     F = [rng.standard_normal((N, N, N)).astype(np.float32) for _ in range(7)]
     dks = [np.ascontiguousarray(C.fft3d_r2c(f)) for f in F]
