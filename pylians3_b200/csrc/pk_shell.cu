@@ -3,7 +3,8 @@
 // Replaces the serial loops of library/Pk_library/Pk_library.pyx: Pk_plane :470-499, XPk_plane :1151-1200,
 // Pk_theta :1273-1316, XPk_dv :1386-1432, XPk_vv :1515-1568, expected_Pk :2004-2037, the real-space binning of
 // Xi / XXi :2233-2267 / :2378-2412, the mode loops of correct_MAS :1909-1929 and Xi / XXi :2198-2218 / :2335-2362,
-// and smoothing_library.pyx:227-232 (field_k * filter_k).
+// smoothing_library.pyx:227-232 / :255-258 (field_k * filter_k) and the filter loops of FT_filter / FT_filter_2D
+// (smoothing_library.pyx:37-114, :141-203).
 //
 // Accumulation: each thread keeps the sums of its current |k| bin in registers and issues red.global.add.f64 /
 // .u64 only on a bin change, into one of SHELL_NREP replicas of the (small) accumulator block chosen by
