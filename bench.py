@@ -39,6 +39,26 @@ GRID_FOR_GPUS = {1: 512, 2: 640, 4: 800, 8: 1024}
 NCU_DEPOSIT_TRAFFIC = {("CIC", 512): 7.65e9}
 
 
+_RESULT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: a duplicate of the original fd 1 is kept for the result, and fd 1 itself is
+    pointed at stderr, so that anything a library prints to stdout (NCCL's "NCCL version ..." banner arrives on the
+    C-level stdout even with NCCL_DEBUG_FILE set) lands on stderr instead."""
+    global _RESULT
+    if _RESULT is None:
+        sys.stdout.flush()
+        _RESULT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT if _RESULT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peak_hbm():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -164,7 +184,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "particles/s", "cores": threads if kind == "reference" else 1,
                              "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def metric_name(grid):
@@ -384,6 +404,19 @@ def run_ours(args):
                     "kernels": "tile_count + tile_scatter + tile_deposit (one pyl_deposit call)",
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                     "avg_launch_ms": ma_ms, "share_of_step": ma_ms / ms_step}
+    if roofline is None and world > 1:
+        # per-GPU deposit roofline of the sharded step, from the stage breakdown (max over ranks; the stage
+        # includes the ghost-plane exchange).  Guarded: a missing stage leaves the key null, never breaks the line.
+        try:
+            dep_ms = float(stages["deposit+halo"])
+            alg_bytes = (npart * 12 + 8 * grid_n ** 3) / world
+            achieved = alg_bytes / (dep_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "deposit + halo exchange, per GPU (%s, pyl_deposit_slab)" % MAS,
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dep_ms,
+                        "share_of_step": dep_ms / ms_step}
+        except Exception:
+            roofline = None
     pk = pk_holder["pk"]
     line = {"metric": metric_name(grid_n), "value": value, "unit": "particles/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -397,7 +430,7 @@ def run_ours(args):
                       "modes_counted": int(pk.Nmodes3D.sum()) + 1}}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -412,6 +445,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
