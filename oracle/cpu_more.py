@@ -382,3 +382,39 @@ def field_smoothing_2D(field, filter_k, threads=1):
     fk = fft2d_r2c(field, threads)
     fk = (fk * np.asarray(filter_k, dtype=np.complex64)).astype(np.complex64)
     return _sfft.irfftn(fk, s=(grid, grid), axes=(0, 1), workers=threads).astype(np.float32)
+
+
+class XXi_multi:
+    """Pk_library.pyx:2443-2670: auto- and cross-correlation function multipoles of several fields.
+    As in the reference, a cross term (i, j) is deconvolved with field i's window for BOTH fields (:2548-2553)."""
+
+    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1):
+        dims = len(delta[0]); F = len(delta)
+        for d in delta[1:]:
+            if len(d) != dims:
+                raise ValueError("Fields have different grid sizes!!!")
+        kmax = _c.frequencies(BoxSize, dims)[4]
+        dk = [np.ascontiguousarray(_c.fft3d_r2c(d, threads)) for d in delta]
+        mi = [_c.MAS_function(m) for m in MAS]
+        grids = []
+        for i in range(F):
+            a = dk[i].copy()
+            _lib().oracle_xi_modes(_cf(a), None, dims, mi[i], 0)
+            grids.append(ifft3d_c2r(a, dims, threads))
+        xgrids = []
+        for i in range(F):
+            for j in range(i + 1, F):
+                a = dk[i].copy()
+                _lib().oracle_xi_modes(_cf(a), _cf(dk[j]), dims, mi[i], mi[i])
+                xgrids.append(ifft3d_c2r(a, dims, threads))
+        X = len(xgrids)
+        xi = np.zeros((kmax, 3, F)); Xxi = np.zeros((kmax, 3, X))
+
+        class _R:
+            pass
+        for n, (src, dst) in enumerate([(g, xi) for g in grids] + [(g, Xxi) for g in xgrids]):
+            r = _R()
+            _xi_finish(r, src, dims, BoxSize, axis)
+            dst[:, :, n if n < F else n - F] = r.xi
+            self.r3D, self.Nmodes3D = r.r3D, r.Nmodes3D
+        self.xi, self.Xxi = xi, Xxi

@@ -4,7 +4,7 @@ Mirrors library/Pk_library/Pk_library.pyx, same names / positional order / defau
   frequencies_2D :64-69, check_number_modes_2D :102-114, IFFT3Dr_f :149-163, FFT2Dr_f :181-194,
   class Pk_plane :435-511, class XPk_imag :811-1077, class XPk_plane :1093-1220, Pk_theta :1238-1326,
   XPk_dv :1345-1444, XPk_vv :1467-1580, XPk_2D :1754-1865, correct_MAS :1882-1939, expected_Pk :1956-2047,
-  class Xi :2168-2282, class XXi :2298-2427
+  class Xi :2168-2282, class XXi :2298-2427, class XXi_multi :2443-2670
 and smoothing_library.field_smoothing (library/smoothing_library/smoothing_library.pyx:215-235).
 
 Every loop over modes or cells runs on the GPU (pyl_shell_bin, pyl_modes_*, pyl_pk_bin of include/pyl_b200.h; cuFFT for
@@ -25,7 +25,7 @@ from . import Pk_library as _P
 from .errors import reference_exit
 
 __all__ = ["frequencies_2D", "check_number_modes_2D", "IFFT3Dr_f", "FFT2Dr_f", "Pk_plane", "XPk_imag", "XPk_plane",
-           "Pk_theta", "XPk_dv", "XPk_vv", "XPk_2D", "correct_MAS", "expected_Pk", "Xi", "XXi", "field_smoothing"]
+           "Pk_theta", "XPk_dv", "XPk_vv", "XPk_2D", "correct_MAS", "expected_Pk", "Xi", "XXi", "XXi_multi", "field_smoothing"]
 
 
 def frequencies_2D(BoxSize, dims):
@@ -478,6 +478,52 @@ class XXi:
         start2 = time.time()
         _xi_results(self, d1, grid, BoxSize, axis)
         print("Time to complete loop = %.2f" % (time.time() - start2))
+        print("Time taken = %.2f seconds" % (time.time() - start))
+
+
+class XXi_multi:
+    """Auto- and cross-correlation function multipoles of several fields (Pk_library.pyx:2443-2670).
+    Attributes: r3D, Nmodes3D, xi (.,3,F), Xxi (.,3,X); pairs i<j in lexicographic order.  As in the reference, the
+    cross term (i, j) is deconvolved with field i's window for BOTH fields (:2548-2553)."""
+
+    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1):
+        start = time.time()
+        print("\nComputing correlation functions of the fields...")
+        D.require_cuda()
+        if axis not in (0, 1, 2):
+            raise ValueError("axis must be 0, 1 or 2")
+        fields = len(delta)
+        dims = len(delta[0])
+        for i in range(1, fields):
+            if len(delta[i]) != dims:
+                reference_exit("Fields have different grid sizes!!!")
+        if MAS is None or len(MAS) != fields:
+            raise TypeError("MAS must be a list with one scheme per field")
+        dev = D.pick_device(*delta)
+        dk = [_P.fft3d_r2c_device(_cube(d, dev, "delta[%d]" % i)) for i, d in enumerate(delta)]
+        print("Time FFTS = %.2f" % (time.time() - start))
+        mi = [_P.MAS_function(m) for m in MAS]
+
+        class _Holder:
+            pass
+        cols, xcols = [], []
+        for i in range(fields):                                    # autos: |delta_i|^2 with its own window
+            a = torch.clone(dk[i])
+            _modes("power", a, None, dims, mi[i], 0)
+            h = _Holder()
+            _xi_results(h, a, dims, BoxSize, axis)
+            cols.append(h)
+        for i in range(fields):                                    # crosses, both fields with window i
+            for j in range(i + 1, fields):
+                a = torch.clone(dk[i])
+                _modes("power", a, dk[j], dims, mi[i], mi[i])
+                h = _Holder()
+                _xi_results(h, a, dims, BoxSize, axis)
+                xcols.append(h)
+        del dk
+        self.r3D, self.Nmodes3D = cols[0].r3D, cols[0].Nmodes3D
+        self.xi = np.stack([h.xi for h in cols], axis=2)
+        self.Xxi = np.stack([h.xi for h in xcols], axis=2) if xcols else np.zeros(self.xi.shape[:2] + (0,))
         print("Time taken = %.2f seconds" % (time.time() - start))
 
 

@@ -48,6 +48,33 @@ def compare_smoothing(got, ref, tol):
     return bad
 
 
+def run_xxi_multi(impl, N, I=None):
+    I = inputs(N) if I is None else I
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = impl.XXi_multi([I["d1"], I["d2"], I["f1"]], BOX, 1, ["CIC", "PCS", "NGP"], 1)
+    return {"N%d_xm_r" % N: r.r3D, "N%d_xm_Nm" % N: r.Nmodes3D, "N%d_xm_xi" % N: r.xi, "N%d_xm_Xxi" % N: r.Xxi}
+
+
+def compare_xxi_multi(got, ref, tol, N):
+    """Counts exact, radii 1e-12, multipoles against max(|value|, 0.01 (2l+1) max|xi_0 of the autos|)."""
+    t = "N%d_xm_" % N
+    bad = []
+    if not np.array_equal(got[t + "Nm"], ref[t + "Nm"]):
+        bad.append("counts")
+    if np.max(np.abs(got[t + "r"] / ref[t + "r"] - 1)) > 1e-12:
+        bad.append("r3D")
+    floor = 0.01 * np.max(np.abs(ref[t + "xi"][:, 0, :])) * np.array([1.0, 5.0, 9.0])[None, :, None]
+    for k in ("xi", "Xxi"):
+        g, r = np.asarray(got[t + k]), np.asarray(ref[t + k])
+        if g.shape != r.shape:
+            bad.append((k, g.shape, r.shape))
+            continue
+        e = float(np.max(np.abs(g - r) / np.maximum(np.abs(r), floor)))
+        if not e < tol:
+            bad.append((k, e))
+    return bad
+
+
 def run_all(impl, N, I=None):
     I = inputs(N) if I is None else I
     t = "N%d_" % N

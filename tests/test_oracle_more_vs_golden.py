@@ -18,7 +18,7 @@ def golden():
 def test_sibling_oracle_matches_reference(oracle, golden, N):
     from oracle import cpu_more
     got = MC.run_all(cpu_more, N)
-    assert set(got) == {k for k in golden if k.startswith("N%d_" % N) and "_sm_" not in k}
+    assert set(got) == {k for k in golden if k.startswith("N%d_" % N) and "_sm_" not in k and "_xm_" not in k}
     # same transform (pocketfft) on both sides: only float64 association / float32 FMA contraction differ
     bad = MC.compare(got, golden, tol=2e-6)
     assert not bad, bad
@@ -31,6 +31,15 @@ def test_smoothing_oracle_matches_reference(oracle, golden, N):
     got = MC.run_smoothing(cpu_more, N)
     assert set(got) == {k for k in golden if k.startswith("N%d_sm_" % N)}
     bad = MC.compare_smoothing(got, golden, tol=1e-6)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("N", MC.SIZES)
+def test_xxi_multi_oracle_matches_reference(oracle, golden, N):
+    from oracle import cpu_more
+    # XXi_multi forms re*re + im*im in double and rounds once (`np.float64_t[::1] real_part`, :2552-2555); the
+    # restatement reuses Xi's float32 mode loop: one float32 ulp per mode
+    bad = MC.compare_xxi_multi(MC.run_xxi_multi(cpu_more, N), golden, 1e-5, N)
     assert not bad, bad
 
 

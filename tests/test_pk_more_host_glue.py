@@ -75,6 +75,10 @@ def fake_device(request, monkeypatch, harness):  # noqa: F811
         def device(*a):
             return None
 
+        @staticmethod
+        def clone(x):
+            return x.copy()
+
         class cuda:
             @staticmethod
             def current_device():
@@ -115,6 +119,14 @@ def test_python_layer_against_reference_golden(fake_device, N):
         bad = MC.compare(got, golden, tol=1e-4, fft_eps=1e-5)      # the GPU tests' bars
     else:
         bad = MC.compare(got, golden, tol=1e-5)     # float32 transforms differ in association (scaled c2r)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("N", MC.SIZES)
+def test_xxi_multi_python_layer(fake_device, N):
+    PM = fake_device
+    golden = dict(np.load(os.path.join(GOLDEN, "pk_more_golden.npz")))
+    bad = MC.compare_xxi_multi(MC.run_xxi_multi(PM, N), golden, 1e-4 if PM.other_fft else 2e-5, N)
     assert not bad, bad
 
 
