@@ -193,3 +193,32 @@ def test_filter_bodies(harness, oracle, N, nd):
         got = sfft.rfftn(field, axes=tuple(range(nd))).astype(np.complex64)
         ref = (M.FT_filter if nd == 3 else M.FT_filter_2D)(MC.BOX, R, N, F, 1, kmin, kmax)
         assert np.max(np.abs(got - ref)) < 1e-6 * np.max(np.abs(ref)), (name, nd)
+
+
+def test_shell_bodies_random_geometries(harness, oracle):
+    """Randomised sweep (seeded): grid side, window exponent, line of sight and SM count (i.e. segmentation) drawn
+    at random; counts must be exact and sums must match the oracle for every draw."""
+    from oracle import cpu as C, cpu_more as M
+    rng = np.random.default_rng(2026)
+    for _ in range(30):
+        N = int(rng.integers(2, 27))
+        mas = int(rng.integers(0, 5))
+        axis = int(rng.integers(0, 3))
+        sms = int(rng.choice([1, 3, 148, 1000, 50000]))
+        kmax = C.frequencies(1000.0, N)[4]
+        # velocity-divergence estimator on three random fields
+        dks = [np.ascontiguousarray(C.fft3d_r2c(rng.standard_normal((N, N, N)).astype(np.float32))) for _ in range(3)]
+        got = run_shell(harness, "theta", dks, [mas], N, sms=sms)
+        k, Nm, P1, P2, PX = z(kmax + 1), z(kmax + 1), z(kmax + 1), z(kmax + 1), z(kmax + 1)
+        M._lib().oracle_vel_bin(0, M._cf(np.ascontiguousarray(np.stack(dks))), N, mas, *[C._dp(a) for a in (k, Nm, P1, P2, PX)])
+        assert np.array_equal(got["Nm"], Nm) and int(Nm.sum()) == C.expected_modes(N), (N, sms)
+        assert close(got["ksum"], k, 1e-12) and close(got["vals"][0], P1, 2e-6), (N, mas, sms)
+        # real-space binning
+        grid = rng.standard_normal((N, N, N)).astype(np.float32)
+        got = run_shell(harness, "xi", [grid], [], N, axis=axis, scale=1.0, sms=sms)
+        r3D, xi3D, Nm = z(kmax + 1), np.zeros((kmax + 1, 3)), z(kmax + 1)
+        M._lib().oracle_xi_bin(grid.ctypes.data_as(M._fpp), N, axis, C._dp(r3D), C._dp(xi3D), C._dp(Nm))
+        assert np.array_equal(got["Nm"], Nm) and int(Nm.sum()) == N ** 3, (N, sms)
+        amp = np.sqrt(np.maximum(Nm, 1.0)) * float(np.abs(grid).max())
+        for l in range(3):
+            assert float(np.max(np.abs(got["vals"][l] - xi3D[:, l]) / amp)) < 1e-12, (N, axis, l)
