@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "libpyl_b200.so")
+SO_PATH = os.environ.get("PYL_B200_SO") or os.path.join(_PKG, "libpyl_b200.so")
 
 PYL_OK = 0
 MAS_IDS = {"NGP": 0, "CIC": 1, "TSC": 2, "PCS": 3}

@@ -12,7 +12,12 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-SO = os.path.join(PKG, "libpyl_b200.so")
+# developer knobs for A/B timing of kernel variants: PYL_BUILD_TAG=x PYL_BUILD_DEFS="-DPYL_PT=256" builds
+# libpyl_b200_x.so beside the product library; PYL_B200_SO=<path> makes _lib.py load it
+TAG = os.environ.get("PYL_BUILD_TAG", "")
+EXTRA = os.environ.get("PYL_BUILD_DEFS", "").split()
+SO = os.path.join(PKG, "libpyl_b200%s.so" % ("_" + TAG if TAG else ""))
+BUILD_DIR = os.path.join(PKG, "build" + ("_" + TAG if TAG else ""))
 SOURCES = ["common.cu", "deposit.cu", "deposit_atomic.cu", "deposit_tiled.cu", "deposit_sorted.cu", "interp.cu", "fft.cu", "transpose.cu", "pk_bin.cu", "pk_shell.cu",
            "hostapi.cu"]
 HEADERS = ["common.cuh", "stencil.cuh", "shell_body.cuh", "deposit_point.cuh", os.path.join(ROOT, "include", "pyl_b200.h")]
@@ -31,15 +36,15 @@ def build(force=False, verbose=False):
         return SO
     objs = []
     procs = []
-    os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
+    os.makedirs(BUILD_DIR, exist_ok=True)
     for s in srcs:
-        o = os.path.join(PKG, "build", os.path.basename(s)[:-3] + ".o")
+        o = os.path.join(BUILD_DIR, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
         if not force and os.path.exists(o) and os.path.getmtime(o) >= _newest([s] + deps[len(srcs):]):
             continue
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
                "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
-               "-c", s, "-o", o]
+               "-c", s, "-o", o] + EXTRA
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -1,36 +1,40 @@
-// K0/K1/K2: tiled deposit -- bucket particles by grid tile, accumulate every tile in shared memory
-// WITHOUT atomics, flush each tile once with coalesced reductions.
+// Tiled deposit, round 2: two-level particle partition with shared-memory ranking and coalesced run writes, then
+// one CTA per grid tile that accumulates in shared memory WITHOUT atomics and flushes with bulk reductions.
 //
 // Replaces the same reference loops as deposit_atomic.cu (MAS_library.pyx:142-166, 288-292, 388-404,
-// 481-497 and W variants).  Why: measured on B200 (profiles/r1_deposit_atomic.md) the particle-parallel
-// red.global kernel moves 21x the algorithmic bytes through DRAM (every stencil row of a randomly
-// placed particle is a 32-byte sector read-modify-write) and runs at 1.8% of the HBM roofline.
+// 481-497 and W variants).
 //
-// Pipeline (all on the caller's stream, scratch in the caller's workspace):
-//   1. tile_count    histogram of a 1-in-8 SAMPLE of the particles over tiles (tile = 8 x 16 x 32 cells):
-//                    cell coordinate dist = fl32(pos*inv) per axis, stencil base cell -> tile id.
-//   2. tile_caps + exclusive scan (cub::DeviceScan): per-tile bucket capacity = 1.125 x estimate +
-//                    4 sigma of the sampling noise + 32, and the bucket start offsets.
-//   3. tile_scatter  ONE full pass over pos: one 64-bit atomicAdd on the tile's packed cursor returns the slot
-//                    and the bucket end; writes (dist.xyz, W) as one aligned float4 into the tile's bucket.  A particle that finds its bucket full (rare:
-//                    beyond 4 sigma) is deposited on the spot with red.global -- correctness never
-//                    depends on the estimate.
-//   4. tile_deposit  one CTA per tile, looping over the bucket in chunks of 1024 particles:
-//        a. counting sort of the chunk by local cell (x,y,z) inside shared memory: one packed-u16
-//           shared atomic per particle for the rank, block scan, scatter into a sorted float4 array
-//           (stencil fractions + W) -- so every (x,y) row of the tile is contiguous and z-ordered;
-//        b. each warp OWNS target x-planes of the shared accumulator (tile + stencil halo).  For a
-//           target plane X it walks the source rows x = X - l (l = 0..S-1), 32 particles at a time;
-//           lanes of equal cell form contiguous runs (sorted), so a segmented warp-shuffle scan
-//           leaves each run's sum in its head lane, and head lanes do plain shared-memory
-//           read-modify-writes.  Target planes are exclusive to a warp and a warp's instructions are
-//           ordered, hence no shared atomics and no block barriers inside the stencil loops;
-//        c. after the last chunk the accumulator (tile + halo) is added to the grid with coalesced
-//           red.global.add.f32 (halo cells are shared with neighbouring tiles).
-// Weights: fractions are taken against the same unwrapped base cell the reference uses; CIC is
-// operation-identical to the reference, TSC/PCS evaluate the same polynomials in float32 (<= 3 ulp from
-// the reference's float64-then-rounded values, far inside the 1e-5 per-cell tolerance).  Unweighted
-// NGP stays bit-exact (sums of 1.0f).
+// Why this shape (measured on B200, scratch/ubench.cu, profiles/r2_ubench.md):
+//   * the particle-parallel red.global kernel moves 21x the algorithmic bytes through DRAM (1.8% of roofline);
+//   * a one-level scatter with one returning global atomic and one scattered 16-byte store per particle is bound
+//     by the L2 request rate (2.8 ms for 134 M records); runs of >= 8 records written by consecutive lanes reach
+//     bandwidth (0.45 ms).  Runs need few bins per pass, hence TWO passes of <= 2048 bins each;
+//   * same-address returning atomics serialise (~20-100 ns each): the per-run cursors of the first pass are
+//     replicated (one sub-segment per replica) so that a cursor sees only 1/REPL of the CTAs;
+//   * shared-memory integer atomics are cheap (3.6 cycles per warp instruction), match.any is not (64 cycles), float
+//     shared atomics are a CAS loop (13 cycles): ranking uses ATOMS, duplicates are found with shuffles on the
+//     cell-sorted order, accumulation is plain conflict-free read-modify-write;
+//   * cp.reduce.async.bulk (UBLKRED) adds a 128-byte row of the tile to the grid at twice the rate of coalesced
+//     red.global.
+//
+// Pipeline (all on the caller's stream, scratch in the caller's workspace, no host synchronisation):
+//   1. tile_count    histogram of a 1-in-8 SAMPLE of the particles over tiles (tile = 8 x 16 x 32 cells).
+//   2. tile_caps + exclusive scan: per-tile bucket capacity = 1.125 x estimate + 4 sigma + 32 (multiple of 4) and
+//                    the bucket start offsets; tile_setup derives the super-tile segments (a super-tile = 2^k
+//                    consecutive tiles, k chosen so that both passes have about sqrt(ntiles) bins).
+//   3. partition<1>  pos (AoS) -> buf1 (SoA planes x,y,z[,W] of cell coordinates dist = fl32(pos*inv)), grouped by
+//                    super-tile.  A CTA ranks 4096 particles by bin in shared memory (ATOMS), reserves one run per
+//                    non-empty bin with ONE global atomic, and writes the runs with consecutive lanes.
+//   4. partition<2>  buf1 -> buf2 grouped by tile, same kernel body, bins = tiles of one super-tile.
+//   5. tile_deposit  one CTA per tile: bucket chunks arrive by cp.async.bulk + mbarrier (UBLKCP); counting sort by
+//                    cell inside shared memory; each warp owns four z-planes of the tile with PRIVATE accumulators
+//                    (own planes + stencil halo), so a particle is visited once, does all S^3 plain
+//                    read-modify-writes, and no barrier is needed inside the accumulation; the overlapping private
+//                    planes are summed and the tile (+ halo) is added to the grid with cp.reduce.async.bulk.
+//   A particle that finds its segment or bucket full (capacities come from a sample) is deposited on the spot with
+//   red.global -- correctness never depends on the estimate.
+// Weights are the reference's own arithmetic (stencil.cuh: float64 where the reference promotes, then rounded),
+// identical to the atomic kernel's; products are formed as (wx*W)*wy*wz and added with a fused multiply-add.
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -41,10 +45,20 @@ namespace pyl {
 
 constexpr int TX = 8, TY = 16, TZ = 32;         // tile extent in cells
 constexpr int TILE_CELLS = TX * TY * TZ;        // 4096
-constexpr int TNT = 256;                        // threads per tile CTA
-constexpr int CHUNK = 1024;                     // particles sorted per pass
-constexpr int PER = CHUNK / TNT;                // 4 per thread
+constexpr int TNT = 256;                        // threads per tile CTA (8 warps)
 constexpr int SAMPLE = 8;                       // tile_count looks at one particle group in SAMPLE
+#ifndef PYL_PT
+#define PYL_PT 512
+#endif
+#ifndef PYL_PPER
+#define PYL_PPER 8
+#endif
+constexpr int PT = PYL_PT;                      // threads per partition CTA
+constexpr int PPER = PYL_PPER;                  // particles per thread
+constexpr int PP = PT * PPER;                   // 4096 particles per partition CTA
+constexpr int MAX_BINS = 2048;                  // bins per partition pass
+constexpr int MAX_REPL = 64;                    // cursor replicas of the first pass
+constexpr int OUT_ROW = 36;                     // floats per flushed row (32 + halo, 16-byte multiple)
 
 struct TileGeom {
     int dims;
@@ -56,67 +70,21 @@ struct TileGeom {
     // x_planes - 1; a particle belongs here iff its first stencil plane is one of the first x_own planes
     // (the other x_planes - x_own planes are the upward ghost planes its stencil may reach).
     int x_origin, x_own, x_planes;
+    int tps_shift;        // a super-tile = 1 << tps_shift consecutive tiles
+    unsigned nsuper;      // number of super-tiles
+    unsigned repl;        // cursor replicas (sub-segments) per super-tile in pass 1
 };
 
 constexpr unsigned NO_TILE = 0xffffffffu;
 
-// unwrapped base cell of the stencil (first of the S cells) and the fraction the weights depend on
 template <int MAS>
-__device__ __forceinline__ int stencil_base(float dist, float &frac) {
-    int b;
-    if (MAS == PYL_MAS_NGP) {
-        b = __double2int_rz(__dadd_rn((double)dist, 0.5));
-        frac = 0.0f;
-    } else if (MAS == PYL_MAS_CIC) {
-        b = __float2int_rz(dist);
-        frac = __fsub_rn(dist, (float)b);                 // u in [0,1)
-    } else if (MAS == PYL_MAS_TSC) {
-        b = __double2int_rd(__dadd_rn((double)dist, -1.5)) + 1;
-        frac = __fsub_rn(dist, (float)b);                 // r in [0.5,1.5)
-    } else {
-        b = __double2int_rd(__dadd_rn((double)dist, -2.0)) + 1;
-        frac = __fsub_rn(dist, (float)b);                 // 1+u in [1,2)
-    }
-    return b;
-}
-
-// all S weights of one axis from the fraction (see header comment)
-template <int MAS>
-__device__ __forceinline__ void stencil_weights(float frac, float *w) {
-    if (MAS == PYL_MAS_NGP) {
-        w[0] = 1.0f;
-    } else if (MAS == PYL_MAS_CIC) {
-        w[0] = __fsub_rn(1.0f, frac);
-        w[1] = frac;
-    } else if (MAS == PYL_MAS_TSC) {
-        // diffs: r, |r-1|, 2-r   (MAS_library.pyx:394-398)
-        const float a = 1.5f - frac;
-        const float c = frac - 0.5f;
-        const float d1 = frac - 1.0f;
-        w[0] = 0.5f * a * a;
-        w[1] = 0.75f - d1 * d1;
-        w[2] = 0.5f * c * c;
-    } else {
-        // diffs: 1+u, u, 1-u, 2-u   (MAS_library.pyx:487-491)
-        const float u = frac - 1.0f;
-        const float v = 1.0f - u;
-        const float sixth = 1.0f / 6.0f;
-        w[0] = v * v * v * sixth;
-        w[1] = (4.0f - 6.0f * u * u + 3.0f * u * u * u) * sixth;
-        w[2] = (4.0f - 6.0f * v * v + 3.0f * v * v * v) * sixth;
-        w[3] = u * u * u * sixth;
-    }
-}
-
-template <int MAS>
-__device__ __forceinline__ unsigned tile_and_local(const float d[3], const TileGeom &g, int local[3],
-                                                   float frac[3]) {
+__device__ __forceinline__ unsigned tile_and_local(const float d[3], const TileGeom &g, int local[3]) {
     int t[3];
     const int T[3] = {TX, TY, TZ};
     bool mine = true;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        const int b = stencil_base<MAS>(d[a], frac[a]);
+        const int b = axis_base<MAS>(d[a]);
         int wb = wrap_index(b, g.dims);
         if (a == 0) {                       // plane index inside the destination window
             wb -= g.x_origin;
@@ -137,7 +105,6 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t groups = vec_ok ? (particles >> 2) : 0;
     int local[3];
-    float frac[3];
     // every SAMPLE-th group of 4 particles
     for (int64_t sg = tid; sg * SAMPLE < groups; sg += stride) {
         const int64_t grp = sg * SAMPLE;
@@ -153,7 +120,7 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict
             float d[3];
 #pragma unroll
             for (int a = 0; a < 3; a++) d[a] = cell_coordinate(p[3 * q + a], g.inv_cell_size);
-            const unsigned t = tile_and_local<MAS>(d, g, local, frac);
+            const unsigned t = tile_and_local<MAS>(d, g, local);
             if (t != NO_TILE) atomicAdd(counts + t, 1u);
         }
     }
@@ -163,17 +130,18 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict
         float d[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) d[a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
-        const unsigned t = tile_and_local<MAS>(d, g, local, frac);
+        const unsigned t = tile_and_local<MAS>(d, g, local);
         if (t != NO_TILE) atomicAdd(counts + t, 1u);
     }
 }
 
 // ---- 2. capacities from the sampled counts (in place; then scanned into bucket starts) ---------------
 __host__ __device__ __forceinline__ unsigned tile_capacity(unsigned sampled) {
-    // 1.125 x estimate + 4 sigma (sigma of the estimate = SAMPLE*sqrt(sampled)) + 32
+    // 1.125 x estimate + 4 sigma (sigma of the estimate = SAMPLE*sqrt(sampled)) + 32, rounded up to a multiple of
+    // 4 slots so that every bucket starts on a 16-byte boundary of its plane (bulk copies)
     const unsigned est = sampled * SAMPLE;
     const unsigned sig = (unsigned)(4.0f * SAMPLE * sqrtf((float)sampled)) + 1u;
-    return est + (est >> 3) + sig + 32u;
+    return (est + (est >> 3) + sig + 32u + 3u) & ~3u;
 }
 
 __global__ void tile_caps_kernel(unsigned *__restrict__ counts, unsigned ntiles) {
@@ -182,20 +150,67 @@ __global__ void tile_caps_kernel(unsigned *__restrict__ counts, unsigned ntiles)
     else if (i == ntiles) counts[i] = 0u;
 }
 
-// cursor[t] = (bucket end << 32) | next free slot: ONE 64-bit atomicAdd in the scatter kernel returns both the
-// slot and the capacity limit (measured: the two extra loads of `starts` per particle were 25% of the scatter
-// kernel's L2 requests, and the kernel is bound by the L2 request rate)
-__global__ void tile_cursor_kernel(const unsigned *__restrict__ starts, unsigned long long *__restrict__ cursor,
-                                   unsigned ntiles) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ntiles) cursor[i] = ((unsigned long long)starts[i + 1] << 32) | starts[i];
+// segment of super-tile s, replica r, inside the bucket array: [seg_begin, seg_begin + rep_cap)
+struct Segment {
+    unsigned begin, cap;
+};
+__device__ __forceinline__ Segment super_segment(const unsigned *__restrict__ starts, const TileGeom &g, unsigned s,
+                                                 unsigned r) {
+    const unsigned t0 = s << g.tps_shift;
+    unsigned t1 = (s + 1) << g.tps_shift;
+    if (t1 > g.ntiles) t1 = g.ntiles;
+    const unsigned b = __ldg(starts + t0), e = __ldg(starts + t1);
+    Segment sg;
+    sg.cap = ((e - b) / g.repl) & ~3u;
+    sg.begin = b + r * sg.cap;
+    return sg;
 }
 
-// ---- 3. scatter into buckets (single full pass) --------------------------------------------------------
-// bucket full (capacity came from a sample): deposit the particle directly.  Out of line: it is rare, and
-// inlined four times it made every atomicAdd below wait for the previous particle's branch.
+// cur2[t] = bucket start of tile t; cur1[r][s] = start of sub-segment (s, r); spre = exclusive prefix over
+// super-tiles of the number of PP-particle chunks one replica sub-segment can hold (CTA -> work map of pass 2)
+__global__ void __launch_bounds__(1024) tile_setup_kernel(const unsigned *__restrict__ starts, TileGeom g,
+                                                          unsigned *__restrict__ cur1, unsigned *__restrict__ cur2,
+                                                          unsigned *__restrict__ spre) {
+    if (blockIdx.x > 0) {
+        const unsigned i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
+        if (i < g.ntiles) cur2[i] = starts[i];
+        return;
+    }
+    __shared__ unsigned part[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned s0 = 0; s0 < g.nsuper; s0 += 1024) {
+        const unsigned s = s0 + threadIdx.x;
+        unsigned nch = 0;
+        if (s < g.nsuper) {
+            const Segment sg = super_segment(starts, g, s, 0);
+            nch = (sg.cap + PP - 1) / PP;
+            for (unsigned r = 0; r < g.repl; r++) cur1[r * g.nsuper + s] = sg.begin + r * sg.cap;
+        }
+        unsigned incl = nch;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) part[warp] = incl;
+        __syncthreads();
+        unsigned base = carry;
+        for (int w = 0; w < warp; w++) base += part[w];
+        if (s < g.nsuper) spre[s] = base + incl - nch;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = base + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) spre[g.nsuper] = carry;
+}
+
+// ---- 3./4. partition passes ---------------------------------------------------------------------------------
+// bucket full (capacity came from a sample): deposit the particle directly.  Out of line: it is rare.
 template <int MAS, bool WEIGHTED>
-__device__ __noinline__ void scatter_overflow(float d0, float d1, float d2, float wp, TileGeom g,
+__device__ __noinline__ void overflow_deposit(float d0, float d1, float d2, float wp, TileGeom g,
                                               float *__restrict__ number, unsigned long long *dropped) {
     const float d[3] = {d0, d1, d2};
     unsigned long long dr = 0;
@@ -206,299 +221,429 @@ __device__ __noinline__ void scatter_overflow(float d0, float d1, float d2, floa
     *dropped += dr;
 }
 
-// One particle per thread, scalar loads: measured on B200 (scratch/s1_bench.cu) this simplest form beats the
-// float4 / 4-particles-per-thread form (2.85 vs 3.25 ms at 512^3) -- the kernel is bound by the rate of
-// returning atomics (1.5 ms for 134 M of them) plus the scattered 16-byte stores, and more independent
-// threads keep more of both in flight.  A two-level shared-memory-staged partition was prototyped in the
-// same file and lost (3.2 ms).
-// Lanes of a warp that go to the same tile share ONE atomic (match_any + leader): snapshot-ordered inputs
-// (lattice order, Peano-Hilbert order) send whole warps to one tile, and same-address returning atomics
-// serialise in L2 (measured 9.7 ms instead of 2.8 ms on a Zel'dovich-displaced lattice without this).
-template <int MAS, bool WEIGHTED>
-__global__ void __launch_bounds__(512) tile_scatter_kernel(const float *__restrict__ pos,
-                                                           const float *__restrict__ W, int64_t particles,
-                                                           TileGeom g, unsigned long long *__restrict__ cursor,
-                                                           float4 *__restrict__ bucket,
-                                                           float *__restrict__ number,
-                                                           unsigned long long *__restrict__ dropped_out) {
-    constexpr int S = StencilWidth<MAS>::value;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < particles;
-    const int lane = threadIdx.x & 31;
-    float d[3] = {0.f, 0.f, 0.f};
-    float wp = 1.0f;
-    unsigned t = NO_TILE;
-    if (live) {
-#pragma unroll
-        for (int a = 0; a < 3; a++) d[a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
-        if (WEIGHTED) wp = __ldg(W + i);
-        int local[3];
-        float frac[3];
-        t = tile_and_local<MAS>(d, g, local, frac);
-    }
-    // match_any only when neighbouring lanes agree (ordered input); for scattered input it would cost ~8%
-    unsigned peers = 1u << lane;
-    if (__any_sync(0xffffffffu, __shfl_down_sync(0xffffffffu, t, 1) == t && lane < 31))
-        peers = __match_any_sync(0xffffffffu, t);
-    const int leader = __ffs(peers) - 1;
-    const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-    unsigned long long cur = 0ull;
-    if (lane == leader && t != NO_TILE) cur = atomicAdd(cursor + t, (unsigned long long)__popc(peers));
-    cur = __shfl_sync(0xffffffffu, cur, leader);
-    const unsigned slot = (unsigned)cur + rank, end = (unsigned)(cur >> 32);
-    unsigned long long dropped = 0;
-    if (t != NO_TILE) {
-        if (slot < end) bucket[slot] = make_float4(d[0], d[1], d[2], wp);
-        else scatter_overflow<MAS, WEIGHTED>(d[0], d[1], d[2], wp, g, number, &dropped);
-    } else if (live) {
-        dropped = S * S * S;            // not routed to this slab: nothing of it is deposited here
-    }
-    if (dropped_out != nullptr && dropped != 0) atomicAdd(dropped_out, dropped);
-}
-
-// ---- 4. per-tile deposit ----------------------------------------------------------------------------
-template <int MAS>
-struct TileSmem {
-    static constexpr int S = MAS + 1;
-    static constexpr int AX = TX + S - 1, AY = TY + S - 1, AZ = TZ + S - 1;
-    static constexpr int ACC = AX * AY * AZ;
-    static constexpr int CNT_WORDS = TILE_CELLS / 2 + 1;      // packed u16 pairs + one end marker
-    static constexpr size_t bytes =
-        (size_t)ACC * 4 + (size_t)CNT_WORDS * 4 + (size_t)CHUNK * 16 + (size_t)CHUNK * 2 + 64;
+struct PartArgs {
+    const float *pos;            // pass 1 input (AoS) ...
+    const float *W;
+    int64_t particles;
+    const float4 *in;            // pass 2 input (buf1)
+    float4 *out;                 // output records (dist.x, dist.y, dist.z, W): buf1 in pass 1, buf2 in pass 2
+    const unsigned *starts;      // ntiles + 1 bucket starts
+    unsigned *cur1;              // [repl][nsuper]
+    unsigned *cur2;              // [ntiles]
+    const unsigned *spre;        // nsuper + 1
+    float *number;               // the grid (overflow path only)
+    unsigned long long *dropped;
+    double *wsum;                // sum of |W| over the particles of this call (pass 1, weighted only)
 };
 
-__device__ __forceinline__ unsigned off16(const unsigned *cnt, int key) {
-    const unsigned w = cnt[key >> 1];
-    return (key & 1) ? (w >> 16) : (w & 0xffffu);
+// dynamic shared memory of a partition CTA: PP staged records + three words per bin + the bin of every staged record
+static size_t part_smem_bytes(int nb) {
+    return (size_t)PP * 16 + 3 * (size_t)((nb + 3) & ~3) * 4 + (size_t)PP * 2 + 64 * 4;
 }
 
-template <int MAS>
-__global__ void __launch_bounds__(TNT, 4)
-tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned long long *__restrict__ cursor,
-                    float *__restrict__ number, TileGeom g) {
-    using SM = TileSmem<MAS>;
-    constexpr int S = SM::S, AY = SM::AY, AZ = SM::AZ, AX = SM::AX;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *sorted = reinterpret_cast<float4 *>(smem_raw);                       // CHUNK float4
-    float *acc = reinterpret_cast<float *>(smem_raw + (size_t)CHUNK * 16);        // ACC floats
-    unsigned *cnt = reinterpret_cast<unsigned *>(acc + SM::ACC);                  // CNT_WORDS
-    unsigned short *sorted_yz = reinterpret_cast<unsigned short *>(cnt + SM::CNT_WORDS);   // CHUNK: y*TZ+z
-    unsigned *warp_part = reinterpret_cast<unsigned *>(sorted_yz + CHUNK);        // 8 words
-
-    const unsigned tile = blockIdx.x;
-    // cursor = (bucket end << 32) | (bucket begin + particles that asked for a slot); the next tile's bucket
-    // begins where this one ends, so this tile's begin is the previous tile's end
-    const unsigned long long cur = cursor[tile];
-    const unsigned begin = tile == 0 ? 0u : (unsigned)(cursor[tile - 1] >> 32);
-    const unsigned end = min((unsigned)cur, (unsigned)(cur >> 32));            // overflow went the direct way
-    if (begin == end) return;                                 // empty tile: nothing to add
+template <int MAS, bool WEIGHTED, int LEVEL>
+__global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, TileGeom g) {
+    constexpr int S = StencilWidth<MAS>::value;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int nb = LEVEL == 1 ? (int)g.nsuper : (1 << g.tps_shift);
+    const int nb4 = (nb + 3) & ~3;
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw);                      // PP records in bin order
+    unsigned *cnt = reinterpret_cast<unsigned *>(stage + PP);                  // nb: counts -> bin starts
+    unsigned *goff = cnt + nb4;                                                // global slot of sorted index 0 of a bin
+    unsigned *lim = goff + nb4;                                                // first slot past the bin's segment
+    unsigned short *sbin = reinterpret_cast<unsigned short *>(lim + nb4);       // PP: bin of a staged record
+    unsigned *misc = reinterpret_cast<unsigned *>(sbin + PP);                  // [0..15] warp partials, [16..] work item
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- which items -------------------------------------------------------------------------------------
+    int64_t first;              // index of this CTA's first item (particle index / slot of buf1)
+    int n_in;                   // items of this CTA
+    unsigned super = 0, repl = 0;
+    if (LEVEL == 1) {
+        first = (int64_t)blockIdx.x * PP;
+        n_in = (int)min((int64_t)PP, a.particles - first);
+        repl = blockIdx.x % g.repl;
+    } else {
+        if (tid == 0) {
+            // CTAs that run at the same time (neighbouring blockIdx) take chunks of DIFFERENT super-tiles: the
+            // chunks of one super-tile all reserve runs on the same few hundred bucket cursors, and same-address
+            // atomics serialise (the straight order made this pass as slow as its atomics)
+            const unsigned rows = gridDim.x / g.nsuper;
+            const unsigned b = (blockIdx.x % g.nsuper) * rows + blockIdx.x / g.nsuper;
+            unsigned lo = 0, hi = g.nsuper;                    // largest s with repl*spre[s] <= b
+            const unsigned total = __ldg(a.spre + g.nsuper) * g.repl;
+            unsigned ok = b < total;
+            if (ok) {
+                while (hi - lo > 1) {
+                    const unsigned mid = (lo + hi) >> 1;
+                    if (__ldg(a.spre + mid) * g.repl <= b) lo = mid; else hi = mid;
+                }
+                const unsigned nch = __ldg(a.spre + lo + 1) - __ldg(a.spre + lo);
+                const unsigned rem = b - __ldg(a.spre + lo) * g.repl;
+                const unsigned r = rem / nch, c = rem - r * nch;
+                const Segment sg = super_segment(a.starts, g, lo, r);
+                const unsigned fill = min(a.cur1[r * g.nsuper + lo], sg.begin + sg.cap);
+                const unsigned b0 = sg.begin + c * PP;
+                misc[16] = lo;
+                misc[17] = b0;
+                misc[18] = b0 < fill ? min((unsigned)PP, fill - b0) : 0u;
+            } else {
+                misc[18] = 0u;
+            }
+        }
+        __syncthreads();
+        n_in = (int)misc[18];
+        if (n_in == 0) return;
+        super = misc[16];
+        first = misc[17];
+    }
+
+    for (int i = tid; i < nb; i += PT) cnt[i] = 0u;
+    __syncthreads();
+
+    // ---- load, bin, rank ------------------------------------------------------------------------------------
+    float d[PPER][3], wv[PPER];
+    unsigned br[PPER];                              // (bin << 12) | rank within the bin; 0xffffffff = no item
+    unsigned long long dropped = 0;
+    // all loads first: the shared-memory atomics of the ranking below are ordering points for the compiler, and a
+    // load issued after one of them would expose a full DRAM latency per particle instead of one per CTA
+#pragma unroll
+    for (int q = 0; q < PPER; q++) {
+        const int i = q * PT + tid;
+        wv[q] = 1.0f;
+        d[q][0] = d[q][1] = d[q][2] = 0.0f;
+        if (i < n_in) {
+            if (LEVEL == 1) {
+                const float *p = a.pos + (first + i) * 3;
+#pragma unroll
+                for (int k = 0; k < 3; k++) d[q][k] = __ldg(p + k);
+                if (WEIGHTED) wv[q] = __ldg(a.W + first + i);
+            } else {
+                const float4 v = __ldg(a.in + first + i);
+                d[q][0] = v.x; d[q][1] = v.y; d[q][2] = v.z;
+                wv[q] = v.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PPER; q++) {
+        const int i = q * PT + tid;
+        int bin = -1;
+        if (i < n_in) {
+            if (LEVEL == 1) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) d[q][k] = cell_coordinate(d[q][k], g.inv_cell_size);
+            }
+            int local[3];
+            const unsigned t = tile_and_local<MAS>(d[q], g, local);
+            if (t == NO_TILE) dropped += S * S * S;      // not routed to this slab: nothing of it is deposited here
+            else bin = LEVEL == 1 ? (int)(t >> g.tps_shift) : (int)(t - (super << g.tps_shift));
+        }
+        // rank within the bin.  Ordered inputs (lattice / Peano-Hilbert order) send whole warps to one bin, and
+        // same-address shared atomics serialise: when neighbouring lanes agree, the lanes of the leading bin share
+        // one atomic (ballot + leader), at most twice, before the per-lane atomics.
+        unsigned rank = 0;
+        bool todo = bin >= 0;
+        const int nbin = __shfl_down_sync(0xffffffffu, bin, 1);
+        if (__popc(__ballot_sync(0xffffffffu, todo && nbin == bin && lane < 31)) >= 8) {
+#pragma unroll 1
+            for (int it = 0; it < 2; it++) {
+                const unsigned pending = __ballot_sync(0xffffffffu, todo);
+                if (pending == 0) break;
+                const int leader = __ffs(pending) - 1;
+                const int lb = __shfl_sync(0xffffffffu, bin, leader);
+                const unsigned m = __ballot_sync(0xffffffffu, todo && bin == lb);
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(cnt + lb, (unsigned)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (todo && bin == lb) {
+                    rank = base + __popc(m & ((1u << lane) - 1u));
+                    todo = false;
+                }
+            }
+        }
+        if (todo) rank = atomicAdd(cnt + bin, 1u);
+        br[q] = bin >= 0 ? (((unsigned)bin << 12) | rank) : 0xffffffffu;
+    }
+    __syncthreads();
+
+    // ---- exclusive scan of the bin counts; one global reservation per non-empty bin -------------------------------
+    {
+        constexpr int EPT = MAX_BINS / PT;          // 4 bins per thread
+        unsigned c[EPT], sum = 0;
+#pragma unroll
+        for (int i = 0; i < EPT; i++) {
+            const int b = tid * EPT + i;
+            c[i] = b < nb ? cnt[b] : 0u;
+            sum += c[i];
+        }
+        unsigned incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) misc[warp] = incl;
+        __syncthreads();
+        unsigned run = incl - sum;
+#pragma unroll
+        for (int w = 0; w < PT / 32; w++) run += (w < warp) ? misc[w] : 0u;
+        // the reservations of this thread's bins are issued back to back (their results are consumed afterwards):
+        // returning global atomics take microseconds under load
+        unsigned got[EPT], end[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; i++) {
+            const int b = tid * EPT + i;
+            got[i] = end[i] = 0u;
+            if (b < nb && c[i] > 0) {
+                if (LEVEL == 1) {
+                    const Segment sg = super_segment(a.starts, g, (unsigned)b, repl);
+                    end[i] = sg.begin + sg.cap;
+                } else {
+                    end[i] = __ldg(a.starts + (super << g.tps_shift) + b + 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < EPT; i++) {
+            const int b = tid * EPT + i;
+            if (b < nb && c[i] > 0) {
+                if (LEVEL == 1) got[i] = atomicAdd(a.cur1 + repl * g.nsuper + b, c[i]);
+                else got[i] = atomicAdd(a.cur2 + (super << g.tps_shift) + b, c[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < EPT; i++) {
+            const int b = tid * EPT + i;
+            if (b < nb) {
+                cnt[b] = run;
+                if (c[i] > 0) {
+                    goff[b] = got[i] - run;
+                    lim[b] = end[i];
+                }
+                run += c[i];
+            }
+        }
+        if (tid == PT - 1) misc[20] = run;         // items staged by this CTA
+    }
+    __syncthreads();
+
+    // ---- stage in bin order -------------------------------------------------------------------------------------
+    float wabs = 0.0f;
+#pragma unroll
+    for (int q = 0; q < PPER; q++) {
+        if (br[q] != 0xffffffffu) {
+            const unsigned bin = br[q] >> 12;
+            const unsigned dst = cnt[bin] + (br[q] & 0xfffu);
+            stage[dst] = make_float4(d[q][0], d[q][1], d[q][2], wv[q]);
+            sbin[dst] = (unsigned short)bin;
+            if (WEIGHTED && LEVEL == 1) wabs += fabsf(wv[q]);
+        }
+    }
+    if (WEIGHTED && LEVEL == 1) {
+        // scale of the fixed-point accumulators of the tile kernel: sum of |W| of the particles deposited here
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wabs += __shfl_xor_sync(0xffffffffu, wabs, o);
+        if (lane == 0 && wabs != 0.0f) atomicAdd(a.wsum, (double)wabs);
+    }
+    __syncthreads();
+
+    // ---- runs out: consecutive lanes write consecutive slots of a bin -------------------------------------------------
+    const int n_out = (int)misc[20];
+    for (int j = tid; j < n_out; j += PT) {
+        const unsigned b = sbin[j];
+        const unsigned slot = goff[b] + (unsigned)j;
+        const float4 v = stage[j];
+        if (slot < lim[b]) a.out[slot] = v;
+        else overflow_deposit<MAS, WEIGHTED>(v.x, v.y, v.z, v.w, g, a.number, &dropped);
+    }
+    if (a.dropped != nullptr && dropped != 0) atomicAdd(a.dropped, dropped);
+}
+
+// ---- 5. per-tile deposit ------------------------------------------------------------------------------------------
+// Accumulators are 64-bit FIXED-POINT sums held as two 32-bit words per cell (tile + stencil halo) and fed with
+// native 32-bit shared-memory atomics (ATOMS.ADD: 3.6 cycles per warp instruction, the price of a plain
+// read-modify-write; 64-bit and float shared atomics are CAS loops).  A contribution c = fl32(wx*wy*wz*W) becomes
+// q = rint(c * 2^k) with 2^k ~ 2^26 / mean|W|: one returning atomic on the low word, the carry (and the high word of
+// a large |q|) goes to the high word -- rarely.  Integer addition is associative, so the tile's sums do not depend on
+// the order the particles arrive in (bit-reproducible), and they are exact to 2^-26 of a typical contribution before
+// the single rounding to float32 when the tile is added to the grid.  Unweighted NGP stays bit-exact (q = 2^26).
+template <int MAS>
+struct TileAcc {
+    static constexpr int S = MAS + 1;
+    static constexpr int AX = TX + S - 1, AY = TY + S - 1;
+    static constexpr int ROWS = AX * AY;
+    static constexpr int CELLS = ROWS * OUT_ROW;               // OUT_ROW floats per row: rows are flushed in place
+    static constexpr size_t bytes = (size_t)CELLS * 8 + 16;
+    static_assert(TZ + S - 1 <= OUT_ROW, "row too short");
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int MAS, bool WEIGHTED>
+__global__ void __launch_bounds__(TNT)
+tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restrict__ starts,
+                    const unsigned *__restrict__ cur2, float *__restrict__ number, TileGeom g,
+                    const double *__restrict__ wsum, double particles, int bulk_ok) {
+    using TA = TileAcc<MAS>;
+    constexpr int S = TA::S, AY = TA::AY;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned *lo = reinterpret_cast<unsigned *>(smem_raw);            // CELLS low words; later the float rows to flush
+    unsigned *hi = lo + TA::CELLS;                                    // CELLS high words
+
+    const unsigned tile = blockIdx.x;
+    const unsigned begin = __ldg(starts + tile);
+    const unsigned end = min(__ldg(cur2 + tile), __ldg(starts + tile + 1));      // overflow went the direct way
+    if (begin >= end) return;                                   // empty tile: nothing to add
+
+    const int tid = threadIdx.x;
     const int tz = tile % g.ntz, ty = (tile / g.ntz) % g.nty, tx = tile / (g.ntz * g.nty);
     const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
 
-    for (int i = tid; i < SM::ACC; i += TNT) acc[i] = 0.0f;
-
-    // the next chunk's particles are fetched while the current chunk is accumulated (the exposed latency of
-    // this load was 18% of the kernel's stall samples)
-    float4 nxt[PER];
-#pragma unroll
-    for (int q = 0; q < PER; q++) {
-        const unsigned i = begin + tid + q * TNT;
-        nxt[q] = i < end ? __ldg(bucket + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // power-of-two scale: a typical contribution lands near 2^26 (exact scaling; see the header comment)
+    int kexp = 26;
+    if (WEIGHTED) {
+        const double mean = __ldg(wsum) / particles;
+        int e = 0;
+        if (mean > 0.0 && mean < 1e300) frexp(mean, &e);         // mean = f * 2^e, f in [0.5, 1)
+        kexp = 26 - e;
+        kexp = kexp > 120 ? 120 : (kexp < -120 ? -120 : kexp);
     }
+    const float scale = __int_as_float((127 + kexp) << 23);
+    const double inv_scale = __longlong_as_double((long long)(1023 - kexp) << 52);
 
-    for (unsigned c0 = begin; c0 < end; c0 += CHUNK) {
-        const int n = (int)min((unsigned)CHUNK, end - c0);
-        for (int i = tid; i < SM::CNT_WORDS; i += TNT) cnt[i] = 0u;
-        __syncthreads();
+    for (int i = tid; i < TA::CELLS / 2; i += TNT) reinterpret_cast<uint4 *>(lo)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
 
-        // ---- a. rank every particle within its cell ------------------------------------------------
-        // sort key: source plane, then the shared-memory BANK of the particle's first target cell, then y.
-        // Lanes of one accumulation batch sit nb sorted slots apart (below), i.e. in different banks most
-        // of the time: the read-modify-writes of a batch then need ~2 wavefronts instead of ~5.
-        float4 part[PER];
-        int key[PER], yzq[PER];
-        unsigned rank[PER];
+    // the next record is requested before the current one is accumulated (the shared-memory atomics below are
+    // ordering points: without this every iteration would wait for its own load)
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (begin + tid < end) nxt = __ldg(bucket + begin + tid);
+    for (unsigned i = begin + tid; i < end; i += TNT) {
+        const float4 v = nxt;
+        if (i + TNT < end) nxt = __ldg(bucket + i + TNT);
+        const float dd[3] = {v.x, v.y, v.z};
+        const int org[3] = {ox, oy, oz};
+        int lc[3];
+        float w[3][S];
 #pragma unroll
-        for (int q = 0; q < PER; q++) {
-            const int i = tid + q * TNT;
-            key[q] = -1;
-            if (i < n) {
-                const float4 v = nxt[q];
-                const float d[3] = {v.x, v.y, v.z};
-                float fr[3];
-                int lc[3];
-                const int org[3] = {ox, oy, oz};
+        for (int k = 0; k < 3; k++) {
+            const int b = axis_base<MAS>(dd[k]);
+            axis_weights<MAS>(dd[k], b, w[k]);
+            int wb = wrap_index(b, g.dims);
+            if (k == 0) { wb -= g.x_origin; if (wb < 0) wb += g.dims; }
+            lc[k] = wb - org[k];
+        }
+        const float ws = WEIGHTED ? v.w * scale : scale;
 #pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    const int b = stencil_base<MAS>(d[a], fr[a]);
-                    int wb = wrap_index(b, g.dims);
-                    if (a == 0) { wb -= g.x_origin; if (wb < 0) wb += g.dims; }
-                    lc[a] = wb - org[a];
+        for (int l = 0; l < S; l++) w[0][l] *= ws;
+        const int cell = (lc[0] * AY + lc[1]) * OUT_ROW + lc[2];
+        // one x-plane of the stencil at a time: its S*S low-word atomics are issued back to back (no branch between
+        // them, so their latencies overlap); the carries and the rare non-zero high words follow under ONE branch
+#pragma unroll
+        for (int l = 0; l < S; l++) {
+            unsigned old[S][S], ql[S][S];
+            int qh[S][S];
+#pragma unroll
+            for (int m = 0; m < S; m++) {
+                const float wxy = w[0][l] * w[1][m];
+#pragma unroll
+                for (int n = 0; n < S; n++) {
+                    const long long q = __float2ll_rn(wxy * w[2][n]);
+                    ql[m][n] = (unsigned)q;
+                    qh[m][n] = (int)(q >> 32);
                 }
-                const int bank = (lc[1] * (S - 1) + lc[2]) & (TZ - 1);       // (y*AZ + z) mod 32, AZ = 32+S-1
-                key[q] = (lc[0] * TZ + bank) * TY + lc[1];
-                yzq[q] = lc[1] * TZ + lc[2];
-                part[q] = make_float4(fr[0], fr[1], fr[2], v.w);
-                const unsigned old = atomicAdd(cnt + (key[q] >> 1), (key[q] & 1) ? 0x10000u : 1u);
-                rank[q] = (key[q] & 1) ? (old >> 16) : (old & 0xffffu);
             }
-        }
-        __syncthreads();
-
-        // ---- exclusive scan of the 8192 packed counters (32 per thread) -------------------------------
-        {
-            constexpr int WPT = TILE_CELLS / 2 / TNT;          // 16 words per thread
-            unsigned words[WPT];
-            unsigned sum = 0;
 #pragma unroll
-            for (int i = 0; i < WPT; i++) {
-                words[i] = cnt[tid * WPT + i];
-                sum += (words[i] & 0xffffu) + (words[i] >> 16);
+            for (int m = 0; m < S; m++) {
+#pragma unroll
+                for (int n = 0; n < S; n++) old[m][n] = atomicAdd(lo + cell + (l * AY + m) * OUT_ROW + n, ql[m][n]);
             }
-            unsigned incl = sum;
+            int any = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
+            for (int m = 0; m < S; m++) {
+#pragma unroll
+                for (int n = 0; n < S; n++) {
+                    qh[m][n] += (old[m][n] + ql[m][n]) < old[m][n] ? 1 : 0;
+                    any |= qh[m][n];
+                }
             }
-            if (lane == 31) warp_part[warp] = incl;
-            __syncthreads();
-            unsigned base = 0;
+            if (any != 0) {
 #pragma unroll
-            for (int w = 0; w < TNT / 32; w++) base += (w < warp) ? warp_part[w] : 0u;
-            unsigned run = base + incl - sum;
+                for (int m = 0; m < S; m++) {
 #pragma unroll
-            for (int i = 0; i < WPT; i++) {
-                const unsigned lo = words[i] & 0xffffu, hi = words[i] >> 16;
-                cnt[tid * WPT + i] = run | ((run + lo) << 16);
-                run += lo + hi;
-            }
-            if (tid == TNT - 1) cnt[TILE_CELLS / 2] = run;     // == n : end marker for the last row
-        }
-        __syncthreads();
-
-        // ---- scatter into cell order ------------------------------------------------------------------
-#pragma unroll
-        for (int q = 0; q < PER; q++) {
-            if (key[q] >= 0) {
-                const unsigned dst = off16(cnt, key[q]) + rank[q];
-                sorted[dst] = part[q];
-                sorted_yz[dst] = (unsigned short)yzq[q];
-            }
-        }
-        __syncthreads();
-
-        if (c0 + CHUNK < end) {
-#pragma unroll
-            for (int q = 0; q < PER; q++) {
-                const unsigned i = c0 + CHUNK + tid + q * TNT;
-                nxt[q] = i < end ? __ldg(bucket + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-
-        // ---- b. stencil accumulation: warp `warp` owns target planes X = warp, warp+8 -------------------
-        // (with TX = 8 and 8 warps every warp gets exactly S source-plane visits per chunk: balanced)
-        for (int X = warp; X < AX; X += TNT / 32) {
-            float *plane = acc + X * AY * AZ;
-#pragma unroll 1
-            for (int l = 0; l < S; l++) {
-                const int x = X - l;                           // source plane
-                if (x < 0 || x >= TX) continue;
-                // the particles of source plane x are contiguous and ordered by (y,z).  Lane i takes the slots
-                // q0 + i*nb + j: lanes of one batch are nb sorted slots apart, so two of them share a cell only
-                // when a run of equal cells is longer than nb -- at ~1 particle per cell almost never, and every
-                // lane then owns a distinct cell of plane X (plain read-modify-writes, no shuffles).  nb is made
-                // odd so that the 16-byte reads of `sorted` at stride nb stay free of bank conflicts.
-                const int q0 = (int)off16(cnt, x * TY * TZ);
-                const int q1 = (int)off16(cnt, (x + 1) * TY * TZ);
-                const int nb = q1 > q0 ? (((q1 - q0 + 31) >> 5) | 1) : 0;
-#pragma unroll 1
-                for (int j = 0; j < nb; j++) {
-                    const int p = q0 + lane * nb + j;
-                    const bool valid = p < q1;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    int yz = 0x4000 + lane;                    // invalid lanes: singleton segments
-                    if (valid) { v = sorted[p]; yz = sorted_yz[p]; }
-                    const int y = (yz >> 5) & (TY - 1), lz = yz & (TZ - 1);
-                    float wx[S], wy[S], wz[S];
-                    stencil_weights<MAS>(v.x, wx);
-                    stencil_weights<MAS>(v.y, wy);
-                    stencil_weights<MAS>(v.z, wz);
-                    float wxl = wx[0];
-#pragma unroll
-                    for (int jj = 1; jj < S; jj++) wxl = (l == jj) ? wx[jj] : wxl;
-                    const float wxw = wxl * v.w;
-
-                    // sorted slots are monotone in the lane: equal cells are adjacent lanes
-                    const int yz_up = __shfl_down_sync(0xffffffffu, yz, 1);
-                    const bool dup = __any_sync(0xffffffffu, lane < 31 && yz_up == yz);
-                    unsigned peers = 1u << lane;
-                    bool head = valid;
-                    int run_max = 1;
-                    if (dup) {
-                        peers = __match_any_sync(0xffffffffu, yz);
-                        head = valid && (lane == __ffs(peers) - 1);
-                        run_max = __reduce_max_sync(0xffffffffu, __popc(peers));
-                    }
-                    float *cellp = plane + y * AZ + lz;
-
-                    if (run_max == 1) {
-                        // every lane owns a distinct cell of the target plane: plain read-modify-writes
-#pragma unroll
-                        for (int m = 0; m < S; m++) {
-                            const float wxy = wxw * wy[m];
-#pragma unroll
-                            for (int nn = 0; nn < S; nn++) {
-                                if (valid) cellp[m * AZ + nn] += wxy * wz[nn];
-                                __syncwarp();
-                            }
-                        }
-                    } else {
-                        // segmented suffix scan over each run; its head lane adds the run's sum
-                        const unsigned above = peers >> lane;          // bit d: lane+d is in my run
-                        const int nsteps = 32 - __clz(run_max - 1);
-#pragma unroll
-                        for (int m = 0; m < S; m++) {
-                            const float wxy = wxw * wy[m];
-#pragma unroll
-                            for (int nn = 0; nn < S; nn++) {
-                                float val = wxy * wz[nn];
-                                for (int k = 0; k < nsteps; k++) {
-                                    const float o = __shfl_down_sync(0xffffffffu, val, 1 << k);
-                                    if (above & (1u << (1 << k))) val += o;
-                                }
-                                if (head) cellp[m * AZ + nn] += val;
-                                __syncwarp();
-                            }
-                        }
-                    }
+                    for (int n = 0; n < S; n++)
+                        if (qh[m][n] != 0) atomicAdd(hi + cell + (l * AY + m) * OUT_ROW + n, (unsigned)qh[m][n]);
                 }
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
-    // ---- c. flush tile + halo into the grid: a warp per (x,y) row, lanes along z (coalesced reductions) -----
+    // ---- fixed point -> float32, in place: lo[] becomes the rows to add to the grid ------------------------------------
+    float *outst = reinterpret_cast<float *>(lo);
+    for (int i = tid; i < TA::CELLS; i += TNT) {
+        const long long q = (long long)(((unsigned long long)hi[i] << 32) | lo[i]);
+        outst[i] = (float)((double)q * inv_scale);               // exact scaling, one rounding
+    }
     const int dims = g.dims;
-    for (int r = warp; r < AX * AY; r += TNT / 32) {
-        const int ax = r / AY, ay = r - ax * AY;
-        int gx = ox + ax, gy = oy + ay;                        // gx: plane inside the destination buffer
-        if (gx >= g.x_planes) gx -= g.x_planes;                // only when the buffer is the whole periodic grid
-        if (gy >= dims) gy -= dims;
-        float *row = number + ((int64_t)gx * dims + gy) * dims;
-        for (int az = lane; az < AZ; az += 32) {
-            const float val = acc[r * AZ + az];
-            int gz = oz + az;
-            if (gz >= dims) gz -= dims;
-            if (val != 0.0f) atomicAdd(row + gz, val);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (bulk_ok) {
+        // make the generic-proxy writes of the rows visible to the bulk-copy engine
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid < TA::ROWS) {
+            const int r = tid;
+            const int ax = r / AY, ay = r - ax * AY;
+            int gx = ox + ax, gy = oy + ay;                    // gx: plane inside the destination buffer
+            if (gx >= g.x_planes) gx -= g.x_planes;            // only when the buffer is the whole periodic grid
+            if (gy >= dims) gy -= dims;
+            const uint4 *rowv = reinterpret_cast<const uint4 *>(outst + r * OUT_ROW);
+            unsigned nz = 0;
+#pragma unroll
+            for (int k = 0; k < OUT_ROW / 4; k++) {
+                const uint4 t = rowv[k];
+                nz |= (t.x | t.y | t.z | t.w) << 1;             // (the shift drops the sign of a -0.0)
+            }
+            // rows beyond a partial tile's extent and untouched rows carry only zeros: skipped
+            if (nz != 0 && gx < g.x_planes && gy < dims) {
+                float *row = number + ((int64_t)gx * dims + gy) * dims;
+                const unsigned src = smem_u32(outst + r * OUT_ROW);
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                             ::"l"(row + oz), "r"(src), "r"(TZ * 4) : "memory");
+                if (S > 1) {
+                    int gz = oz + TZ;
+                    if (gz >= dims) gz -= dims;
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                 ::"l"(row + gz), "r"(src + TZ * 4), "r"(16) : "memory");
+                }
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else {
+        __syncthreads();
+        for (int r = warp; r < TA::ROWS; r += TNT / 32) {
+            const int ax = r / AY, ay = r - ax * AY;
+            int gx = ox + ax, gy = oy + ay;
+            if (gx >= g.x_planes) gx -= g.x_planes;
+            if (gy >= dims) gy -= dims;
+            if (gx >= g.x_planes || gy >= dims) continue;       // beyond a partial tile: zeros only
+            float *row = number + ((int64_t)gx * dims + gy) * dims;
+            for (int az = lane; az < TZ + S - 1; az += 32) {
+                const float val = outst[r * OUT_ROW + az];
+                int gz = oz + az;
+                if (gz >= dims) gz -= dims;
+                if (val != 0.0f && gz < dims) atomicAdd(row + gz, val);
+            }
         }
     }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
-static TileGeom make_geom(int dims, float BoxSize, int x_origin = 0, int x_own = -1, int x_planes = -1) {
+static TileGeom make_geom(int dims, float BoxSize, int64_t particles, int x_origin = 0, int x_own = -1,
+                          int x_planes = -1) {
     TileGeom g;
     g.dims = dims;
     g.x_origin = x_origin;
@@ -509,6 +654,17 @@ static TileGeom make_geom(int dims, float BoxSize, int x_origin = 0, int x_own =
     g.ntz = (dims + TZ - 1) / TZ;
     g.ntiles = (unsigned)g.ntx * g.nty * g.ntz;
     g.inv_cell_size = (float)dims / BoxSize;      // float32 division, MAS_library.pyx:135
+    // both passes get about sqrt(ntiles) bins (a power of two tiles per super-tile)
+    int sh = 0;
+    while (((uint64_t)1 << (2 * sh)) < g.ntiles) sh++;
+    while ((g.ntiles + ((1u << sh) - 1)) >> sh > (unsigned)MAX_BINS) sh++;
+    g.tps_shift = sh;
+    g.nsuper = (g.ntiles + ((1u << sh) - 1)) >> sh;
+    // one cursor replica per 64 first-pass CTAs: a cursor then serves few enough same-address atomics, and every
+    // replica still receives an even share of the particles
+    const int64_t ctas = (particles + PP - 1) / PP;
+    int64_t r = ctas / 64;
+    g.repl = (unsigned)(r < 1 ? 1 : (r > MAX_REPL ? MAX_REPL : r));
     return g;
 }
 
@@ -519,45 +675,59 @@ static size_t scan_temp_bytes(unsigned n) {
 }
 
 // upper bound of sum_t tile_capacity(c_t) given sum_t c_t <= particles/SAMPLE + 4 (Cauchy-Schwarz on
-// the sqrt term); the scatter kernel can therefore never write past the bucket array
+// the sqrt term); the partition kernels can therefore never write past the bucket planes
 static size_t bucket_slots_bound(int64_t particles, unsigned ntiles) {
     const double sampled = (double)particles / SAMPLE + 8.0;
     const double bound = 1.125 * SAMPLE * sampled + (4.0 * SAMPLE + 1.0) * sqrt((double)ntiles * sampled) +
-                         34.0 * (double)ntiles;
-    return (size_t)bound + 1024;
+                         38.0 * (double)ntiles;
+    return ((size_t)bound + 1024 + 3) & ~(size_t)3;
 }
 
 bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes, int x_own) {
     (void)mas;
     if (axes != 3 || dims < 64) return false;                       // halo wrap assumes dims >> stencil
-    const TileGeom g = make_geom(dims, 1.0f, 0, x_own, x_own);
-    if ((int64_t)g.ntiles > ((int64_t)1 << 30)) return false;
-    // 32-bit slots; the cursor's low word may run past its bucket by the number of overflowing particles
+    const TileGeom g = make_geom(dims, 1.0f, particles, 0, x_own, x_own);
+    if ((uint64_t)g.ntx * g.nty * g.ntz > (uint64_t)MAX_BINS * MAX_BINS) return false;
+    if (g.tps_shift > 11) return false;                             // more than MAX_BINS tiles per super-tile
+    // 32-bit slots; a cursor may run past its bucket by the number of overflowing particles
     if (bucket_slots_bound(particles, g.ntiles) + (size_t)particles >= ((size_t)1 << 32)) return false;
     return particles >= (int64_t)g.ntiles * 64;                     // sparse inputs: per-tile overhead loses
 }
 
 struct TiledWorkspace {
-    float4 *bucket;
-    unsigned *starts;   // ntiles + 1 : sampled counts -> capacities -> exclusive scan
-    unsigned long long *cursor;   // ntiles : (bucket end << 32) | next free slot
+    float4 *buf1, *buf2;          // `slots` records (dist.x, dist.y, dist.z, W) each
+    size_t slots;
+    double *wsum;                 // sum of |W| of this call's particles
+    unsigned *starts;             // ntiles + 1 : sampled counts -> capacities -> exclusive scan
+    unsigned *cur2;               // ntiles : next free slot of a tile's bucket
+    unsigned *cur1;               // MAX_REPL x nsuper : next free slot of a super-tile sub-segment
+    unsigned *spre;               // nsuper + 1
     void *scan_tmp;
     size_t scan_bytes;
     size_t total;
 };
 
-static TiledWorkspace carve(void *ws, int64_t particles, unsigned ntiles) {
+static TiledWorkspace carve(void *ws, int64_t particles, const TileGeom &g) {
     TiledWorkspace w;
     char *base = reinterpret_cast<char *>(ws);
     size_t off = 0;
-    w.bucket = reinterpret_cast<float4 *>(base + off);
-    off += align_up(bucket_slots_bound(particles, ntiles) * 16, 256);
+    w.slots = bucket_slots_bound(particles, g.ntiles);
+    w.buf1 = reinterpret_cast<float4 *>(base + off);
+    off += align_up(w.slots * 16, 256);
+    w.buf2 = reinterpret_cast<float4 *>(base + off);
+    off += align_up(w.slots * 16, 256);
+    w.wsum = reinterpret_cast<double *>(base + off);
+    off += 256;
     w.starts = reinterpret_cast<unsigned *>(base + off);
-    off += align_up(((size_t)ntiles + 1) * 4, 256);
-    w.cursor = reinterpret_cast<unsigned long long *>(base + off);
-    off += align_up((size_t)ntiles * 8, 256);
+    off += align_up(((size_t)g.ntiles + 1) * 4, 256);
+    w.cur2 = reinterpret_cast<unsigned *>(base + off);
+    off += align_up((size_t)g.ntiles * 4, 256);
+    w.cur1 = reinterpret_cast<unsigned *>(base + off);
+    off += align_up((size_t)MAX_REPL * g.nsuper * 4, 256);
+    w.spre = reinterpret_cast<unsigned *>(base + off);
+    off += align_up(((size_t)g.nsuper + 1) * 4, 256);
     w.scan_tmp = base + off;
-    w.scan_bytes = scan_temp_bytes(ntiles + 1);
+    w.scan_bytes = scan_temp_bytes(g.ntiles + 1);
     off += align_up(w.scan_bytes, 256);
     w.total = off;
     return w;
@@ -565,16 +735,54 @@ static TiledWorkspace carve(void *ws, int64_t particles, unsigned ntiles) {
 
 size_t deposit_tiled_workspace(int mas, int64_t particles, int dims, int axes, int mode, int x_own) {
     (void)mas; (void)axes; (void)mode;
-    const TileGeom g = make_geom(dims, 1.0f, 0, x_own, x_own);
-    return carve(nullptr, particles, g.ntiles).total;
+    const TileGeom g = make_geom(dims, 1.0f, particles, 0, x_own, x_own);
+    return carve(nullptr, particles, g).total;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    PYL_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PYL_OK;
+}
+
+template <int MAS, bool WEIGHTED>
+static int run_tiled_w(const float *pos, float *number, const float *W, int64_t particles, const TileGeom &g,
+                       const TiledWorkspace &w, unsigned long long *dropped, cudaStream_t stream) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        int st = set_smem(partition_kernel<MAS, WEIGHTED, 1>, part_smem_bytes(MAX_BINS));
+        if (st == PYL_OK) st = set_smem(partition_kernel<MAS, WEIGHTED, 2>, part_smem_bytes(MAX_BINS));
+        if (st == PYL_OK) st = set_smem(tile_deposit_kernel<MAS, WEIGHTED>, TileAcc<MAS>::bytes);
+        if (st != PYL_OK) return st;
+        attr_done = true;
+    }
+    PartArgs a;
+    a.pos = pos; a.W = W; a.particles = particles; a.in = w.buf1; a.out = w.buf1;
+    a.starts = w.starts; a.cur1 = w.cur1; a.cur2 = w.cur2; a.spre = w.spre; a.number = number; a.dropped = dropped;
+    a.wsum = w.wsum;
+    if (WEIGHTED) PYL_CUDA_CHECK(cudaMemsetAsync(w.wsum, 0, 8, stream));
+    const unsigned ctas1 = (unsigned)((particles + PP - 1) / PP);
+    partition_kernel<MAS, WEIGHTED, 1><<<ctas1, PT, part_smem_bytes((int)g.nsuper), stream>>>(a, g);
+    PYL_LAUNCH_CHECK();
+    a.out = w.buf2;
+    // upper bound of the chunk count, rounded up to a multiple of nsuper (pass 2 walks it transposed)
+    const unsigned ctas2 = (unsigned)((w.slots / PP + (size_t)g.repl * g.nsuper + g.nsuper) / g.nsuper * g.nsuper);
+    partition_kernel<MAS, WEIGHTED, 2><<<ctas2, PT, part_smem_bytes(1 << g.tps_shift), stream>>>(a, g);
+    PYL_LAUNCH_CHECK();
+    // bulk reductions need 16-byte aligned 128-byte rows: whole tiles along z and an aligned grid
+    const int bulk_ok = (g.dims % TZ == 0) && ((reinterpret_cast<uintptr_t>(number) & 15) == 0);
+    tile_deposit_kernel<MAS, WEIGHTED><<<g.ntiles, TNT, TileAcc<MAS>::bytes, stream>>>(
+        w.buf2, w.starts, w.cur2, number, g, w.wsum, (double)particles, bulk_ok);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
 }
 
 template <int MAS>
 static int run_tiled(const float *pos, float *number, const float *W, int64_t particles, int dims,
                      float BoxSize, int x_origin, int x_own, int x_planes, unsigned long long *dropped,
                      void *ws, cudaStream_t stream) {
-    const TileGeom g = make_geom(dims, BoxSize, x_origin, x_own, x_planes);
-    const TiledWorkspace w = carve(ws, particles, g.ntiles);
+    const TileGeom g = make_geom(dims, BoxSize, particles, x_origin, x_own, x_planes);
+    const TiledWorkspace w = carve(ws, particles, g);
 
     const int vec_ok = ((reinterpret_cast<uintptr_t>(pos) & 15) == 0) &&
                        (W == nullptr || (reinterpret_cast<uintptr_t>(W) & 15) == 0);
@@ -592,26 +800,10 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
     PYL_LAUNCH_CHECK();
     PYL_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.scan_tmp, const_cast<size_t &>(w.scan_bytes), w.starts, w.starts,
                                                  (int)(g.ntiles + 1), stream));
-    tile_cursor_kernel<<<(g.ntiles + 255) / 256, 256, 0, stream>>>(w.starts, w.cursor, g.ntiles);
+    tile_setup_kernel<<<1 + (g.ntiles + 1023) / 1024, 1024, 0, stream>>>(w.starts, g, w.cur1, w.cur2, w.spre);
     PYL_LAUNCH_CHECK();
-    const unsigned sblocks = (unsigned)((particles + 511) / 512);
-    if (W)
-        tile_scatter_kernel<MAS, true><<<sblocks, 512, 0, stream>>>(pos, W, particles, g, w.cursor, w.bucket, number,
-                                                                    dropped);
-    else
-        tile_scatter_kernel<MAS, false><<<sblocks, 512, 0, stream>>>(pos, W, particles, g, w.cursor, w.bucket, number,
-                                                                     dropped);
-    PYL_LAUNCH_CHECK();
-
-    static bool attr_done[4] = {false, false, false, false};
-    if (!attr_done[MAS]) {
-        PYL_CUDA_CHECK(cudaFuncSetAttribute(tile_deposit_kernel<MAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)TileSmem<MAS>::bytes));
-        attr_done[MAS] = true;
-    }
-    tile_deposit_kernel<MAS><<<g.ntiles, TNT, TileSmem<MAS>::bytes, stream>>>(w.bucket, w.cursor, number, g);
-    PYL_LAUNCH_CHECK();
-    return PYL_OK;
+    if (W) return run_tiled_w<MAS, true>(pos, number, W, particles, g, w, dropped, stream);
+    return run_tiled_w<MAS, false>(pos, number, W, particles, g, w, dropped, stream);
 }
 
 // x_own < 0: whole periodic grid.  Otherwise the slab window of pyl_deposit_slab.

@@ -35,72 +35,75 @@ __device__ __forceinline__ float cell_coordinate(float pos, float inv_cell_size)
     return __fmul_rn(pos, inv_cell_size);
 }
 
-// idx[j] : wrapped cell index along this axis, w[j] : its weight, j < StencilWidth<MAS>
+// First (unwrapped) cell of the stencil along one axis.
 template <int MAS>
-__device__ __forceinline__ void axis_stencil(float dist, int dims, int *idx, float *w);
-
-template <>
-__device__ __forceinline__ void axis_stencil<PYL_MAS_NGP>(float dist, int dims, int *idx, float *w) {
-    // <int>(pos*inv + 0.5): the 0.5 is a double in the reference, so the add is done in f64
-    const int i = __double2int_rz(__dadd_rn((double)dist, 0.5));
-    idx[0] = wrap_index(i, dims);
-    w[0] = 1.0f;
+__device__ __forceinline__ int axis_base(float dist) {
+    if (MAS == PYL_MAS_NGP) return __double2int_rz(__dadd_rn((double)dist, 0.5));   // the 0.5 is a double in the reference
+    if (MAS == PYL_MAS_CIC) return __float2int_rz(dist);
+    if (MAS == PYL_MAS_TSC) return __double2int_rd(__dadd_rn((double)dist, -1.5)) + 1;
+    return __double2int_rd(__dadd_rn((double)dist, -2.0)) + 1;
 }
 
-template <>
-__device__ __forceinline__ void axis_stencil<PYL_MAS_CIC>(float dist, int dims, int *idx, float *w) {
-    const int i = __float2int_rz(dist);
-    const float u = __fsub_rn(dist, (float)i);
-    const float d = __fsub_rn(1.0f, u);
-    idx[0] = wrap_index(i, dims);
-    idx[1] = (idx[0] + 1 == dims) ? 0 : idx[0] + 1;
-    w[0] = d;
-    w[1] = u;
-}
-
-template <>
-__device__ __forceinline__ void axis_stencil<PYL_MAS_TSC>(float dist, int dims, int *idx, float *w) {
-    const int minimum = __double2int_rd(__dadd_rn((double)dist, -1.5));
+// The S weights of the cells base, base+1, ... in the reference's own arithmetic (float64 where the reference
+// promotes, then rounded to float32).  `base` = axis_base<MAS>(dist).
+template <int MAS>
+__device__ __forceinline__ void axis_weights(float dist, int base, float *w) {
+    if (MAS == PYL_MAS_NGP) {
+        w[0] = 1.0f;
+    } else if (MAS == PYL_MAS_CIC) {
+        const float u = __fsub_rn(dist, (float)base);
+        w[0] = __fsub_rn(1.0f, u);
+        w[1] = u;
+    } else if (MAS == PYL_MAS_TSC) {
 #pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const int c = minimum + j + 1;
-        idx[j] = wrap_index(c, dims);
-        const float diff = fabsf(__fsub_rn((float)c, dist));
-        float v;
-        if (diff < 0.5f) {
-            v = __double2float_rn(__dsub_rn(0.75, (double)__fmul_rn(diff, diff)));
-        } else if (diff < 1.5f) {
-            const double t = __dsub_rn(1.5, (double)diff);
-            v = __double2float_rn(__dmul_rn(__dmul_rn(0.5, t), t));
-        } else {
-            v = 0.0f;
+        for (int j = 0; j < 3; j++) {
+            const float diff = fabsf(__fsub_rn((float)(base + j), dist));
+            float v;
+            if (diff < 0.5f) {
+                v = __double2float_rn(__dsub_rn(0.75, (double)__fmul_rn(diff, diff)));
+            } else if (diff < 1.5f) {
+                const double t = __dsub_rn(1.5, (double)diff);
+                v = __double2float_rn(__dmul_rn(__dmul_rn(0.5, t), t));
+            } else {
+                v = 0.0f;
+            }
+            w[j] = v;
         }
-        w[j] = v;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float diff = fabsf(__fsub_rn((float)(base + j), dist));
+            const double x = (double)diff;
+            float v;
+            if (diff < 1.0f) {
+                // (4 - 6x^2 + 3x^3)/6 in double, left to right; the reference is compiled with -ffast-math
+                // (setup.py:26-31), which turns the division by 6.0 into a multiplication by its reciprocal
+                const double a = __dsub_rn(4.0, __dmul_rn(__dmul_rn(6.0, x), x));
+                const double b = __dmul_rn(__dmul_rn(__dmul_rn(3.0, x), x), x);
+                v = __double2float_rn(__dmul_rn(__dadd_rn(a, b), 1.0 / 6.0));
+            } else if (diff < 2.0f) {
+                const double t = __dsub_rn(2.0, x);
+                v = __double2float_rn(__dmul_rn(__dmul_rn(__dmul_rn(t, t), t), 1.0 / 6.0));
+            } else {
+                v = 0.0f;
+            }
+            w[j] = v;
+        }
     }
 }
 
-template <>
-__device__ __forceinline__ void axis_stencil<PYL_MAS_PCS>(float dist, int dims, int *idx, float *w) {
-    const int minimum = __double2int_rd(__dadd_rn((double)dist, -2.0));
+// idx[j] : wrapped cell index along this axis, w[j] : its weight, j < StencilWidth<MAS>
+// (one definition of the arithmetic for the atomic, tiled and deterministic deposits)
+template <int MAS>
+__device__ __forceinline__ void axis_stencil(float dist, int dims, int *idx, float *w) {
+    constexpr int S = StencilWidth<MAS>::value;
+    const int base = axis_base<MAS>(dist);
+    axis_weights<MAS>(dist, base, w);
+    idx[0] = wrap_index(base, dims);
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int c = minimum + j + 1;
-        idx[j] = wrap_index(c, dims);
-        const float diff = fabsf(__fsub_rn((float)c, dist));
-        const double x = (double)diff;
-        float v;
-        if (diff < 1.0f) {
-            // (4 - 6x^2 + 3x^3)/6, left-to-right like the reference's double expression
-            const double a = __dsub_rn(4.0, __dmul_rn(__dmul_rn(6.0, x), x));
-            const double b = __dmul_rn(__dmul_rn(__dmul_rn(3.0, x), x), x);
-            v = __double2float_rn(__ddiv_rn(__dadd_rn(a, b), 6.0));
-        } else if (diff < 2.0f) {
-            const double t = __dsub_rn(2.0, x);
-            v = __double2float_rn(__ddiv_rn(__dmul_rn(__dmul_rn(t, t), t), 6.0));
-        } else {
-            v = 0.0f;
-        }
-        w[j] = v;
+    for (int j = 1; j < S; j++) {
+        if (MAS == PYL_MAS_CIC) idx[j] = (idx[j - 1] + 1 == dims) ? 0 : idx[j - 1] + 1;   // (i_d + 1) % dims
+        else idx[j] = wrap_index(base + j, dims);
     }
 }
 
