@@ -1,17 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- MA -> delta -> Pk throughput of the B200-native path (and of the reference's CPU path).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config3|config2]
 
-One "step" = one pass of the hot path over one batch of synthetic input (BASELINE.json config 2 at
-N=1): zero the grid, MAS_library.MA (CIC) of dims^3 uniform-random particles onto a dims^3 grid,
-delta = n/<n> - 1, Pk_library.Pk (FFT + deconvolution + binning of l=0,2,4, 1D and 2D spectra),
-results on the host.  `value` = particles per second through that whole step with the positions
-resident in HBM; `e2e` = the same step with the positions starting in pinned HOST memory (H2D copy
-inside the timed region).  Rank 0 prints ONE JSON line.
+One "step" = one pass of the hot path over one batch of synthetic input.  Default workload = BASELINE.json config 3,
+the configuration the metric is quoted on: 1024^3 Zel'dovich-displaced particles with weights onto a 1024^3 grid
+with PCS (MAS_library.MA), delta = n/<n> - 1, Pk_library.Pk (r2c FFT, window deconvolution, l = 0,2,4 multipoles,
+1D and 2D(kpar,kper) spectra), results on the host.  `value` = particles per second through that whole step with the
+particles resident in HBM; `e2e` = the same step with positions and weights starting in pinned HOST memory (H2D
+inside the timed region, results back on the host).  Rank 0 prints ONE JSON line.
 
-N>1 (torchrun, one rank per GPU): weak scaling -- each rank owns an x-slab of a larger grid and the
-same number of particles; halo exchange, distributed FFT and bin all-reduce are inside the step.
+N > 1 (torchrun, one rank per GPU): STRONG scaling of the same workload -- every rank starts with the particles of
+its share of the Lagrangian lattice (not yet on their owner ranks); routing to the x-slab owners, halo exchange of
+the stencil overlap, slab-decomposed FFT (peer-memory transpose) and the all-reduce of the bin sums are inside the
+step.  `--workload config2` runs BASELINE config 2 (512^3 uniform particles, CIC) instead.
 """
 import argparse
 import contextlib
@@ -29,15 +31,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 BOX = 1000.0
-MAS = "CIC"
-AXIS = 0
-# weak-scaling ladder: ~512^3 particles and cells per GPU, FFT-friendly sizes (2^a 5^b)
-GRID_FOR_GPUS = {1: 512, 2: 640, 4: 800, 8: 1024}
-# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one MA(CIC) call at 512^3/512^3 from the
-# `ncu --set full` capture summarised in profiles/r1_tiled_deposit_cic_final.md: tile_count 0.54 GB +
-# tile_scatter 3.90 GB + tile_deposit 3.21 GB
-NCU_DEPOSIT_TRAFFIC = {("CIC", 512): 7.65e9}
-
+WORKLOADS = {
+    "config3": {"label": "BASELINE config 3", "grid": 1024, "particles": "zeldovich", "weighted": True, "mas": "PCS",
+                "axis": 0, "seed": 3},
+    "config2": {"label": "BASELINE config 2", "grid": 512, "particles": "uniform", "weighted": False, "mas": "CIC",
+                "axis": 0, "seed": 1},
+}
+CPU_SAMPLE_DIMS = 256          # the CPU legs run the same recipe at 256^3 particles -> 256^3 grid
+METRIC = "MA+Pk particles/sec (MAS_library.MA -> delta -> Pk_library.Pk incl. l=0,2,4, Pk1D, Pk2D), 1024^3-class grid"
 
 _RESULT = None
 
@@ -65,6 +66,17 @@ def measured_peak_hbm():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(key):
+    """DRAM bytes per MA call (dram__bytes_read.sum + dram__bytes_write.sum over the deposit's kernels) from the
+    committed `ncu --set full` capture of the same workload, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            e = json.load(f).get(key)
+        return (e["bytes"], e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -114,6 +126,24 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def workload_text(wl, grid):
+    return ("%s: %d^3 %s float32 particles%s, %d^3 grid, BoxSize=%g, MA(%s%s) -> delta=n/<n>-1 -> Pk(axis=%d) with "
+            "l=0,2,4 + Pk1D + Pk2D(kpar,kper)" % (
+                wl["label"], grid, "Zel'dovich-displaced" if wl["particles"] == "zeldovich" else "uniform-random",
+                " with weights W" if wl["weighted"] else "", grid, BOX, wl["mas"], ",W" if wl["weighted"] else "",
+                wl["axis"]))
+
+
+def workload_config(wl, grid, gpus):
+    per = grid ** 3 * (16 if wl["weighted"] else 12) / gpus / 1e9
+    return {"workload": workload_text(wl, grid), "particles": grid ** 3, "grid": grid, "mas": wl["mas"],
+            "weighted": wl["weighted"], "axis": wl["axis"], "gpus": gpus,
+            "decomposition": "single GPU" if gpus == 1 else
+            "x-slabs: particle routing to slab owners, halo exchange, slab FFT with peer-memory transpose, bin all-reduce",
+            "l2": "inputs larger than L2 (particles %.2f GB + grid %.2f GB per GPU >> 126 MB)" % (
+                per, grid ** 3 * 4 / gpus / 1e9)}
+
+
 # ------------------------------------------------------------------------------------------------
 # reference / CPU baseline legs (the only places that may execute oracle/)
 # ------------------------------------------------------------------------------------------------
@@ -129,82 +159,159 @@ def cpu_path():
     return O.MA, (lambda d, box, axis, mas, thr: O.Pk(d, box, axis, mas, thr, False)), "port"
 
 
-def cpu_step(MA, Pk, pos, dims, threads):
+def cpu_inputs(wl, dims):
+    from pylians3_b200 import synth
+    if wl["particles"] == "zeldovich":
+        pos = synth.zeldovich_host(dims, BOX, wl["seed"])
+    else:
+        pos = synth.uniform_host(dims ** 3, BOX, wl["seed"])
+    W = np.random.default_rng(wl["seed"] + 7919).random(dims ** 3, dtype=np.float32) if wl["weighted"] else None
+    return pos, W
+
+
+def cpu_step(MA, Pk, wl, pos, W, dims, threads):
     grid = np.zeros((dims, dims, dims), np.float32)
-    MA(pos, grid, BOX, MAS)
-    grid /= np.mean(grid, dtype=np.float64)
-    grid -= 1.0
-    return Pk(grid, BOX, AXIS, MAS, threads)
+    with contextlib.redirect_stdout(io.StringIO()):
+        MA(pos, grid, BOX, wl["mas"], W)
+        grid /= np.mean(grid, dtype=np.float64)
+        grid -= 1.0
+        return Pk(grid, BOX, wl["axis"], wl["mas"], threads)
 
 
-CPU_SAMPLE_DIMS = 256
+def cpu_sample_text(wl, dims, threads):
+    return ("%d^3 %s particles%s -> %d^3 grid, MA(%s) + delta + Pk(axis=%d): the workload's recipe at 1/%d of its "
+            "particles and cells; particles/s is size-normalised (the reference gets slower on larger grids); MA is "
+            "serial in the reference, threads=%d reach only its FFT" % (
+                dims, wl["particles"], " + W" if wl["weighted"] else "", dims, wl["mas"], wl["axis"],
+                (WORKLOADS_GRID[0] // dims) ** 3, threads))
 
 
-def cpu_baseline(reps=2):
-    """Reference CPU path on a bounded sample of the workload: 256^3 particles -> 256^3 grid + Pk
-    (1/8 of the 512^3 step in particles and in modes), best of `reps`."""
+WORKLOADS_GRID = [1024]
+
+
+def cpu_baseline(wl, reps=1):
+    """Reference CPU path on a bounded sample of the workload, best of `reps`."""
     MA, Pk, kind = cpu_path()
     dims = CPU_SAMPLE_DIMS
-    pos = np.random.default_rng(1).random((dims ** 3, 3), dtype=np.float32) * np.float32(BOX)
+    pos, W = cpu_inputs(wl, dims)
     threads = os.cpu_count() or 1
     best = None
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_step(MA, Pk, pos, dims, threads)
+        cpu_step(MA, Pk, wl, pos, W, dims, threads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return {"value": dims ** 3 / best, "unit": "particles/s", "cores": 1 if kind == "port" else threads,
-            "kind": kind, "seconds_per_sample": best,
-            "sample": "%d^3 uniform particles -> %d^3 grid, MA(%s) + delta + Pk(axis=%d): 1/8 of one step; "
-                      "MA is serial in the reference, threads=%d reach only its FFT" % (dims, dims, MAS, AXIS, threads)}
+            "kind": kind, "seconds_per_sample": best, "sample": cpu_sample_text(wl, dims, threads)}
 
 
-def run_reference(args):
+def run_reference(args, wl, grid):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     MA, Pk, kind = cpu_path()
     dims = CPU_SAMPLE_DIMS
-    pos = np.random.default_rng(1).random((dims ** 3, 3), dtype=np.float32) * np.float32(BOX)
+    pos, W = cpu_inputs(wl, dims)
     threads = os.cpu_count() or 1
     for _ in range(args.warmup):
-        cpu_step(MA, Pk, pos, dims, threads)
+        cpu_step(MA, Pk, wl, pos, W, dims, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(MA, Pk, pos, dims, threads)
+        cpu_step(MA, Pk, wl, pos, W, dims, threads)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = dims ** 3 / dt
-    grid = GRID_FOR_GPUS.get(args.gpus, 512)
-    sample = ("each step = %d^3 uniform particles -> %d^3 grid, MA(%s)+delta+Pk(axis=%d) on the host CPU "
-              "(bounded sample of the %d^3 workload; particles/s is size-normalised)" % (dims, dims, MAS, AXIS, grid))
-    line = {"impl": "reference", "metric": metric_name(grid), "value": value, "unit": "particles/s",
+    sample = cpu_sample_text(wl, dims, threads)
+    cfg = workload_config(wl, grid, args.gpus)
+    # the label says what was actually run: a bounded sample of the workload, on the host CPU
+    cfg["workload"] += " [reference arm: each step is a %d^3-particle / %d^3-grid SAMPLE of this workload on the " \
+                       "host CPU; particles/s is size-normalised]" % (dims, dims)
+    cfg["reference_sample"] = sample
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "particles/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(grid, args.gpus),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
             "cpu_baseline": {"value": value, "unit": "particles/s", "cores": threads if kind == "reference" else 1,
                              "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
-def metric_name(grid):
-    return "MA+Pk particles/sec (%s, %d^3 uniform particles -> %d^3 grid, Pk l=0,2,4 + 1D + 2D, axis=%d)" % (
-        MAS, grid, grid, AXIS)
-
-
-def workload_config(grid, gpus):
-    return {"workload": "BASELINE config 2 shape: %d^3 uniform-random float32 particles, %d^3 grid, BoxSize=%g, "
-                        "MA(%s) -> delta=n/<n>-1 -> Pk(axis=%d)" % (grid, grid, BOX, MAS, AXIS),
-            "particles": grid ** 3, "grid": grid, "mas": MAS, "axis": AXIS, "gpus": gpus,
-            "decomposition": "single GPU" if gpus == 1 else "x-slabs, halo exchange + slab FFT all-to-all + bin all-reduce",
-            "l2": "inputs larger than L2 (positions %.2f GB + grid %.2f GB per GPU >> 126 MB)" % (
-                grid ** 3 * 12 / gpus / 1e9, grid ** 3 * 4 / gpus / 1e9)}
-
-
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def make_inputs(wl, grid, world, rank, dev):
+    """Particles (and weights) of this rank: everything at N = 1, else the rank's share of the Lagrangian lattice /
+    of the particle list -- NOT yet on the ranks that own their cells."""
+    import torch
+    from pylians3_b200 import synth
+    n3 = grid ** 3
+    if wl["particles"] == "zeldovich":
+        pos = synth.zeldovich_device(grid, BOX, wl["seed"], dev)
+        if world > 1:
+            i0, i1 = rank * grid // world, (rank + 1) * grid // world
+            pos = pos.view(grid, grid * grid, 3)[i0:i1].reshape(-1, 3).clone()
+        lo, hi = (0, n3) if world == 1 else (i0 * grid * grid, i1 * grid * grid)
+    else:
+        lo, hi = rank * n3 // world, (rank + 1) * n3 // world
+        pos = synth.uniform_device(hi - lo, BOX, wl["seed"] + 1000 * rank, dev)
+    W = None
+    if wl["weighted"]:
+        W = synth.weights_device(n3, wl["seed"], dev)
+        if world > 1:
+            W = W[lo:hi].clone()
+    torch.cuda.empty_cache()
+    return pos, W
+
+
+def small_parity_check(world, rank, dev):
+    """Before timing: the step's own code path on a small case against the CPU oracle (64^3 grid, 2*64^3 clustered
+    particles with weights, PCS): max per-cell deposit error and max Pk monopole error.  The oracle is the checker
+    here, never the thing measured."""
+    import torch
+    import torch.distributed as dist
+    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, overdensity_
+    N = 64
+    rng = np.random.default_rng(11)
+    pos = rng.random((2 * N ** 3, 3), dtype=np.float32) * np.float32(BOX)
+    k = len(pos) // 2
+    c = rng.random((8, 3), dtype=np.float32) * np.float32(BOX)
+    pos[:k] = (c[rng.integers(0, 8, k)] + rng.normal(0, BOX * 0.05, (k, 3)).astype(np.float32)) % np.float32(BOX)
+    W = rng.random(len(pos), dtype=np.float32)
+    out = {}
+    if world == 1:
+        g = torch.zeros((N, N, N), dtype=torch.float32, device=dev)
+        MASL.MA(torch.from_numpy(pos).to(dev), g, BOX, "PCS", torch.from_numpy(W).to(dev), mode="tiled")
+        got = g.cpu().numpy()
+        overdensity_(g)
+        pk = PKL.Pk(g, BOX, 0, "PCS", verbose=False)
+    else:
+        from pylians3_b200 import dist as PD
+        ctx = PD.SlabContext(N, BOX)
+        lo, hi = rank * len(pos) // world, (rank + 1) * len(pos) // world
+        slab = ctx.new_slab()
+        ctx.MA(torch.from_numpy(pos[lo:hi]).to(dev), slab, "PCS", W=torch.from_numpy(W[lo:hi]).to(dev))
+        ctx.check_dropped()
+        parts = [torch.empty((s, N, N), dtype=torch.float32, device=dev) for s in ctx.x_sizes]
+        dist.all_gather(parts, slab)
+        got = torch.cat(parts).cpu().numpy()
+        ctx.overdensity_(slab)
+        pk = ctx.Pk(slab, 0, "PCS")
+    if rank == 0:
+        from oracle import build as obuild
+        obuild.build()
+        from oracle import cpu as O
+        ref = np.zeros((N, N, N), np.float32)
+        O.MA(pos, ref, BOX, "PCS", W)
+        out["deposit_max_rel_err"] = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), ref.mean())))
+        d = (ref / np.mean(ref, dtype=np.float64) - 1.0).astype(np.float32)
+        rp = O.Pk(d, BOX, 0, "PCS", 1, False)
+        out["Pk0_max_rel_err"] = float(np.max(np.abs(pk.Pk[:, 0] / rp.Pk[:, 0] - 1.0)))
+        out["Nmodes_equal"] = bool(np.array_equal(pk.Nmodes3D, rp.Nmodes3D))
+        out["case"] = "%d^3 grid, %d clustered particles + W, PCS, %d rank(s), against oracle/" % (N, len(pos), world)
+    return out
+
+
+def run_ours(args, wl, grid_n):
     import torch
     import torch.distributed as dist
 
@@ -220,43 +327,52 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pyl_b200_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
-    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, _lib, overdensity_, synth
+    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, _device as D, _lib, overdensity_, synth
     lib = _lib.load()
-    grid_n = args.grid or GRID_FOR_GPUS.get(world, 512)
+    MAS, AXIS = wl["mas"], wl["axis"]
     npart = grid_n ** 3
+    parity = {}
+    try:
+        parity = small_parity_check(world, rank, dev)
+    except Exception as e:                                   # the check must never cost the measurement
+        parity = {"error": repr(e)[:200]}
+    D.release_workspaces()
+    torch.cuda.empty_cache()
 
+    pos, W = make_inputs(wl, grid_n, world, rank, dev)
+    ctx = None
     if world > 1:
         from pylians3_b200 import dist as PD
         ctx = PD.SlabContext(grid_n, BOX)
-        x0, x1 = ctx.x_range
-        cell = BOX / grid_n
-        n_local = npart // world
-        pos = synth.uniform_device(n_local, BOX, 1000 + rank, dev, x_range=(x0 * cell, x1 * cell))
         slab = ctx.new_slab()
 
-        def step(p):
+        def step(p, w):
             slab.zero_()
-            ctx.MA(p, slab, MAS, routed=True)
+            ctx.MA(p, slab, MAS, W=w, routed=False)
             ctx.overdensity_(slab)
             return ctx.Pk(slab, AXIS, MAS)
-        n_step_particles = n_local * world
     else:
-        pos = synth.uniform_device(npart, BOX, 1, dev)
         grid = torch.zeros((grid_n, grid_n, grid_n), dtype=torch.float32, device=dev)
 
-        def step(p):
+        def step(p, w):
             grid.zero_()
-            MASL.MA(p, grid, BOX, MAS)
+            MASL.MA(p, grid, BOX, MAS, w)
             overdensity_(grid)
             return PKL.Pk(grid, BOX, AXIS, MAS, verbose=False)
-        n_step_particles = npart
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, with_ma_events=False):
+    def max_over_ranks(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
         barrier()
@@ -266,20 +382,19 @@ def run_ours(args):
             fn()
         ev1.record()
         barrier()
-        ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps
+        return max_over_ranks([ev0.elapsed_time(ev1)])[0] / steps
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
 
     # ---- timed region 1: device-resident inputs --------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
-    n0 = lib.pyl_kernel_launches()
     pk_holder = {}
 
     def fn_dev():
-        pk_holder["pk"] = step(pos)
+        pk_holder["pk"] = step(pos, W)
 
     for _ in range(args.warmup):
         fn_dev()
@@ -289,35 +404,20 @@ def run_ours(args):
         sampler.start()
     ms_step = timed(fn_dev, args.steps, 0)
     clocks = sampler.stop() if sampler else None
-    gpu_launches = lib.pyl_kernel_launches() - launches0
-    value = n_step_particles / (ms_step * 1e-3)
+    gpu_launches = (lib.pyl_kernel_launches() - launches0) // max(args.steps, 1)
+    value = npart / (ms_step * 1e-3)
+    if world > 1:
+        ctx.check_dropped()
+    peak_hbm_gb = torch.cuda.max_memory_allocated() / 1e9
 
-    # ---- dominant kernel (the deposit) timed live with CUDA events -------------------------------
-    ma_ms = None
+    # ---- stage breakdown, CUDA events on the launching stream (outside the timed region) ---------------
+    reps = 3
+    stages = {}
     if world == 1:
-        evs = []
-        for _ in range(max(3, args.steps)):
-            grid.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            MASL.MA(pos, grid, BOX, MAS)
-            b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        ma_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-
-    # ---- stage breakdown and per-scheme deposit rates (outside the timed region) -----------------
-    stages, ma_rates = {}, {}
-    if world == 1:
-        def ev():
-            e = torch.cuda.Event(enable_timing=True)
-            e.record()
-            return e
-        reps = 3
         acc = {k: 0.0 for k in ("zero", "deposit", "overdensity", "fft", "bin+finalise+d2h")}
         for _ in range(reps):
             e0 = ev(); grid.zero_()
-            e1 = ev(); MASL.MA(pos, grid, BOX, MAS)
+            e1 = ev(); MASL.MA(pos, grid, BOX, MAS, W)
             e2 = ev(); overdensity_(grid)
             e3 = ev(); dk = PKL.fft3d_r2c_device(grid)
             e4 = ev(); PKL.spectra([dk], [PKL.MAS_function(MAS)], grid_n, AXIS, BOX, want_phase=True)
@@ -326,110 +426,153 @@ def run_ours(args):
                 acc[k] += a.elapsed_time(b) / reps
             del dk
         stages = {k: round(v, 4) for k, v in acc.items()}
-        # binning kernel alone (device time, no D2H)
         dk = PKL.fft3d_r2c_device(grid)
         a = ev()
         for _ in range(reps):
-            PKL.bin_device([dk], [2], grid_n, AXIS, True)
+            PKL.bin_device([dk], [PKL.MAS_function(MAS)], grid_n, AXIS, True)
         b = ev(); torch.cuda.synchronize()
         stages["bin_kernels_only"] = round(a.elapsed_time(b) / reps, 4)
         del dk
-        W = synth.weights_device(npart, 1, dev)
-        for mode in ("auto", "atomic"):
-            for mas in ("NGP", "CIC", "TSC", "PCS"):
-                for w, tag in ((None, ""), (W, "+W")):
-                    if mode == "atomic" and w is not None:
-                        continue
-                    MASL.MA(pos, grid, BOX, mas, w, mode=mode)
-                    a = ev()
-                    for _ in range(reps):
-                        MASL.MA(pos, grid, BOX, mas, w, mode=mode)
-                    b = ev(); torch.cuda.synchronize()
-                    ma_rates[mas + tag + ("" if mode == "auto" else "[atomic]")] = npart / (a.elapsed_time(b) / reps * 1e-3)
-        del W
-
-    if world > 1:
-        # stage breakdown of the distributed step (device time on this rank, max over ranks)
-        def ev():
-            e = torch.cuda.Event(enable_timing=True)
-            e.record()
-            return e
-        reps = 3
-        acc = {k: 0.0 for k in ("zero", "deposit+halo", "overdensity", "fft(yz,transpose,x)", "bin+allreduce+finalise+d2h")}
+    else:
+        names = ("zero", "route", "deposit+halo", "overdensity", "fft_yz", "transpose", "fft_x",
+                 "bin+allreduce+finalise+d2h")
+        acc = {k: 0.0 for k in names}
         for _ in range(reps):
             barrier()                      # ranks start each repetition together: no inter-rank skew in the stage times
             e0 = ev(); slab.zero_()
-            e1 = ev(); ctx.MA(pos, slab, MAS, routed=True)
-            e2 = ev(); ctx.overdensity_(slab)
-            e3 = ev(); dk = ctx.fft(slab)
-            e4 = ev(); ctx._spectra([dk], [PKL.MAS_function(MAS)], AXIS, True)
-            e5 = ev(); torch.cuda.synchronize()
-            for k, (a, b) in zip(acc, ((e0, e1), (e1, e2), (e2, e3), (e3, e4), (e4, e5))):
-                acc[k] += a.elapsed_time(b) / reps
-            del dk
-        t = torch.tensor(list(acc.values()), dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        stages = {k: round(float(v), 4) for k, v in zip(acc, t.tolist())}
+            e1 = ev(); p_r, w_r = ctx.route(pos, MAS, W)
+            e2 = ev(); ctx.MA(p_r, slab, MAS, W=w_r, routed=True)
+            e3 = ev(); ctx.overdensity_(slab)
+            e4 = ev(); marks = []
+            dk = ctx.fft(slab, marks=marks)
+            e5 = ev(); ctx._spectra([dk], [PKL.MAS_function(MAS)], AXIS, True)
+            e6 = ev(); torch.cuda.synchronize()
+            pairs = {"zero": (e0, e1), "route": (e1, e2), "deposit+halo": (e2, e3), "overdensity": (e3, e4),
+                     "bin+allreduce+finalise+d2h": (e5, e6)}
+            if len(marks) == 2:
+                pairs.update({"fft_yz": (e4, marks[0]), "transpose": (marks[0], marks[1]), "fft_x": (marks[1], e5)})
+            else:
+                pairs["fft_yz"] = (e4, e5)
+            for k, (x, y) in pairs.items():
+                acc[k] += x.elapsed_time(y) / reps
+            del dk, p_r, w_r
+        stages = {k: round(v, 4) for k, v in zip(acc, max_over_ranks(acc.values()))}
 
     # ---- timed region 2: end to end from pinned host memory --------------------------------------
     pos_host = torch.empty(pos.shape, dtype=torch.float32, pin_memory=True)
     pos_host.copy_(pos)
+    W_host = None
+    if W is not None:
+        W_host = torch.empty(W.shape, dtype=torch.float32, pin_memory=True)
+        W_host.copy_(W)
     torch.cuda.synchronize()
-    h2d = pos_host.numel() * 4
+    h2d = pos_host.numel() * 4 + (W_host.numel() * 4 if W_host is not None else 0)
     d2h = _lib.pk_layout(grid_n, 1).total_words * 8
-    del pos
+    n_local = pos.shape[0]
+    del pos, W
     torch.cuda.empty_cache()
 
     def fn_e2e():
-        pk_holder["pk"] = step(pos_host)
+        pk_holder["pk"] = step(pos_host, W_host)
 
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 3))
     ms_e2e = timed(fn_e2e, e2e_steps, 1)
-    e2e_value = n_step_particles / (ms_e2e * 1e-3)
+    e2e_value = npart / (ms_e2e * 1e-3)
+    h2d_total = int(max_over_ranks([h2d])[0]) * world if world > 1 else h2d
+
+    # ---- config 2's four schemes as MA rates (1 GPU, 512^3 uniform particles -> 512^3 grid) ----------------
+    ma_rates = {}
+    if world == 1 and not args.no_ma_rates:
+        del pos_host, W_host
+        if grid_n != 512:
+            del grid
+            D.release_workspaces()
+            torch.cuda.empty_cache()
+            grid = torch.zeros((512, 512, 512), dtype=torch.float32, device=dev)
+        p2 = synth.uniform_device(512 ** 3, BOX, 1, dev)
+        w2 = synth.weights_device(512 ** 3, 1, dev)
+        for mode in ("auto", "atomic"):
+            for mas in ("NGP", "CIC", "TSC", "PCS"):
+                for w, tag in ((None, ""), (w2, "+W")):
+                    if mode == "atomic" and (w is not None or mas in ("TSC", "PCS")):
+                        continue
+                    MASL.MA(p2, grid, BOX, mas, w, mode=mode)
+                    a = ev()
+                    for _ in range(reps):
+                        MASL.MA(p2, grid, BOX, mas, w, mode=mode)
+                    b = ev(); torch.cuda.synchronize()
+                    ma_rates[mas + tag + ("" if mode == "auto" else "[atomic]")] = \
+                        512 ** 3 / (a.elapsed_time(b) / reps * 1e-3)
+        ma_rates["workload"] = "BASELINE config 2 deposits: 512^3 uniform particles -> 512^3 grid, particles/s per MA call"
+        del p2, w2
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
+    # ---- rooflines (algorithmic bytes of SURVEY section 8d over CUDA-event times) ---------------------------
     peak, peak_src = measured_peak_hbm()
-    roofline = None
-    if ma_ms is not None:
-        alg_bytes = npart * 12 + 8 * grid_n ** 3          # positions once + grid RMW once
-        achieved = alg_bytes / (ma_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "deposit (%s, %s)" % (MAS, "pyl_deposit"), "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": NCU_DEPOSIT_TRAFFIC.get((MAS, grid_n)),
-                    "traffic_source": "profiles/r1_tiled_deposit_cic_final.md (ncu --set full, per MA call)",
-                    "kernels": "tile_count + tile_scatter + tile_deposit (one pyl_deposit call)",
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                    "avg_launch_ms": ma_ms, "share_of_step": ma_ms / ms_step}
-    if roofline is None and world > 1:
-        # per-GPU deposit roofline of the sharded step, from the stage breakdown (max over ranks; the stage
-        # includes the ghost-plane exchange).  Guarded: a missing stage leaves the key null, never breaks the line.
-        try:
-            dep_ms = float(stages["deposit+halo"])
-            alg_bytes = (npart * 12 + 8 * grid_n ** 3) / world
-            achieved = alg_bytes / (dep_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": "deposit + halo exchange, per GPU (%s, pyl_deposit_slab)" % MAS,
-                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dep_ms,
-                        "share_of_step": dep_ms / ms_step}
-        except Exception:
-            roofline = None
+    bpp = 16 if wl["weighted"] else 12
+    half = grid_n * grid_n * (grid_n // 2 + 1)
+
+    def roof(name, alg_bytes, ms, **extra):
+        ach = alg_bytes / (ms * 1e-3) / 1e9
+        r = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms, "share_of_step": ms / ms_step,
+             "peak_source": peak_src}
+        r.update(extra)
+        return r
+
+    rooflines = {}
+    if world == 1:
+        traffic, tsrc = ncu_traffic("%s%s_%d" % (MAS, "W" if wl["weighted"] else "", grid_n))
+        rooflines["deposit"] = roof("deposit: pyl_deposit = tile_count + partition<1> + partition<2> + tile_deposit (%s%s)"
+                                    % (MAS, "+W" if wl["weighted"] else ""), npart * bpp + 8 * grid_n ** 3,
+                                    stages["deposit"], traffic=traffic, traffic_source=tsrc)
+        rooflines["fft"] = roof("r2c FFT (cuFFT), lower bound 4N^3 + 8N^2(N/2+1)", 4 * grid_n ** 3 + 8 * half,
+                                stages["fft"], traffic=None)
+        rooflines["bin"] = roof("pk_bin_walk_kernel + fold (device time, no D2H)", 8 * half,
+                                stages["bin_kernels_only"], traffic=None)
+        rooflines["step"] = roof("whole step: deposit + delta RMW + FFT + bin",
+                                 npart * bpp + 8 * grid_n ** 3 + 8 * grid_n ** 3 + 4 * grid_n ** 3 + 8 * half + 8 * half,
+                                 ms_step, traffic=None)
+    else:
+        per = 1.0 / world
+        rooflines["deposit"] = roof("deposit + halo exchange, per GPU (%s, pyl_deposit_slab)" % MAS,
+                                    (npart * bpp + 8 * grid_n ** 3) * per, stages["deposit+halo"], traffic=None)
+        if stages.get("transpose"):
+            sent = 8 * half * per * (world - 1) / world
+            ach = sent / (stages["transpose"] * 1e-3) / 1e9
+            rooflines["transpose"] = {"bound": "nvlink", "kernel": "transpose_scatter_kernel (peer stores over NVLink)",
+                                      "achieved": ach, "peak": 770.0, "unit": "GB/s", "frac": ach / 770.0,
+                                      "peak_source": "measured peer copy per direction (B200_PROFILING.md; 900 nominal)",
+                                      "algorithmic_bytes_per_launch": sent, "avg_launch_ms": stages["transpose"],
+                                      "share_of_step": stages["transpose"] / ms_step, "traffic": None}
+        rooflines["bin"] = roof("pk_bin (mirrored slab) + all-reduce + finalise + d2h, per GPU", 8 * half * per,
+                                stages["bin+allreduce+finalise+d2h"], traffic=None)
+    roofline = dict(rooflines["deposit"])
+
     pk = pk_holder["pk"]
-    line = {"metric": metric_name(grid_n), "value": value, "unit": "particles/s", "n_gpus": world,
+    m = grid_n // 2
+    check = {"modes_counted": int(pk.Nmodes3D.sum()) + 1, "modes_expected": (grid_n ** 3 - 8) // 2 + 8,
+             "n2d_bins": int(pk.Pk2D.shape[0]), "n2d_expected": (m + 1) * (int(np.sqrt(2.0 * m * m)) + 1),
+             "Pk0_finite": bool(np.all(np.isfinite(pk.Pk[:, 0]))), "small_case_vs_oracle": parity}
+    if wl["particles"] == "uniform" and not wl["weighted"]:
+        check["Pk0_mean_over_shot_noise"] = float(np.mean(pk.Pk[10:200, 0]) / (BOX ** 3 / npart))
+    line = {"metric": METRIC, "value": value, "unit": "particles/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(grid_n, world),
-            "e2e": {"value": e2e_value, "unit": "particles/s", "h2d_bytes_per_step": h2d * world,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps},
-            "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline,
-            "stages_ms": stages, "ma_particles_per_s": ma_rates,
-            "check": {"Pk0_mean_over_shot_noise": float(np.mean(pk.Pk[10:200, 0]) / (BOX ** 3 / npart)),
-                      "modes_counted": int(pk.Nmodes3D.sum()) + 1}}
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(wl, grid_n, world),
+            "e2e": {"value": e2e_value, "unit": "particles/s", "h2d_bytes_per_step": h2d_total,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps,
+                    "h2d_GBps_per_gpu": h2d / (ms_e2e * 1e-3) / 1e9,
+                    "note": "upper bound per GPU = PCIe gen5 x16, ~55 GB/s: the copy, not the kernels, bounds e2e"},
+            "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
+            "stages_ms": stages, "ma_particles_per_s": ma_rates, "check": check,
+            "hbm_peak_allocated_GB_rank0": peak_hbm_gb, "particles_rank0": int(n_local)}
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline()
+        line["cpu_baseline"] = cpu_baseline(wl)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -438,18 +581,23 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--grid", type=int, default=0, help="override the grid side (default: by --gpus)")
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--grid", type=int, default=0, help="override the grid side / particle lattice side")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ma-rates", action="store_true", help="skip the config-2 per-scheme deposit rates")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    wl = WORKLOADS[args.workload]
+    grid = args.grid or wl["grid"]
+    WORKLOADS_GRID[0] = grid
     claim_stdout()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, wl, grid)
     else:
-        run_ours(args)
+        run_ours(args, wl, grid)
 
 
 if __name__ == "__main__":

@@ -213,6 +213,11 @@ int pyl_pk_bin(const float *const *delta_k, int fields, const int *mas_index, in
                int ky_lo, int nky, int axis, int want_phase, void *out, void *ws,
                size_t ws_bytes, pyl_stream_t stream);
 
+/* Slab-distributed spectra (no reference counterpart: the reference is one process): converts the
+ * uint64 mode counts of an accumulator block (layout of pyl_pk_layout) to float64 in place -- exact below 2^53 -- so
+ * that a single float64 SUM all-reduce covers the whole block; follow with pyl_pk_finalize(counts_are_f64 = 1). */
+int pyl_pk_counts_to_f64(void *acc, int dims, int fields, pyl_stream_t stream);
+
 /* Finalisation of the accumulators IN PLACE (Pk_library.pyx:384-418 / :735-791): afterwards every word of `acc`
  * is the float64 value the reference stores for that slot -- k3D = <k> kF, Pk3D = P_l (2l+1)/Nmodes (BoxSize/
  * dims^2)^3, phase likewise, Pk1D with its perpendicular-area weight, Pk2D = P/Nmodes2D * units; counts are

@@ -55,6 +55,15 @@ STREAM_CHUNK = 16 * 1024 * 1024          # particles per chunk (192 MB of positi
 _copy_streams = {}
 
 
+def stream_chunk(dims, coord=3):
+    """Particles per streamed chunk: every chunk is a complete tiled deposit, which adds each 8x16x32-cell tile
+    (+ halo) to the grid once, so a chunk should bring a few hundred particles per tile (1024^3: 8 chunks of 134 M)."""
+    if coord != 3:
+        return STREAM_CHUNK
+    tiles = ((dims + 7) // 8) * ((dims + 15) // 16) * ((dims + 31) // 32)
+    return max(STREAM_CHUNK, 512 * tiles)
+
+
 def _host_f32(x, name):
     """numpy array / CPU tensor -> contiguous float32 CPU tensor sharing memory when possible."""
     if isinstance(x, torch.Tensor):
@@ -125,8 +134,9 @@ def MA(pos, number, BoxSize, MAS="CIC", W=None, verbose=False, renormalize_2D=Tr
     if any(s != dims for s in number.shape):
         raise ValueError("number must be a (dims,)*%d grid, got %s" % (coord, tuple(number.shape)))
     dev = D.pick_device(number, pos, W)
+    chunk = stream_chunk(dims, coord)
     streamed = (not D.is_cuda_tensor(pos)) and (W is None or not D.is_cuda_tensor(W)) and \
-        pos.shape[0] >= 2 * STREAM_CHUNK
+        pos.shape[0] >= 2 * chunk
     pos_d = W_d = None
     if streamed:
         pos_h = _host_f32(pos, "pos")
@@ -150,8 +160,7 @@ def MA(pos, number, BoxSize, MAS="CIC", W=None, verbose=False, renormalize_2D=Tr
 
     if streamed:
         with torch.cuda.device(dev):
-            _deposit_streamed(L.MAS_IDS[MAS], pos_h, number_d, W_h, dims, coord, BoxSize, L.MODE_IDS[mode],
-                              STREAM_CHUNK)
+            _deposit_streamed(L.MAS_IDS[MAS], pos_h, number_d, W_h, dims, coord, BoxSize, L.MODE_IDS[mode], chunk)
     else:
         _deposit_device(L.MAS_IDS[MAS], pos_d, number_d, W_d, dims, coord, BoxSize, L.MODE_IDS[mode])
     if coord == 2 and renormalize_2D and MAS != "NGP":

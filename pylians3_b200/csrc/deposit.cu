@@ -101,6 +101,13 @@ int pyl_deposit_slab(int mas, const float *pos, float *number, const float *W,
     PYL_REQUIRE(particles >= 0 && BoxSize > 0.0f, "pyl_deposit_slab: bad particles/BoxSize");
     if (particles == 0) return PYL_OK;
     PYL_REQUIRE(pos != nullptr && number != nullptr, "pyl_deposit_slab: NULL pos/number");
+    if (x_origin == 0 && x_own == dims && x_planes == dims) {
+        // a one-rank "slab": the window is the whole periodic grid
+        const size_t whole = pyl_deposit_workspace_bytes(mas, particles, dims, 3, PYL_MODE_TILED);
+        if (whole > 0 && ws != nullptr && ws_bytes >= whole)
+            return deposit_tiled(mas, pos, number, W, particles, dims, BoxSize, 0, -1, -1, dropped, ws,
+                                 as_stream(stream));
+    }
     const size_t need = pyl_deposit_slab_workspace_bytes(mas, particles, dims, x_own);
     if (need > 0 && ws != nullptr && ws_bytes >= need && x_planes < dims)
         return deposit_tiled(mas, pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dropped,

@@ -77,24 +77,33 @@ struct TileGeom {
 
 constexpr unsigned NO_TILE = 0xffffffffu;
 
+// periodic wrap for the partition kernels: branch-free single fold (inputs inside the documented domain
+// 0 <= pos <= BoxSize need no more); anything still outside is sent through the true modulo
+__device__ __forceinline__ int wrap_once(int i, int dims) {
+    i += i < 0 ? dims : 0;
+    i -= i >= dims ? dims : 0;
+    return i;
+}
+
 template <int MAS>
 __device__ __forceinline__ unsigned tile_and_local(const float d[3], const TileGeom &g, int local[3]) {
-    int t[3];
-    const int T[3] = {TX, TY, TZ};
-    bool mine = true;
+    static_assert(TX == 8 && TY == 16 && TZ == 32, "shifts below");
+    int wb[3];
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-        const int b = axis_base<MAS>(d[a]);
-        int wb = wrap_index(b, g.dims);
-        if (a == 0) {                       // plane index inside the destination window
-            wb -= g.x_origin;
-            if (wb < 0) wb += g.dims;
-            mine = wb < g.x_own;
-        }
-        t[a] = wb / T[a];
-        local[a] = wb - t[a] * T[a];
+    for (int a = 0; a < 3; a++) wb[a] = wrap_once(axis_base<MAS>(d[a]), g.dims);
+    if (__builtin_expect(((unsigned)wb[0] >= (unsigned)g.dims) | ((unsigned)wb[1] >= (unsigned)g.dims) |
+                         ((unsigned)wb[2] >= (unsigned)g.dims), 0)) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) wb[a] = wrap_index_slow(wb[a], g.dims);
     }
-    return mine ? ((unsigned)t[0] * g.nty + t[1]) * g.ntz + t[2] : NO_TILE;
+    wb[0] -= g.x_origin;                // plane index inside the destination window
+    wb[0] += wb[0] < 0 ? g.dims : 0;
+    const bool mine = wb[0] < g.x_own;
+    const unsigned t0 = (unsigned)wb[0] >> 3, t1 = (unsigned)wb[1] >> 4, t2 = (unsigned)wb[2] >> 5;
+    local[0] = wb[0] & (TX - 1);
+    local[1] = wb[1] & (TY - 1);
+    local[2] = wb[2] & (TZ - 1);
+    return mine ? (t0 * g.nty + t1) * g.ntz + t2 : NO_TILE;
 }
 
 // ---- 1. sampled histogram --------------------------------------------------------------------------
@@ -265,31 +274,33 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         n_in = (int)min((int64_t)PP, a.particles - first);
         repl = blockIdx.x % g.repl;
     } else {
-        if (tid == 0) {
+        if (warp == 0) {
             // CTAs that run at the same time (neighbouring blockIdx) take chunks of DIFFERENT super-tiles: the
             // chunks of one super-tile all reserve runs on the same few hundred bucket cursors, and same-address
             // atomics serialise (the straight order made this pass as slow as its atomics)
             const unsigned rows = gridDim.x / g.nsuper;
             const unsigned b = (blockIdx.x % g.nsuper) * rows + blockIdx.x / g.nsuper;
-            unsigned lo = 0, hi = g.nsuper;                    // largest s with repl*spre[s] <= b
+            // largest s with repl*spre[s] <= b: spre is non-decreasing, so it is (number of such s) - 1; the lanes
+            // count in parallel (a binary search by one thread was ~10 dependent L2 round trips per CTA)
+            unsigned below = 0;
+            for (unsigned s = lane; s < g.nsuper; s += 32) below += (__ldg(a.spre + s) * g.repl <= b) ? 1u : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
             const unsigned total = __ldg(a.spre + g.nsuper) * g.repl;
-            unsigned ok = b < total;
-            if (ok) {
-                while (hi - lo > 1) {
-                    const unsigned mid = (lo + hi) >> 1;
-                    if (__ldg(a.spre + mid) * g.repl <= b) lo = mid; else hi = mid;
-                }
-                const unsigned nch = __ldg(a.spre + lo + 1) - __ldg(a.spre + lo);
-                const unsigned rem = b - __ldg(a.spre + lo) * g.repl;
-                const unsigned r = rem / nch, c = rem - r * nch;
-                const Segment sg = super_segment(a.starts, g, lo, r);
-                const unsigned fill = min(a.cur1[r * g.nsuper + lo], sg.begin + sg.cap);
-                const unsigned b0 = sg.begin + c * PP;
-                misc[16] = lo;
-                misc[17] = b0;
-                misc[18] = b0 < fill ? min((unsigned)PP, fill - b0) : 0u;
-            } else {
+            if (lane == 0) {
                 misc[18] = 0u;
+                if (b < total) {
+                    const unsigned lo = below - 1u;
+                    const unsigned nch = __ldg(a.spre + lo + 1) - __ldg(a.spre + lo);
+                    const unsigned rem = b - __ldg(a.spre + lo) * g.repl;
+                    const unsigned r = rem / nch, c = rem - r * nch;
+                    const Segment sg = super_segment(a.starts, g, lo, r);
+                    const unsigned fill = min(a.cur1[r * g.nsuper + lo], sg.begin + sg.cap);
+                    const unsigned b0 = sg.begin + c * PP;
+                    misc[16] = lo;
+                    misc[17] = b0;
+                    misc[18] = b0 < fill ? min((unsigned)PP, fill - b0) : 0u;
+                }
             }
         }
         __syncthreads();
@@ -524,17 +535,11 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
         const float4 v = nxt;
         if (i + TNT < end) nxt = __ldg(bucket + i + TNT);
         const float dd[3] = {v.x, v.y, v.z};
-        const int org[3] = {ox, oy, oz};
         int lc[3];
         float w[3][S];
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int b = axis_base<MAS>(dd[k]);
-            axis_weights<MAS>(dd[k], b, w[k]);
-            int wb = wrap_index(b, g.dims);
-            if (k == 0) { wb -= g.x_origin; if (wb < 0) wb += g.dims; }
-            lc[k] = wb - org[k];
-        }
+        for (int k = 0; k < 3; k++) axis_weights<MAS>(dd[k], axis_base<MAS>(dd[k]), w[k]);
+        tile_and_local<MAS>(dd, g, lc);
         const float ws = WEIGHTED ? v.w * scale : scale;
 #pragma unroll
         for (int l = 0; l < S; l++) w[0][l] *= ws;

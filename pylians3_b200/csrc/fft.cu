@@ -20,7 +20,11 @@ struct Plan {
     size_t work = 0;
 };
 
-using PlanKey = std::tuple<int, int, int, int>;   // device, kind, dims, extent (nx or nky)
+using PlanKey = std::tuple<int, int, int, int, int>;   // device, kind, dims, batch, nky (x plans: row stride)
+// slab transforms run in batches so that cuFFT's work area (which grows with the batch) stays bounded at
+// 4096^3-class grids: at most this many (y,z) planes / x columns per cufftExec call
+constexpr int YZ_BATCH = 16;
+constexpr int X_BATCH = 1 << 16;
 static std::map<PlanKey, Plan> g_plans;
 static std::mutex g_plans_mu;
 
@@ -52,10 +56,10 @@ static const char *cufft_name(cufftResult r) {
         }                                                                                 \
     } while (0)
 
-static int get_plan(PlanKind kind, int dims, int extent, Plan *out) {
+static int get_plan(PlanKind kind, int dims, int extent, Plan *out, int nky = 0) {
     int dev = 0;
     PYL_CUDA_CHECK(cudaGetDevice(&dev));
-    const PlanKey key(dev, (int)kind, dims, extent);
+    const PlanKey key(dev, (int)kind, dims, extent, nky);
     std::lock_guard<std::mutex> lock(g_plans_mu);
     auto it = g_plans.find(key);
     if (it != g_plans.end()) { *out = it->second; return PYL_OK; }
@@ -81,12 +85,12 @@ static int get_plan(PlanKind kind, int dims, int extent, Plan *out) {
             r = cufftMakePlanMany64(p.handle, 2, n, nullptr, 1, N * N, nullptr, 1, N * nz, CUFFT_R2C,
                                     (long long)extent, &p.work);
         } else {
-            // in-place 1D transforms along x of a (N, nky, nz) array: element stride nky*nz
+            // in-place 1D transforms along x of a (N, nky, nz) array: element stride nky*nz, `extent` columns
             long long n[1] = {N};
             long long embed[1] = {N};
-            const long long stride = (long long)extent * nz;
+            const long long stride = (long long)nky * nz;
             r = cufftMakePlanMany64(p.handle, 1, n, embed, stride, 1, embed, stride, 1, CUFFT_C2C,
-                                    stride, &p.work);
+                                    (long long)extent, &p.work);
         }
     }
     if (r != CUFFT_SUCCESS) {
@@ -183,12 +187,23 @@ size_t pyl_fft_slab_workspace_bytes(int dims, int nx, int nky) {
     size_t need = 0;
     Plan p;
     if (nx > 0) {
-        if (get_plan(PLAN_R2C_YZ, dims, nx, &p) != PYL_OK) return (size_t)-1;
+        const int full = nx < YZ_BATCH ? nx : YZ_BATCH, rest = nx % full;
+        if (get_plan(PLAN_R2C_YZ, dims, full, &p) != PYL_OK) return (size_t)-1;
         need = p.work;
+        if (rest > 0) {
+            if (get_plan(PLAN_R2C_YZ, dims, rest, &p) != PYL_OK) return (size_t)-1;
+            if (p.work > need) need = p.work;
+        }
     }
     if (nky > 0) {
-        if (get_plan(PLAN_C2C_X, dims, nky, &p) != PYL_OK) return (size_t)-1;
+        const long long cols = (long long)nky * (dims / 2 + 1);
+        const int full = cols < X_BATCH ? (int)cols : X_BATCH, rest = (int)(cols % full);
+        if (get_plan(PLAN_C2C_X, dims, full, &p, nky) != PYL_OK) return (size_t)-1;
         if (p.work > need) need = p.work;
+        if (rest > 0) {
+            if (get_plan(PLAN_C2C_X, dims, rest, &p, nky) != PYL_OK) return (size_t)-1;
+            if (p.work > need) need = p.work;
+        }
     }
     return need;
 }
@@ -198,13 +213,17 @@ int pyl_fft_slab_yz(const float *slab, float *slab_k, int dims, int nx, void *ws
     PYL_REQUIRE(dims > 0 && nx >= 0, "pyl_fft_slab_yz: bad sizes");
     if (nx == 0) return PYL_OK;
     PYL_REQUIRE(slab != nullptr && slab_k != nullptr, "pyl_fft_slab_yz: NULL pointer");
-    Plan p;
-    int st = get_plan(PLAN_R2C_YZ, dims, nx, &p);
-    if (st != PYL_OK) return st;
-    st = bind(p, ws, ws_bytes, as_stream(stream));
-    if (st != PYL_OK) return st;
-    PYL_CUFFT_CHECK(cufftExecR2C(p.handle, const_cast<cufftReal *>(slab),
-                                 reinterpret_cast<cufftComplex *>(slab_k)));
+    const long long plane_in = (long long)dims * dims, plane_out = (long long)dims * (dims / 2 + 1);
+    for (int x = 0; x < nx; x += YZ_BATCH) {
+        const int b = nx - x < YZ_BATCH ? nx - x : YZ_BATCH;
+        Plan p;
+        int st = get_plan(PLAN_R2C_YZ, dims, b, &p);
+        if (st != PYL_OK) return st;
+        st = bind(p, ws, ws_bytes, as_stream(stream));
+        if (st != PYL_OK) return st;
+        PYL_CUFFT_CHECK(cufftExecR2C(p.handle, const_cast<cufftReal *>(slab) + x * plane_in,
+                                     reinterpret_cast<cufftComplex *>(slab_k) + x * plane_out));
+    }
     return PYL_OK;
 }
 
@@ -213,13 +232,17 @@ int pyl_fft_slab_x(float *cols_k, int dims, int nky, void *ws, size_t ws_bytes,
     PYL_REQUIRE(dims > 0 && nky >= 0, "pyl_fft_slab_x: bad sizes");
     if (nky == 0) return PYL_OK;
     PYL_REQUIRE(cols_k != nullptr, "pyl_fft_slab_x: NULL pointer");
-    Plan p;
-    int st = get_plan(PLAN_C2C_X, dims, nky, &p);
-    if (st != PYL_OK) return st;
-    st = bind(p, ws, ws_bytes, as_stream(stream));
-    if (st != PYL_OK) return st;
+    const long long cols = (long long)nky * (dims / 2 + 1);
     cufftComplex *c = reinterpret_cast<cufftComplex *>(cols_k);
-    PYL_CUFFT_CHECK(cufftExecC2C(p.handle, c, c, CUFFT_FORWARD));
+    for (long long j = 0; j < cols; j += X_BATCH) {
+        const int b = cols - j < X_BATCH ? (int)(cols - j) : X_BATCH;
+        Plan p;
+        int st = get_plan(PLAN_C2C_X, dims, b, &p, nky);
+        if (st != PYL_OK) return st;
+        st = bind(p, ws, ws_bytes, as_stream(stream));
+        if (st != PYL_OK) return st;
+        PYL_CUFFT_CHECK(cufftExecC2C(p.handle, c + j, c + j, CUFFT_FORWARD));
+    }
     return PYL_OK;
 }
 

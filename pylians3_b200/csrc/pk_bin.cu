@@ -388,6 +388,18 @@ __global__ void pk_fold_replicas_kernel(unsigned long long *out, const unsigned 
     }
 }
 
+// uint64 counts -> float64 in place (exact below 2^53): lets ONE float64 sum all-reduce cover the whole accumulator
+// block of a slab-distributed spectrum
+__global__ void pk_counts_to_f64_kernel(unsigned long long *acc, long long c0, long long n0, long long c1, long long n1,
+                                        long long c2, long long n2) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long w = -1;
+    if (t < n0) w = c0 + t;
+    else if (t < n0 + n1) w = c1 + (t - n0);
+    else if (t < n0 + n1 + n2) w = c2 + (t - n0 - n1);
+    if (w >= 0) acc[w] = (unsigned long long)__double_as_longlong((double)acc[w]);
+}
+
 // ---- finalisation on the device (Pk_library.pyx:384-418 / :735-791): units, averages, (2l+1) factors ----------
 // In place on the accumulator buffer: every word becomes the float64 value the reference stores in the same
 // slot (counts become float64 too; the DC bins keep their slots and are dropped by the caller).  One thread per
@@ -601,6 +613,19 @@ int pyl_pk_layout(int dims, int fields, pyl_pk_layout_t *layout) {
     PYL_REQUIRE(layout != nullptr, "pyl_pk_layout: layout is NULL");
     PYL_REQUIRE(dims > 0 && fields >= 1, "pyl_pk_layout: bad dims/fields");
     fill_layout(dims, fields, layout);
+    return PYL_OK;
+}
+
+int pyl_pk_counts_to_f64(void *acc, int dims, int fields, pyl_stream_t stream) {
+    PYL_REQUIRE(acc != nullptr, "pyl_pk_counts_to_f64: NULL buffer");
+    PYL_REQUIRE(dims > 0 && fields >= 1, "pyl_pk_counts_to_f64: bad dims/fields");
+    pyl_pk_layout_t L;
+    fill_layout(dims, fields, &L);
+    const long long n0 = L.kmax + 1, n1 = L.kmax_par + 1, n2 = L.n2d;
+    const long long n = n0 + n1 + n2;
+    pk_counts_to_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<unsigned long long *>(acc), L.Nm3D, n0, L.Nm1D, n1, L.Nm2D, n2);
+    PYL_LAUNCH_CHECK();
     return PYL_OK;
 }
 

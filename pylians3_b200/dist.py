@@ -99,9 +99,11 @@ class DeviceOps:
         L.check(self.lib.pyl_overdensity_inplace(D.ptr(x), x.numel(), D.ptr(total), float(cells), self._s()),
                 "pyl_overdensity_inplace")
 
-    def fft_yz(self, slab, dims):
+    def fft_yz(self, slab, dims, out=None):
+        """Batched 2D r2c over (y,z) of the planes of `slab`; `out` (nx, dims, nz) complex64 or a fresh tensor."""
         nx = slab.shape[0]
-        out = torch.empty((nx, dims, dims // 2 + 1), dtype=torch.complex64, device=slab.device)
+        if out is None:
+            out = torch.empty((nx, dims, dims // 2 + 1), dtype=torch.complex64, device=slab.device)
         need = self.lib.pyl_fft_slab_workspace_bytes(dims, nx, 0)
         if need == ctypes.c_size_t(-1).value:
             L.check(-3, "pyl_fft_slab_workspace_bytes")
@@ -208,6 +210,11 @@ class SlabContext:
             s = self._peer_slots[slot] = (buf, hdl, [int(p) for p in hdl.buffer_ptrs])
         return s
 
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def _buf(self, name, shape, dtype):
         """Persistent scratch buffer per (name, shape, dtype): the multi-GB work/transpose buffers are
         allocated once per context instead of once per step (allocator churn showed up as several ms of
@@ -221,8 +228,26 @@ class SlabContext:
         return b
 
     # ---- helpers ----------------------------------------------------------------------------------
+    FFT_BATCH_PLANES = 16       # x-planes per 2D-FFT / transpose batch of the pipelined slab FFT
+    GHOST_PLANES = 3            # PCS: the stencil reaches three planes above the particle's first plane
+
     def new_slab(self):
-        return torch.zeros((self.nx, self.dims, self.dims), dtype=torch.float32, device=self.device)
+        """(nx_local, dims, dims) float32 zeros.  The allocation carries GHOST_PLANES more planes behind the slab:
+        MA deposits straight into [own planes | ghost planes] and ships the ghost planes to the next rank, so no
+        slab-sized work buffer exists (at 4096^3 over 8 GPUs a slab is 34 GB)."""
+        store = torch.zeros((self.nx + self.GHOST_PLANES, self.dims, self.dims), dtype=torch.float32,
+                            device=self.device)
+        return store[:self.nx]
+
+    def _with_ghosts(self, slab, ghosts):
+        """The (nx + ghosts, dims, dims) view over a slab made by new_slab(), or None for foreign tensors."""
+        if slab.device.type != "cuda" or not slab.is_contiguous() or slab.storage_offset() != 0:
+            return None
+        n2 = self.dims * self.dims
+        if slab.untyped_storage().nbytes() < (self.nx + ghosts) * n2 * 4:
+            return None
+        return torch.empty(0, dtype=torch.float32, device=slab.device).set_(
+            slab.untyped_storage(), 0, (self.nx + ghosts, self.dims, self.dims), (n2, self.dims, 1))
 
     def plane_owner(self):
         if self._plane_owner is None:
@@ -271,10 +296,12 @@ class SlabContext:
         ghosts = _S[MAS] - 1
         x0 = self.x_range[0]
 
+        chunk = MASL.stream_chunk(self.dims) // self.world
+
         def deposit(target):
-            if host and pos.shape[0] >= 2 * MASL.STREAM_CHUNK:
+            if host and pos.shape[0] >= 2 * chunk:
                 # routed particles still in (pinned) host memory: stream them, one slab deposit per chunk
-                MASL.stream_host_chunks(pos, W, self.device, MASL.STREAM_CHUNK,
+                MASL.stream_host_chunks(pos, W, self.device, chunk,
                                         lambda p, w: self.ops.deposit_slab(MAS, p, target, w, self.dims, self.BoxSize,
                                                                            x0, self.nx, self.dropped))
             elif host:
@@ -284,22 +311,26 @@ class SlabContext:
             else:
                 self.ops.deposit_slab(MAS, pos, target, W, self.dims, self.BoxSize, x0, self.nx, self.dropped)
 
-        if ghosts == 0:
+        if ghosts == 0 or self.world == 1:
+            # one rank: the window is the whole periodic grid (x_own = x_planes = dims), nothing to exchange
             deposit(slab)
             return
-        work = self._buf("work", (self.nx + ghosts, self.dims, self.dims), torch.float32)
-        work.zero_()
+        work = self._with_ghosts(slab, ghosts)
+        own_slab = work is not None
+        if own_slab:
+            work[self.nx:].zero_()                       # the ghost planes behind the slab
+        else:                                            # a slab not made by new_slab(): side buffer, then add
+            work = self._buf("work", (self.nx + ghosts, self.dims, self.dims), torch.float32)
+            work.zero_()
         deposit(work)
         halo_out = work[self.nx:]                        # planes x1 .. x1+ghosts-1 belong to the next rank
-        if self.world == 1:
-            halo_in = halo_out
-        else:
-            halo_in = self._buf("halo_in", halo_out.shape, torch.float32)
-            nxt, prv = (self.rank + 1) % self.world, (self.rank - 1) % self.world
-            ops = [dist.P2POp(dist.isend, halo_out, nxt, self.group), dist.P2POp(dist.irecv, halo_in, prv, self.group)]
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        self.ops.add_inplace(slab, work[:self.nx])
+        halo_in = self._buf("halo_in", halo_out.shape, torch.float32)
+        nxt, prv = (self.rank + 1) % self.world, (self.rank - 1) % self.world
+        ops = [dist.P2POp(dist.isend, halo_out, nxt, self.group), dist.P2POp(dist.irecv, halo_in, prv, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if not own_slab:
+            self.ops.add_inplace(slab, work[:self.nx])
         self.ops.add_inplace(slab[:ghosts], halo_in)
 
     def check_dropped(self):
@@ -318,21 +349,50 @@ class SlabContext:
         return slab
 
     # ---- distributed r2c: (nx_local, N, N) real -> (N, nky_local, nz) complex ---------------------
-    def fft(self, slab, slot=0):
+    def fft(self, slab, slot=0, marks=None):
         """(nx_local, N, N) real -> (N, nky_local, nz) complex.  With the peer-memory transpose the result lives
-        in symmetric receive buffer `slot` and stays valid until the next fft() with the same slot."""
+        in symmetric receive buffer `slot` and stays valid until the next fft() with the same slot.  `marks`
+        (a list) receives two CUDA events bracketing the transpose, for the NVLink figure of bench.py."""
         N, nz, P = self.dims, self.nz, self.world
-        a = self.ops.fft_yz(slab, N)                                   # (nx, N, nz)
+
+        def mark():
+            if marks is not None and self.device.type == "cuda":
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+
         if P == 1:
-            return self.ops.fft_x_(a, N)
+            return self.ops.fft_x_(self.ops.fft_yz(slab, N), N)
         if self._peer is not None:
+            # Batches of x-planes: the 2D transforms of batch b+1 (main stream) run while batch b travels to the
+            # owners of its ky rows (side stream, one kernel storing over NVLink).  Two batch buffers replace the
+            # slab-sized stage-1 array.
             buf, hdl, ptrs = self._peer_slot(slot)
+            nb = max(1, min(self.nx, self.FFT_BATCH_PLANES))
+            ring = self._buf("fft_ring", (2, nb, N, nz), torch.complex64)
+            main = torch.cuda.current_stream(self.device)
+            side = self._side_stream()
             hdl.barrier(channel=0)                                     # every rank is done with this slot
-            self.ops.transpose_scatter(a, ptrs, self._peer["nky"], self._peer["owner"], self._peer["row"], N,
-                                       self.x_range[0])
+            mark()
+            free = [None, None]
+            for k, b0 in enumerate(range(0, self.nx, nb)):
+                b1, j = min(b0 + nb, self.nx), k & 1
+                if free[j] is not None:
+                    main.wait_event(free[j])                           # the scatter that read this buffer is done
+                a = self.ops.fft_yz(slab[b0:b1], N, out=ring[j, :b1 - b0])
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    self.ops.transpose_scatter(a, ptrs, self._peer["nky"], self._peer["owner"], self._peer["row"], N,
+                                               self.x_range[0] + b0)
+                    free[j] = torch.cuda.Event()
+                    free[j].record(side)
+            main.wait_stream(side)
             hdl.barrier(channel=0)                                     # every row has landed
-            del a
+            mark()
             return self.ops.fft_x_(buf[:N * self.nky * nz].view(N, self.nky, nz), N)
+        a = self.ops.fft_yz(slab, N)                                   # (nx, N, nz)
         send = self._buf("send", (self.nx * N * nz,), a.dtype)
         send_sizes, off = [], 0                                        # (complex64 on the GPU path)
         for r in range(P):                                             # pack: the ky rows of rank r, every local plane
@@ -358,8 +418,13 @@ class SlabContext:
         """All-reduce the raw accumulators.  Counts (uint64 words) become float64 first -- exact below
         2^53 -- so that one float64 SUM covers the whole buffer."""
         f64 = out.view(torch.float64)
-        for off, n in ((lay.Nm3D, lay.kmax + 1), (lay.Nm1D, lay.kmax_par + 1), (lay.Nm2D, lay.n2d)):
-            f64[off:off + n] = out[off:off + n].to(torch.float64)
+        if out.is_cuda:
+            with torch.cuda.device(out.device):
+                L.check(L.load().pyl_pk_counts_to_f64(D.ptr(out), self.dims, int(lay.fields), D.stream_ptr(out.device)),
+                        "pyl_pk_counts_to_f64")
+        else:
+            for off, n in ((lay.Nm3D, lay.kmax + 1), (lay.Nm1D, lay.kmax_par + 1), (lay.Nm2D, lay.n2d)):
+                f64[off:off + n] = out[off:off + n].to(torch.float64)
         dist.all_reduce(f64[:lay.total_words], group=self.group)     # (kpar/kper scratch behind it is not reduced)
         return f64
 

@@ -13,6 +13,33 @@ def uniform_host(n, BoxSize, seed):
     return pos
 
 
+def zeldovich_host(n_side, BoxSize, seed, rms_cells=1.5, slope=-1.5, kcut_frac=0.25):
+    """NumPy twin of zeldovich_device (same recipe, NumPy's generator): host inputs for the CPU legs and tests."""
+    n = n_side
+    rng = np.random.default_rng(seed)
+    kf = 2.0 * np.pi / BoxSize
+    k1 = (np.fft.fftfreq(n, d=1.0 / n) * kf).astype(np.float32)
+    kz = (np.fft.rfftfreq(n, d=1.0 / n) * kf).astype(np.float32)
+    k2 = k1[:, None, None] ** 2 + k1[None, :, None] ** 2 + kz[None, None, :] ** 2
+    k2[0, 0, 0] = 1.0
+    kc = kcut_frac * (n // 2) * kf
+    amp = np.sqrt(k2 ** (slope / 2.0) * np.exp(-k2 / kc ** 2)).astype(np.float32)
+    amp[0, 0, 0] = 0.0
+    dk = (rng.standard_normal(k2.shape, dtype=np.float32) + 1j * rng.standard_normal(k2.shape, dtype=np.float32)) * amp
+    disp = [np.fft.irfftn(1j * kv * dk / k2, s=(n, n, n)).astype(np.float32)
+            for kv in (k1[:, None, None], k1[None, :, None], kz[None, None, :])]
+    rms = np.sqrt(sum(np.mean(d.astype(np.float64) ** 2) for d in disp) / 3.0)
+    scale = np.float32(rms_cells * (BoxSize / n) / max(rms, 1e-30))
+    q = ((np.arange(n, dtype=np.float32) + np.float32(0.5)) * np.float32(BoxSize / n))
+    pos = np.empty((n, n, n, 3), dtype=np.float32)
+    shapes = ((n, 1, 1), (1, n, 1), (1, 1, n))
+    for ax in range(3):
+        pos[..., ax] = np.remainder(q.reshape(shapes[ax]) + disp[ax] * scale, np.float32(BoxSize))
+    pos = pos.reshape(-1, 3)
+    np.clip(pos, 0.0, np.nextafter(np.float32(BoxSize), np.float32(0)), out=pos)
+    return pos
+
+
 def uniform_device(n, BoxSize, seed, device, x_range=None):
     """Uniform positions on the device.  x_range=(lo,hi) restricts the first coordinate (per-slab
     generation for multi-GPU runs: same density everywhere, particles already on their owner)."""

@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) smem_ops(unsigned *out, int iters, int tb
         else if (KIND == 3) { float v = ftbl[a]; ftbl[a] = v + 1.0f; }      // plain RMW, random banks
         else if (KIND == 4) { unsigned b = (a & ~31u) | (threadIdx.x & 31); float v = ftbl[b]; ftbl[b] = v + 1.0f; }  // conflict-free RMW
         else if (KIND == 5) atomicAdd(&tbl[a], 1u);                         // ATOMS non-returning (RED.shared)
+        else if (KIND == 6) { unsigned b = (a & ~31u) | (threadIdx.x & 31); acc += atomicAdd(&tbl[b], 1u); }  // ATOMS, one lane per bank
     }
     if (acc == 0xdeadbeef) out[0] = acc;
     __syncthreads();
@@ -179,15 +180,16 @@ int main() {
 
     {   // shared-memory ops: 8 CTAs/SM x 256 threads, table 4096 words
         const int iters = 4096, blocks = sms * 8;
-        const char *names[] = {"ATOMS.ADD u32 returning, random", "atomicAdd float smem, random", "match_any", "plain RMW random banks", "plain RMW conflict-free", "ATOMS.ADD u32 no return"};
-        float ms[6];
+        const char *names[] = {"ATOMS.ADD u32 returning, random", "atomicAdd float smem, random", "match_any", "plain RMW random banks", "plain RMW conflict-free", "ATOMS.ADD u32 no return", "ATOMS.ADD u32 returning, conflict-free"};
+        float ms[7];
+        ms[6] = timeit([&] { smem_ops<6><<<blocks, 256, 16384>>>(out, iters, 4095); });
         ms[0] = timeit([&] { smem_ops<0><<<blocks, 256, 16384>>>(out, iters, 4095); });
         ms[1] = timeit([&] { smem_ops<1><<<blocks, 256, 16384>>>(out, iters, 4095); });
         ms[2] = timeit([&] { smem_ops<2><<<blocks, 256, 16384>>>(out, iters, 4095); });
         ms[3] = timeit([&] { smem_ops<3><<<blocks, 256, 16384>>>(out, iters, 4095); });
         ms[4] = timeit([&] { smem_ops<4><<<blocks, 256, 16384>>>(out, iters, 4095); });
         ms[5] = timeit([&] { smem_ops<5><<<blocks, 256, 16384>>>(out, iters, 4095); });
-        for (int k = 0; k < 6; k++) {
+        for (int k = 0; k < 7; k++) {
             const double warp_ops_per_sm = (double)iters * 8 * 8;      // warps per SM x iters
             printf("smem %-34s %8.3f ms  %.2f cycles per warp-op per SM\n", names[k], ms[k], ms[k] * 1e-3 * ghz * 1e9 / warp_ops_per_sm);
         }

@@ -22,7 +22,9 @@ def test_reference_arm_prints_one_json_line():
     assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] == ("reference" if ref_loader.have_ref() else "port")
-    assert line["config"]["workload"].startswith("BASELINE config 2")
+    assert line["config"]["workload"].startswith("BASELINE config 3")
+    # the label says what the reference arm really ran: a bounded sample, not the 1024^3 workload itself
+    assert "SAMPLE" in line["config"]["workload"] and "256^3" in line["config"]["workload"]
 
 
 def test_other_ranks_of_the_reference_arm_stay_silent():

@@ -48,18 +48,21 @@ def _tol(ref, scale, tol):
     return tol * np.abs(ref) + EPS_FFT * np.sqrt(scale * peak) + EPS_FFT ** 2 * peak
 
 
-def check_pk(got, ref, cross=False, tol=TOL, fft_floor=True):
+def check_pk(got, ref, cross=False, tol=TOL, fft_floor=True, phase_min_modes=0):
+    """phase_min_modes: Pkphase (a scale-free angle per mode) of a nearly empty shell is dominated by the float32
+    FFT noise of its few low-amplitude modes; callers whose transform differs from the oracle's in structure
+    (slab FFT) compare it only on shells with at least that many modes."""
     global EPS_FFT
     eps_saved = EPS_FFT
     if not fft_floor:
         EPS_FFT = 1e-11            # float64 accumulation-order noise only
     try:
-        _check_pk(got, ref, cross, tol)
+        _check_pk(got, ref, cross, tol, phase_min_modes)
     finally:
         EPS_FFT = eps_saved
 
 
-def _check_pk(got, ref, cross, tol):
+def _check_pk(got, ref, cross, tol, phase_min_modes=0):
     for nm in ("Nmodes3D", "Nmodes1D", "Nmodes2D"):
         assert np.array_equal(np.asarray(getattr(got, nm)), np.asarray(getattr(ref, nm))), nm
     for nm in ("k3D", "k1D", "kpar", "kper"):
@@ -85,7 +88,8 @@ def _check_pk(got, ref, cross, tol):
         ok = np.abs(a - b) <= _tol(b, b, tol)
         assert np.all(ok | np.isnan(b)), nm
     if hasattr(ref, "Pkphase") and not cross:
-        assert rel_err(np.asarray(got.Pkphase), np.asarray(ref.Pkphase), 1e-300) < max(tol, 2e-6), "Pkphase"
+        sel = np.asarray(ref.Nmodes3D) >= phase_min_modes
+        assert rel_err(np.asarray(got.Pkphase)[sel], np.asarray(ref.Pkphase)[sel], 1e-300) < max(tol, 2e-6), "Pkphase"
     if cross:
         Xr, Xg = np.asarray(ref.XPk), np.asarray(got.XPk)
         ix = 0
