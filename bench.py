@@ -305,7 +305,12 @@ def small_parity_check(world, rank, dev):
         out["deposit_max_rel_err"] = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), ref.mean())))
         d = (ref / np.mean(ref, dtype=np.float64) - 1.0).astype(np.float32)
         rp = O.Pk(d, BOX, 0, "PCS", 1, False)
-        out["Pk0_max_rel_err"] = float(np.max(np.abs(pk.Pk[:, 0] / rp.Pk[:, 0] - 1.0)))
+        # the bar of tests/test_gpu_pk.py: 1e-4 relative + the float32-FFT floor eps*sqrt(P_bin*P_peak), eps = 1e-5
+        p_ref, peak = np.abs(rp.Pk[:, 0]), float(np.max(np.abs(rp.Pk[:, 0])))
+        tol = 1e-4 * p_ref + 1e-5 * np.sqrt(p_ref * peak) + 1e-10 * peak
+        out["Pk0_max_err_over_tolerance"] = float(np.max(np.abs(pk.Pk[:, 0] - rp.Pk[:, 0]) / tol))
+        out["Pk0_max_rel_err_top_half_of_bins_by_power"] = float(np.max(
+            (np.abs(pk.Pk[:, 0] / rp.Pk[:, 0] - 1.0))[p_ref >= np.median(p_ref)]))
         out["Nmodes_equal"] = bool(np.array_equal(pk.Nmodes3D, rp.Nmodes3D))
         out["case"] = "%d^3 grid, %d clustered particles + W, PCS, %d rank(s), against oracle/" % (N, len(pos), world)
     return out
@@ -434,25 +439,31 @@ def run_ours(args, wl, grid_n):
         stages["bin_kernels_only"] = round(a.elapsed_time(b) / reps, 4)
         del dk
     else:
-        names = ("zero", "route", "deposit+halo", "overdensity", "fft_yz", "transpose", "fft_x",
-                 "bin+allreduce+finalise+d2h")
+        names = ("zero", "route", "deposit+halo", "overdensity", "fft_yz+transpose(pipelined)", "transpose_kernels",
+                 "fft_x", "bin+allreduce+finalise+d2h")
         acc = {k: 0.0 for k in names}
+        peer_route = ctx._peer is not None and ctx._route_mode == "peer"
         for _ in range(reps):
             barrier()                      # ranks start each repetition together: no inter-rank skew in the stage times
             e0 = ev(); slab.zero_()
-            e1 = ev(); p_r, w_r = ctx.route(pos, MAS, W)
-            e2 = ev(); ctx.MA(p_r, slab, MAS, W=w_r, routed=True)
+            e1 = ev()
+            if peer_route:
+                p_r, w_r, cnt = ctx.route_peer(pos, MAS, W)
+            else:
+                (p_r, w_r), cnt = ctx.route(pos, MAS, W), None
+            e2 = ev(); ctx.MA(p_r, slab, MAS, W=w_r, routed=True, count=cnt)
             e3 = ev(); ctx.overdensity_(slab)
-            e4 = ev(); marks = []
+            e4 = ev(); marks = {}
             dk = ctx.fft(slab, marks=marks)
             e5 = ev(); ctx._spectra([dk], [PKL.MAS_function(MAS)], AXIS, True)
             e6 = ev(); torch.cuda.synchronize()
             pairs = {"zero": (e0, e1), "route": (e1, e2), "deposit+halo": (e2, e3), "overdensity": (e3, e4),
                      "bin+allreduce+finalise+d2h": (e5, e6)}
-            if len(marks) == 2:
-                pairs.update({"fft_yz": (e4, marks[0]), "transpose": (marks[0], marks[1]), "fft_x": (marks[1], e5)})
+            if "t1" in marks:
+                pairs.update({"fft_yz+transpose(pipelined)": (e4, marks["t1"]), "fft_x": (marks["t1"], e5)})
+                acc["transpose_kernels"] += sum(x.elapsed_time(y) for x, y in marks.get("pairs", [])) / reps
             else:
-                pairs["fft_yz"] = (e4, e5)
+                pairs["fft_yz+transpose(pipelined)"] = (e4, e5)
             for k, (x, y) in pairs.items():
                 acc[k] += x.elapsed_time(y) / reps
             del dk, p_r, w_r
@@ -541,14 +552,16 @@ def run_ours(args, wl, grid_n):
         per = 1.0 / world
         rooflines["deposit"] = roof("deposit + halo exchange, per GPU (%s, pyl_deposit_slab)" % MAS,
                                     (npart * bpp + 8 * grid_n ** 3) * per, stages["deposit+halo"], traffic=None)
-        if stages.get("transpose"):
+        if stages.get("transpose_kernels"):
             sent = 8 * half * per * (world - 1) / world
-            ach = sent / (stages["transpose"] * 1e-3) / 1e9
+            ach = sent / (stages["transpose_kernels"] * 1e-3) / 1e9
             rooflines["transpose"] = {"bound": "nvlink", "kernel": "transpose_scatter_kernel (peer stores over NVLink)",
                                       "achieved": ach, "peak": 770.0, "unit": "GB/s", "frac": ach / 770.0,
                                       "peak_source": "measured peer copy per direction (B200_PROFILING.md; 900 nominal)",
-                                      "algorithmic_bytes_per_launch": sent, "avg_launch_ms": stages["transpose"],
-                                      "share_of_step": stages["transpose"] / ms_step, "traffic": None}
+                                      "algorithmic_bytes_per_launch": sent, "avg_launch_ms": stages["transpose_kernels"],
+                                      "share_of_step": stages["transpose_kernels"] / ms_step, "traffic": None,
+                                      "note": "sum of the per-batch transpose kernels, timed on their side stream "
+                                              "while the 2D FFTs of the next batch run on the main stream"}
         rooflines["bin"] = roof("pk_bin (mirrored slab) + all-reduce + finalise + d2h, per GPU", 8 * half * per,
                                 stages["bin+allreduce+finalise+d2h"], traffic=None)
     roofline = dict(rooflines["deposit"])

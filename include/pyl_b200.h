@@ -213,6 +213,27 @@ int pyl_pk_bin(const float *const *delta_k, int fields, const int *mas_index, in
                int ky_lo, int nky, int axis, int want_phase, void *out, void *ws,
                size_t ws_bytes, pyl_stream_t stream);
 
+/* pyl_deposit_slab for particles whose COUNT lives on the device (the output of pyl_route_scatter): `capacity` is the
+ * size of the pos/W arrays, *count (device uint32) the number of particles in them.  No reference counterpart. */
+int pyl_deposit_slab_counted(int mas, const float *pos, float *number, const float *W, int64_t capacity,
+                             const uint32_t *count, int dims, float BoxSize, int x_origin, int x_own, int x_planes,
+                             int64_t *dropped, void *ws, size_t ws_bytes, pyl_stream_t stream);
+
+/* Particle routing to the x-slab owners over peer memory (no reference counterpart: the reference is one process).
+ * Every rank owns the planes [x_offsets[r], x_offsets[r+1]) and a receive block of pyl_route_block_bytes(capacity)
+ * bytes, allocated symmetrically and mapped into every peer (peer_blocks[r] = this process's pointer to rank r's
+ * block).  Block layout: byte 0: uint32 cursor = particles received; byte 256: positions, (capacity, 3) float32;
+ * then, 256-byte aligned, `capacity` float32 weights.  The kernel sends each of the caller's particles to the
+ * owner of the x-plane of its first stencil cell (pyl_stencil_base_plane's rule): one system-scope atomic per
+ * (4096-particle chunk, destination) reserves a run behind the destination's cursor, consecutive lanes store the
+ * run into the destination's arrays.  The caller zeroes its cursor, synchronises the ranks, launches, synchronises
+ * again, and deposits [block + 256] with pyl_deposit_slab_counted(count = block).  *lost (device int64) counts
+ * particles that found a block full; it must stay 0. */
+size_t pyl_route_block_bytes(int64_t capacity);
+int pyl_route_scatter(int mas, const float *pos, const float *W, int64_t particles, int dims, float BoxSize,
+                      int nranks, const int *x_offsets, void *const *peer_blocks, int64_t capacity, int64_t *lost,
+                      pyl_stream_t stream);
+
 /* Slab-distributed spectra (no reference counterpart: the reference is one process): converts the
  * uint64 mode counts of an accumulator block (layout of pyl_pk_layout) to float64 in place -- exact below 2^53 -- so
  * that a single float64 SUM all-reduce covers the whole block; follow with pyl_pk_finalize(counts_are_f64 = 1). */

@@ -53,6 +53,9 @@ PROTOTYPES = {
     "pyl_deposit": (_i, [_i, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp, _sz, _vp]),
     "pyl_deposit_slab_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "pyl_deposit_slab": (_i, [_i, _vp, _vp, _vp, _i64, _i, _f, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "pyl_deposit_slab_counted": (_i, [_i, _vp, _vp, _vp, _i64, _vp, _i, _f, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "pyl_route_block_bytes": (_sz, [_i64]),
+    "pyl_route_scatter": (_i, [_i, _vp, _vp, _i64, _i, _f, _i, _vp, _vp, _i64, _vp, _vp]),
     "pyl_stencil_base_plane": (_i, [_i, _vp, _i64, _i, _f, _vp, _vp]),
     "pyl_cic_interp": (_i, [_vp, _i, _f, _vp, _i64, _vp, _vp]),
     "pyl_pos_redshift_space": (_i, [_vp, _vp, _i64, _f, _f, _f, _i, _vp]),

@@ -18,7 +18,7 @@ TAG = os.environ.get("PYL_BUILD_TAG", "")
 EXTRA = os.environ.get("PYL_BUILD_DEFS", "").split()
 SO = os.path.join(PKG, "libpyl_b200%s.so" % ("_" + TAG if TAG else ""))
 BUILD_DIR = os.path.join(PKG, "build" + ("_" + TAG if TAG else ""))
-SOURCES = ["common.cu", "deposit.cu", "deposit_atomic.cu", "deposit_tiled.cu", "deposit_sorted.cu", "interp.cu", "fft.cu", "transpose.cu", "pk_bin.cu", "pk_shell.cu",
+SOURCES = ["common.cu", "deposit.cu", "deposit_atomic.cu", "deposit_tiled.cu", "deposit_sorted.cu", "interp.cu", "fft.cu", "transpose.cu", "route.cu", "pk_bin.cu", "pk_shell.cu",
            "hostapi.cu"]
 HEADERS = ["common.cuh", "stencil.cuh", "shell_body.cuh", "deposit_point.cuh", os.path.join(ROOT, "include", "pyl_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

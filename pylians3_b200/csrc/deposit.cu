@@ -4,11 +4,11 @@
 namespace pyl {
 int deposit_atomic(int mas, const float *pos, float *number, const float *W, int64_t particles,
                    int dims, int axes, float BoxSize, bool slab, int x_origin, int x_planes,
-                   int64_t *dropped, cudaStream_t stream, float plane_mult = 0.0f);
+                   int64_t *dropped, cudaStream_t stream, float plane_mult = 0.0f, const unsigned *n_dev = nullptr);
 size_t deposit_tiled_workspace(int mas, int64_t particles, int dims, int axes, int mode, int x_own);
 int deposit_tiled(int mas, const float *pos, float *number, const float *W, int64_t particles, int dims,
                   float BoxSize, int x_origin, int x_own, int x_planes, int64_t *dropped, void *ws,
-                  cudaStream_t stream);
+                  cudaStream_t stream, const unsigned *n_dev = nullptr);
 bool deposit_tiled_supported(int mas, int64_t particles, int dims, int axes, int x_own);
 bool deposit_sorted_supported(int64_t particles);
 size_t deposit_sorted_workspace(int64_t particles, int dims, int axes);
@@ -91,9 +91,9 @@ size_t pyl_deposit_slab_workspace_bytes(int mas, int64_t particles, int dims, in
     return deposit_tiled_workspace(mas, particles, dims, 3, PYL_MODE_TILED, x_own);
 }
 
-int pyl_deposit_slab(int mas, const float *pos, float *number, const float *W,
-                     int64_t particles, int dims, float BoxSize, int x_origin, int x_own, int x_planes,
-                     int64_t *dropped, void *ws, size_t ws_bytes, pyl_stream_t stream) {
+static int deposit_slab_impl(int mas, const float *pos, float *number, const float *W, int64_t particles,
+                             const unsigned *n_dev, int dims, float BoxSize, int x_origin, int x_own, int x_planes,
+                             int64_t *dropped, void *ws, size_t ws_bytes, pyl_stream_t stream) {
     PYL_REQUIRE(mas >= PYL_MAS_NGP && mas <= PYL_MAS_PCS, "pyl_deposit_slab: unknown scheme");
     PYL_REQUIRE(dims > 0 && x_planes > 0 && x_planes <= dims, "pyl_deposit_slab: bad plane window");
     PYL_REQUIRE(x_own > 0 && x_own <= x_planes, "pyl_deposit_slab: x_own must be in 1..x_planes");
@@ -106,15 +106,30 @@ int pyl_deposit_slab(int mas, const float *pos, float *number, const float *W,
         const size_t whole = pyl_deposit_workspace_bytes(mas, particles, dims, 3, PYL_MODE_TILED);
         if (whole > 0 && ws != nullptr && ws_bytes >= whole)
             return deposit_tiled(mas, pos, number, W, particles, dims, BoxSize, 0, -1, -1, dropped, ws,
-                                 as_stream(stream));
+                                 as_stream(stream), n_dev);
     }
     const size_t need = pyl_deposit_slab_workspace_bytes(mas, particles, dims, x_own);
     if (need > 0 && ws != nullptr && ws_bytes >= need && x_planes < dims)
         return deposit_tiled(mas, pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dropped,
-                             ws, as_stream(stream));
+                             ws, as_stream(stream), n_dev);
     // no (or too small a) workspace, sparse input, or a window spanning the whole grid: atomic kernel
     return deposit_atomic(mas, pos, number, W, particles, dims, 3, BoxSize, true, x_origin,
-                          x_planes, dropped, as_stream(stream));
+                          x_planes, dropped, as_stream(stream), 0.0f, n_dev);
+}
+
+int pyl_deposit_slab(int mas, const float *pos, float *number, const float *W,
+                     int64_t particles, int dims, float BoxSize, int x_origin, int x_own, int x_planes,
+                     int64_t *dropped, void *ws, size_t ws_bytes, pyl_stream_t stream) {
+    return deposit_slab_impl(mas, pos, number, W, particles, nullptr, dims, BoxSize, x_origin, x_own, x_planes,
+                             dropped, ws, ws_bytes, stream);
+}
+
+int pyl_deposit_slab_counted(int mas, const float *pos, float *number, const float *W, int64_t capacity,
+                             const uint32_t *count, int dims, float BoxSize, int x_origin, int x_own, int x_planes,
+                             int64_t *dropped, void *ws, size_t ws_bytes, pyl_stream_t stream) {
+    PYL_REQUIRE(count != nullptr, "pyl_deposit_slab_counted: NULL count");
+    return deposit_slab_impl(mas, pos, number, W, capacity, count, dims, BoxSize, x_origin, x_own, x_planes,
+                             dropped, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

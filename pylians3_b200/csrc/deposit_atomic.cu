@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(256)
 deposit_atomic_kernel(const float *__restrict__ pos, const float *__restrict__ W,
                       float *__restrict__ number, int64_t particles, int dims,
                       float inv_cell_size, SlabWindow win, unsigned long long *dropped_out,
-                      int vec_ok) {
+                      int vec_ok, const unsigned *__restrict__ n_dev) {
+    if (n_dev != nullptr) particles = min(particles, (int64_t)__ldg(n_dev));     // count known on the device only
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long dropped = 0;
@@ -57,7 +58,7 @@ deposit_atomic_kernel(const float *__restrict__ pos, const float *__restrict__ W
 template <int MAS, int AXES, bool WEIGHTED, bool SLAB>
 static int launch_atomic(const float *pos, const float *W, float *number, int64_t particles,
                          int dims, float inv_cell_size, SlabWindow win,
-                         unsigned long long *dropped, cudaStream_t stream) {
+                         unsigned long long *dropped, cudaStream_t stream, const unsigned *n_dev) {
     const int vec_ok = ((reinterpret_cast<uintptr_t>(pos) & 15) == 0) &&
                        (!WEIGHTED || (reinterpret_cast<uintptr_t>(W) & 15) == 0);
     int64_t blocks = ((particles + 3) / 4 + 255) / 256;
@@ -65,7 +66,7 @@ static int launch_atomic(const float *pos, const float *W, float *number, int64_
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     deposit_atomic_kernel<MAS, AXES, WEIGHTED, SLAB><<<(int)blocks, 256, 0, stream>>>(
-        pos, W, number, particles, dims, inv_cell_size, win, dropped, vec_ok);
+        pos, W, number, particles, dims, inv_cell_size, win, dropped, vec_ok, n_dev);
     PYL_LAUNCH_CHECK();
     return PYL_OK;
 }
@@ -73,17 +74,17 @@ static int launch_atomic(const float *pos, const float *W, float *number, int64_
 template <int MAS>
 static int dispatch_atomic(const float *pos, const float *W, float *number, int64_t particles,
                            int dims, int axes, float inv, bool slab, SlabWindow win,
-                           unsigned long long *dropped, cudaStream_t s) {
+                           unsigned long long *dropped, cudaStream_t s, const unsigned *n_dev) {
     if (slab) {
-        return W ? launch_atomic<MAS, 3, true, true>(pos, W, number, particles, dims, inv, win, dropped, s)
-                 : launch_atomic<MAS, 3, false, true>(pos, W, number, particles, dims, inv, win, dropped, s);
+        return W ? launch_atomic<MAS, 3, true, true>(pos, W, number, particles, dims, inv, win, dropped, s, n_dev)
+                 : launch_atomic<MAS, 3, false, true>(pos, W, number, particles, dims, inv, win, dropped, s, n_dev);
     }
     if (axes == 3) {
-        return W ? launch_atomic<MAS, 3, true, false>(pos, W, number, particles, dims, inv, win, dropped, s)
-                 : launch_atomic<MAS, 3, false, false>(pos, W, number, particles, dims, inv, win, dropped, s);
+        return W ? launch_atomic<MAS, 3, true, false>(pos, W, number, particles, dims, inv, win, dropped, s, n_dev)
+                 : launch_atomic<MAS, 3, false, false>(pos, W, number, particles, dims, inv, win, dropped, s, n_dev);
     }
-    return W ? launch_atomic<MAS, 2, true, false>(pos, W, number, particles, dims, inv, win, dropped, s)
-             : launch_atomic<MAS, 2, false, false>(pos, W, number, particles, dims, inv, win, dropped, s);
+    return W ? launch_atomic<MAS, 2, true, false>(pos, W, number, particles, dims, inv, win, dropped, s, n_dev)
+             : launch_atomic<MAS, 2, false, false>(pos, W, number, particles, dims, inv, win, dropped, s, n_dev);
 }
 
 // first stencil cell along x (wrapped), same arithmetic as axis_stencil<MAS>
@@ -121,17 +122,17 @@ int stencil_base_plane(int mas, const float *pos, int64_t particles, int dims, f
 // shared with deposit.cu
 int deposit_atomic(int mas, const float *pos, float *number, const float *W, int64_t particles,
                    int dims, int axes, float BoxSize, bool slab, int x_origin, int x_planes,
-                   int64_t *dropped, cudaStream_t stream, float plane_mult) {
+                   int64_t *dropped, cudaStream_t stream, float plane_mult, const unsigned *n_dev) {
     // inv_cell_size = dims/BoxSize evaluated in float32 like `cdef float inv_cell_size`
     // (MAS_library.pyx:135); IEEE division on the host, identical to the CPU's.
     const float inv = (float)dims / BoxSize;
     SlabWindow win{x_origin, x_planes, plane_mult};
     unsigned long long *dr = reinterpret_cast<unsigned long long *>(dropped);
     switch (mas) {
-        case PYL_MAS_NGP: return dispatch_atomic<PYL_MAS_NGP>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream);
-        case PYL_MAS_CIC: return dispatch_atomic<PYL_MAS_CIC>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream);
-        case PYL_MAS_TSC: return dispatch_atomic<PYL_MAS_TSC>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream);
-        case PYL_MAS_PCS: return dispatch_atomic<PYL_MAS_PCS>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream);
+        case PYL_MAS_NGP: return dispatch_atomic<PYL_MAS_NGP>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream, n_dev);
+        case PYL_MAS_CIC: return dispatch_atomic<PYL_MAS_CIC>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream, n_dev);
+        case PYL_MAS_TSC: return dispatch_atomic<PYL_MAS_TSC>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream, n_dev);
+        case PYL_MAS_PCS: return dispatch_atomic<PYL_MAS_PCS>(pos, W, number, particles, dims, axes, inv, slab, win, dr, stream, n_dev);
     }
     set_last_error("deposit: unknown mass-assignment scheme %d", mas);
     return PYL_ERR_ARG;

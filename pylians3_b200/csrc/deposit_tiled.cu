@@ -109,7 +109,9 @@ __device__ __forceinline__ unsigned tile_and_local(const float d[3], const TileG
 // ---- 1. sampled histogram --------------------------------------------------------------------------
 template <int MAS>
 __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict__ pos, int64_t particles,
-                                                         TileGeom g, unsigned *__restrict__ counts, int vec_ok) {
+                                                         TileGeom g, unsigned *__restrict__ counts, int vec_ok,
+                                                         const unsigned *__restrict__ n_dev) {
+    if (n_dev != nullptr) particles = min(particles, (int64_t)__ldg(n_dev));     // count known on the device only
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t groups = vec_ok ? (particles >> 2) : 0;
@@ -243,6 +245,8 @@ struct PartArgs {
     float *number;               // the grid (overflow path only)
     unsigned long long *dropped;
     double *wsum;                // sum of |W| over the particles of this call (pass 1, weighted only)
+    const unsigned *n_dev;       // optional: the particle count lives on the device (routed particles); then
+                                 // `particles` is the capacity of the arrays
 };
 
 // dynamic shared memory of a partition CTA: PP staged records + three words per bin + the bin of every staged record
@@ -271,7 +275,9 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
     unsigned super = 0, repl = 0;
     if (LEVEL == 1) {
         first = (int64_t)blockIdx.x * PP;
-        n_in = (int)min((int64_t)PP, a.particles - first);
+        const int64_t n_all = a.n_dev != nullptr ? min(a.particles, (int64_t)__ldg(a.n_dev)) : a.particles;
+        if (first >= n_all) return;
+        n_in = (int)min((int64_t)PP, n_all - first);
         repl = blockIdx.x % g.repl;
     } else {
         if (warp == 0) {
@@ -496,7 +502,8 @@ template <int MAS, bool WEIGHTED>
 __global__ void __launch_bounds__(TNT)
 tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restrict__ starts,
                     const unsigned *__restrict__ cur2, float *__restrict__ number, TileGeom g,
-                    const double *__restrict__ wsum, double particles, int bulk_ok) {
+                    const double *__restrict__ wsum, double particles, const unsigned *__restrict__ n_dev,
+                    int bulk_ok) {
     using TA = TileAcc<MAS>;
     constexpr int S = TA::S, AY = TA::AY;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -515,7 +522,8 @@ tile_deposit_kernel(const float4 *__restrict__ bucket, const unsigned *__restric
     // power-of-two scale: a typical contribution lands near 2^26 (exact scaling; see the header comment)
     int kexp = 26;
     if (WEIGHTED) {
-        const double mean = __ldg(wsum) / particles;
+        if (n_dev != nullptr) particles = fmin(particles, (double)__ldg(n_dev));
+        const double mean = __ldg(wsum) / fmax(particles, 1.0);
         int e = 0;
         if (mean > 0.0 && mean < 1e300) frexp(mean, &e);         // mean = f * 2^e, f in [0.5, 1)
         kexp = 26 - e;
@@ -752,7 +760,8 @@ static int set_smem(K kernel, size_t bytes) {
 
 template <int MAS, bool WEIGHTED>
 static int run_tiled_w(const float *pos, float *number, const float *W, int64_t particles, const TileGeom &g,
-                       const TiledWorkspace &w, unsigned long long *dropped, cudaStream_t stream) {
+                       const TiledWorkspace &w, unsigned long long *dropped, const unsigned *n_dev,
+                       cudaStream_t stream) {
     static bool attr_done = false;
     if (!attr_done) {
         int st = set_smem(partition_kernel<MAS, WEIGHTED, 1>, part_smem_bytes(MAX_BINS));
@@ -765,6 +774,7 @@ static int run_tiled_w(const float *pos, float *number, const float *W, int64_t 
     a.pos = pos; a.W = W; a.particles = particles; a.in = w.buf1; a.out = w.buf1;
     a.starts = w.starts; a.cur1 = w.cur1; a.cur2 = w.cur2; a.spre = w.spre; a.number = number; a.dropped = dropped;
     a.wsum = w.wsum;
+    a.n_dev = n_dev;
     if (WEIGHTED) PYL_CUDA_CHECK(cudaMemsetAsync(w.wsum, 0, 8, stream));
     const unsigned ctas1 = (unsigned)((particles + PP - 1) / PP);
     partition_kernel<MAS, WEIGHTED, 1><<<ctas1, PT, part_smem_bytes((int)g.nsuper), stream>>>(a, g);
@@ -777,7 +787,7 @@ static int run_tiled_w(const float *pos, float *number, const float *W, int64_t 
     // bulk reductions need 16-byte aligned 128-byte rows: whole tiles along z and an aligned grid
     const int bulk_ok = (g.dims % TZ == 0) && ((reinterpret_cast<uintptr_t>(number) & 15) == 0);
     tile_deposit_kernel<MAS, WEIGHTED><<<g.ntiles, TNT, TileAcc<MAS>::bytes, stream>>>(
-        w.buf2, w.starts, w.cur2, number, g, w.wsum, (double)particles, bulk_ok);
+        w.buf2, w.starts, w.cur2, number, g, w.wsum, (double)particles, n_dev, bulk_ok);
     PYL_LAUNCH_CHECK();
     return PYL_OK;
 }
@@ -785,7 +795,7 @@ static int run_tiled_w(const float *pos, float *number, const float *W, int64_t 
 template <int MAS>
 static int run_tiled(const float *pos, float *number, const float *W, int64_t particles, int dims,
                      float BoxSize, int x_origin, int x_own, int x_planes, unsigned long long *dropped,
-                     void *ws, cudaStream_t stream) {
+                     void *ws, const unsigned *n_dev, cudaStream_t stream) {
     const TileGeom g = make_geom(dims, BoxSize, particles, x_origin, x_own, x_planes);
     const TiledWorkspace w = carve(ws, particles, g);
 
@@ -799,7 +809,7 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
     if (cblocks < 1) cblocks = 1;
 
     PYL_CUDA_CHECK(cudaMemsetAsync(w.starts, 0, ((size_t)g.ntiles + 1) * 4, stream));
-    tile_count_kernel<MAS><<<(int)cblocks, 256, 0, stream>>>(pos, particles, g, w.starts, vec_ok);
+    tile_count_kernel<MAS><<<(int)cblocks, 256, 0, stream>>>(pos, particles, g, w.starts, vec_ok, n_dev);
     PYL_LAUNCH_CHECK();
     tile_caps_kernel<<<(g.ntiles + 1 + 255) / 256, 256, 0, stream>>>(w.starts, g.ntiles);
     PYL_LAUNCH_CHECK();
@@ -807,20 +817,20 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
                                                  (int)(g.ntiles + 1), stream));
     tile_setup_kernel<<<1 + (g.ntiles + 1023) / 1024, 1024, 0, stream>>>(w.starts, g, w.cur1, w.cur2, w.spre);
     PYL_LAUNCH_CHECK();
-    if (W) return run_tiled_w<MAS, true>(pos, number, W, particles, g, w, dropped, stream);
-    return run_tiled_w<MAS, false>(pos, number, W, particles, g, w, dropped, stream);
+    if (W) return run_tiled_w<MAS, true>(pos, number, W, particles, g, w, dropped, n_dev, stream);
+    return run_tiled_w<MAS, false>(pos, number, W, particles, g, w, dropped, n_dev, stream);
 }
 
 // x_own < 0: whole periodic grid.  Otherwise the slab window of pyl_deposit_slab.
 int deposit_tiled(int mas, const float *pos, float *number, const float *W, int64_t particles, int dims,
                   float BoxSize, int x_origin, int x_own, int x_planes, int64_t *dropped, void *ws,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const unsigned *n_dev) {
     unsigned long long *dr = reinterpret_cast<unsigned long long *>(dropped);
     switch (mas) {
-        case PYL_MAS_NGP: return run_tiled<PYL_MAS_NGP>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, stream);
-        case PYL_MAS_CIC: return run_tiled<PYL_MAS_CIC>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, stream);
-        case PYL_MAS_TSC: return run_tiled<PYL_MAS_TSC>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, stream);
-        case PYL_MAS_PCS: return run_tiled<PYL_MAS_PCS>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, stream);
+        case PYL_MAS_NGP: return run_tiled<PYL_MAS_NGP>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, n_dev, stream);
+        case PYL_MAS_CIC: return run_tiled<PYL_MAS_CIC>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, n_dev, stream);
+        case PYL_MAS_TSC: return run_tiled<PYL_MAS_TSC>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, n_dev, stream);
+        case PYL_MAS_PCS: return run_tiled<PYL_MAS_PCS>(pos, number, W, particles, dims, BoxSize, x_origin, x_own, x_planes, dr, ws, n_dev, stream);
     }
     set_last_error("deposit_tiled: unknown scheme %d", mas);
     return PYL_ERR_ARG;

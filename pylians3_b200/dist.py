@@ -80,12 +80,29 @@ class DeviceOps:
                 "pyl_stencil_base_plane")
         return out
 
-    def deposit_slab(self, mas, pos, work, W, dims, BoxSize, x_origin, x_own, dropped):
+    def deposit_slab(self, mas, pos, work, W, dims, BoxSize, x_origin, x_own, dropped, count=None):
+        """`count` (device uint32/int32 tensor of one element): the number of particles in pos/W is known on the
+        device only (routed particles); pos.shape[0] is then the capacity of the arrays."""
         need = self.lib.pyl_deposit_slab_workspace_bytes(L.MAS_IDS[mas], pos.shape[0], dims, int(x_own))
         ws = D.workspace(need, work.device, "deposit")
-        L.check(self.lib.pyl_deposit_slab(L.MAS_IDS[mas], D.ptr(pos), D.ptr(work), D.ptr(W), pos.shape[0], dims,
-                                          float(np.float32(BoxSize)), int(x_origin), int(x_own), work.shape[0],
-                                          D.ptr(dropped), D.ptr(ws), need, self._s()), "pyl_deposit_slab")
+        if count is None:
+            L.check(self.lib.pyl_deposit_slab(L.MAS_IDS[mas], D.ptr(pos), D.ptr(work), D.ptr(W), pos.shape[0], dims,
+                                              float(np.float32(BoxSize)), int(x_origin), int(x_own), work.shape[0],
+                                              D.ptr(dropped), D.ptr(ws), need, self._s()), "pyl_deposit_slab")
+        else:
+            L.check(self.lib.pyl_deposit_slab_counted(L.MAS_IDS[mas], D.ptr(pos), D.ptr(work), D.ptr(W), pos.shape[0],
+                                                      D.ptr(count), dims, float(np.float32(BoxSize)), int(x_origin),
+                                                      int(x_own), work.shape[0], D.ptr(dropped), D.ptr(ws), need,
+                                                      self._s()), "pyl_deposit_slab_counted")
+
+    def route_scatter(self, mas, pos, W, dims, BoxSize, x_offs, peer_ptrs, capacity, lost):
+        """Particles -> receive blocks of the ranks owning their first stencil plane (peer stores over NVLink)."""
+        P = len(peer_ptrs)
+        offs = (ctypes.c_int * (P + 1))(*[int(o) for o in x_offs])
+        ptrs = (ctypes.c_void_p * P)(*[int(p) for p in peer_ptrs])
+        L.check(self.lib.pyl_route_scatter(L.MAS_IDS[mas], D.ptr(pos), D.ptr(W), pos.shape[0], dims,
+                                           float(np.float32(BoxSize)), P, offs, ptrs, int(capacity), D.ptr(lost),
+                                           self._s()), "pyl_route_scatter")
 
     def add_inplace(self, out, inp):
         L.check(self.lib.pyl_add_inplace(D.ptr(out), D.ptr(inp), out.numel(), self._s()), "pyl_add_inplace")
@@ -175,7 +192,9 @@ class SlabContext:
         # memory is available: CUDA, one node.  PYL_TRANSPOSE=nccl keeps the pack + all-to-all path.
         self._peer = None
         self._peer_slots = {}
+        self._route = None
         import os
+        self._route_mode = os.environ.get("PYL_ROUTE", "peer")      # "nccl": argsort + all_to_all_single
         if self.device.type == "cuda" and self.world > 1 and os.environ.get("PYL_TRANSPOSE", "peer") == "peer":
             self._peer = self._setup_peer()
 
@@ -282,17 +301,51 @@ class SlabContext:
             self._all_to_all(W_r, W_s, rc, sc)
         return pos_r, W_r
 
+    def route_peer(self, pos, MAS, W=None):
+        """route() as ONE kernel over peer memory (pyl_route_scatter): returns (pos_r, W_r, count) where pos_r / W_r
+        are views of this rank's symmetric receive block (capacity rows) and `count` is the device word holding the
+        number of particles received.  No host synchronisation after the first call (which agrees on the capacity)."""
+        symm = self._peer["symm"]
+        n = int(pos.shape[0])
+        R = getattr(self, "_route", None)
+        if R is None:
+            t = torch.tensor([n], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            cap = int(1.25 * int(t.item())) + 65536
+            nbytes = int(self.ops.lib.pyl_route_block_bytes(cap))
+            buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+            hdl = symm.rendezvous(buf, self._peer["group"])
+            R = self._route = {"cap": cap, "buf": buf, "hdl": hdl, "ptrs": [int(p) for p in hdl.buffer_ptrs],
+                               "lost": torch.zeros(1, dtype=torch.int64, device=self.device),
+                               "w_off": (256 + cap * 12 + 255) // 256 * 256}
+        cap, buf, hdl = R["cap"], R["buf"], R["hdl"]
+        if n > cap:
+            raise ValueError("route_peer: %d particles exceed the receive capacity %d agreed on the first call; "
+                             "make a new SlabContext for larger inputs" % (n, cap))
+        buf[:256].zero_()                                   # this rank's cursor
+        hdl.barrier(channel=1)                              # every cursor is zero, every block is free
+        self.ops.route_scatter(MAS, pos, W, self.dims, self.BoxSize, self.x_offs, R["ptrs"], cap, R["lost"])
+        hdl.barrier(channel=1)                              # every particle has landed
+        pos_r = buf[256:256 + cap * 12].view(torch.float32).view(cap, 3)
+        W_r = None if W is None else buf[R["w_off"]:R["w_off"] + cap * 4].view(torch.float32)
+        return pos_r, W_r, buf[:4].view(torch.int32)
+
     # ---- mass assignment -------------------------------------------------------------------------
-    def MA(self, pos, slab, MAS="CIC", W=None, routed=False):
-        """slab (nx_local, dims, dims) += deposit of this rank's share; ghost planes go to the next rank."""
+    def MA(self, pos, slab, MAS="CIC", W=None, routed=False, count=None):
+        """slab (nx_local, dims, dims) += deposit of this rank's share; ghost planes go to the next rank.
+        routed=True: the particles are already on their owner ranks (`count`: their number as a device word, when
+        they are the output of route_peer)."""
         if MAS not in _S:
             raise ValueError("option not valid!!!")
         host = isinstance(pos, torch.Tensor) and not pos.is_cuda
-        if not routed:
+        if not routed and self.world > 1:
             if host:
-                pos, W = pos.to(self.device), (None if W is None else W.to(self.device))
+                pos, W = pos.to(self.device, non_blocking=True), (None if W is None else W.to(self.device, non_blocking=True))
                 host = False
-            pos, W = self.route(pos, MAS, W)
+            if self._peer is not None and self._route_mode == "peer":
+                pos, W, count = self.route_peer(pos, MAS, W)
+            else:
+                pos, W = self.route(pos, MAS, W)
         ghosts = _S[MAS] - 1
         x0 = self.x_range[0]
 
@@ -308,6 +361,9 @@ class SlabContext:
                 self.ops.deposit_slab(MAS, pos.to(self.device, non_blocking=True), target,
                                       None if W is None else W.to(self.device, non_blocking=True), self.dims,
                                       self.BoxSize, x0, self.nx, self.dropped)
+            elif count is not None:
+                self.ops.deposit_slab(MAS, pos, target, W, self.dims, self.BoxSize, x0, self.nx, self.dropped,
+                                      count=count)
             else:
                 self.ops.deposit_slab(MAS, pos, target, W, self.dims, self.BoxSize, x0, self.nx, self.dropped)
 
@@ -336,6 +392,8 @@ class SlabContext:
     def check_dropped(self):
         """Raise if any stencil contribution fell outside a rank's planes (mis-routed particles)."""
         d = self.dropped.clone()
+        if getattr(self, "_route", None) is not None:
+            d += self._route["lost"]
         dist.all_reduce(d, group=self.group)
         n = int(d.item())
         if n:
@@ -352,14 +410,18 @@ class SlabContext:
     def fft(self, slab, slot=0, marks=None):
         """(nx_local, N, N) real -> (N, nky_local, nz) complex.  With the peer-memory transpose the result lives
         in symmetric receive buffer `slot` and stays valid until the next fft() with the same slot.  `marks`
-        (a list) receives two CUDA events bracketing the transpose, for the NVLink figure of bench.py."""
+        (a dict) receives CUDA events for bench.py: "t0"/"t1" bracket the pipelined 2D-FFT + transpose region on the
+        main stream, "pairs" brackets every transpose kernel on its side stream (the NVLink figure)."""
         N, nz, P = self.dims, self.nz, self.world
 
-        def mark():
-            if marks is not None and self.device.type == "cuda":
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                marks.append(e)
+        def mark(key=None, stream=None):
+            if marks is None or self.device.type != "cuda":
+                return None
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream) if stream is not None else e.record()
+            if key is not None:
+                marks[key] = e
+            return e
 
         if P == 1:
             return self.ops.fft_x_(self.ops.fft_yz(slab, N), N)
@@ -373,7 +435,7 @@ class SlabContext:
             main = torch.cuda.current_stream(self.device)
             side = self._side_stream()
             hdl.barrier(channel=0)                                     # every rank is done with this slot
-            mark()
+            mark("t0")
             free = [None, None]
             for k, b0 in enumerate(range(0, self.nx, nb)):
                 b1, j = min(b0 + nb, self.nx), k & 1
@@ -384,13 +446,17 @@ class SlabContext:
                 ready.record(main)
                 with torch.cuda.stream(side):
                     side.wait_event(ready)
+                    ea = mark(stream=side)
                     self.ops.transpose_scatter(a, ptrs, self._peer["nky"], self._peer["owner"], self._peer["row"], N,
                                                self.x_range[0] + b0)
+                    eb = mark(stream=side)
+                    if ea is not None:
+                        marks.setdefault("pairs", []).append((ea, eb))
                     free[j] = torch.cuda.Event()
                     free[j].record(side)
             main.wait_stream(side)
             hdl.barrier(channel=0)                                     # every row has landed
-            mark()
+            mark("t1")
             return self.ops.fft_x_(buf[:N * self.nky * nz].view(N, self.nky, nz), N)
         a = self.ops.fft_yz(slab, N)                                   # (nx, N, nz)
         send = self._buf("send", (self.nx * N * nz,), a.dtype)
