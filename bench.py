@@ -316,6 +316,128 @@ def small_parity_check(world, rank, dev):
     return out
 
 
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs 4 and 5: slab-sharded only (multi-GPU)
+# ------------------------------------------------------------------------------------------------
+EXTRA = {
+    "config5": {"label": "BASELINE config 5", "grid": 4096, "min_world": 8,
+                "text": "%d^3 uniform-random float32 particles (generated on their owner ranks) onto a %d^3 grid, "
+                        "MA(CIC) -> delta -> Pk(axis=0) via the slab-decomposed FFT"},
+    "config4": {"label": "BASELINE config 4", "grid": 2048, "min_world": 2,
+                "text": "XPk of 3 fields (same %d^3 particles, weights 1 / uniform(0,1) / exp(2N(0,1))) on a %d^3 grid: "
+                        "3 x MA(CIC[,W]) -> delta -> XPk(axis=0), slab-sharded"},
+}
+
+
+def run_extra(name, world, rank, dev, steps, grid_override=0):
+    """One of the slab-only BASELINE configs on `world` GPUs; returns a dict (rank 0: full, others: None)."""
+    import torch
+    import torch.distributed as dist
+    from pylians3_b200 import Pk_library as PKL, _device as D, dist as PD, synth
+    cfg = EXTRA[name]
+    N = grid_override or cfg["grid"]
+    n_side = N // 2
+    npart = n_side ** 3
+    D.release_workspaces()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    ctx = PD.SlabContext(N, BOX)
+    x0, x1 = ctx.x_range
+    n_local = npart // world
+    # SURVEY section 8e: the synthetic configs generate the particles per slab, on their owner
+    pos = synth.uniform_device(n_local, BOX, 5000 + rank, dev, x_range=synth.slab_x_bounds(x0, x1, N, BOX))
+    nf = 1 if name == "config5" else 3
+    Ws = [None] if nf == 1 else [None, synth.weights_device(n_local, 1 + rank, dev),
+                                 synth.weights_device(n_local, 2 + rank, dev, kind="heavy")]
+    slabs = [ctx.new_slab() for _ in range(nf)]
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def step(times=None):
+        e = [ev()]
+        for s_, w in zip(slabs, Ws):
+            s_.zero_()
+            ctx.MA(pos, s_, "CIC", W=w, routed=True)
+        e.append(ev())
+        for s_ in slabs:
+            ctx.overdensity_(s_)
+        e.append(ev())
+        marks = {}
+        dks = [ctx.fft(s_, slot=i, marks=marks if i == 0 else None) for i, s_ in enumerate(slabs)]
+        e.append(ev())
+        o = ctx._spectra(dks, [PKL.MAS_function("CIC")] * nf, 0, nf == 1)
+        e.append(ev())
+        if times is not None:
+            torch.cuda.synchronize()
+            for k, (a, b) in zip(("zero+deposit+halo", "overdensity", "slab_fft", "bin+allreduce+finalise+d2h"),
+                                 zip(e[:-1], e[1:])):
+                times[k] = times.get(k, 0.0) + a.elapsed_time(b)
+            times["transpose_kernels_field0"] = times.get("transpose_kernels_field0", 0.0) + \
+                sum(a.elapsed_time(b) for a, b in marks.get("pairs", []))
+        return o
+
+    step()                                                   # warm-up: plans, workspaces, symmetric buffers
+    step()
+    barrier()
+    a = ev()
+    for _ in range(steps):
+        o = step()
+    b = ev()
+    barrier()
+    ms = maxr([a.elapsed_time(b)])[0] / steps
+    ctx.check_dropped()
+    times = {}
+    barrier()
+    step(times)
+    keys = sorted(times)
+    stage = dict(zip(keys, maxr([times[k] for k in keys])))
+    peak_gb = maxr([torch.cuda.max_memory_allocated() / 1e9])[0]
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak_hbm()
+    half = N * N * (N // 2 + 1)
+    dep_bytes = nf * (npart * 12 + 8 * N ** 3) / world + (nf - 1) * npart * 4 / world
+    sent = 8 * half / world * (world - 1) / world
+    nm = np.asarray(o["Nmodes3D"])
+    res = {"workload": cfg["label"] + ": " + cfg["text"] % (n_side, N), "gpus": world, "grid": N, "particles": npart,
+           "fields": nf, "ms_per_step": ms, "particles_per_s": npart / (ms * 1e-3), "steps": steps,
+           "stages_ms_max_over_ranks": {k: round(v, 3) for k, v in stage.items()},
+           "hbm_peak_allocated_GB_max_over_ranks": peak_gb,
+           "rooflines_per_gpu": {
+               "deposit": {"bound": "hbm", "achieved": dep_bytes / (stage["zero+deposit+halo"] * 1e-3) / 1e9, "peak": peak,
+                           "unit": "GB/s", "frac": dep_bytes / (stage["zero+deposit+halo"] * 1e-3) / 1e9 / peak,
+                           "algorithmic_bytes": dep_bytes, "note": "includes zeroing the slab and the halo exchange"},
+               "slab_fft": {"bound": "hbm+nvlink", "lower_bound_bytes": nf * (4 * N ** 3 + 8 * half) / world,
+                            "achieved": nf * (4 * N ** 3 + 8 * half) / world / (stage["slab_fft"] * 1e-3) / 1e9,
+                            "unit": "GB/s of the one-read-one-write lower bound"},
+               "transpose": {"bound": "nvlink", "achieved": sent / (stage["transpose_kernels_field0"] * 1e-3) / 1e9
+                             if stage.get("transpose_kernels_field0") else None, "peak": 770.0, "unit": "GB/s",
+                             "bytes_sent_per_gpu_per_field": sent},
+               "bin": {"bound": "hbm", "achieved": nf * 8 * half / world / (stage["bin+allreduce+finalise+d2h"] * 1e-3) / 1e9,
+                       "peak": peak, "unit": "GB/s",
+                       "frac": nf * 8 * half / world / (stage["bin+allreduce+finalise+d2h"] * 1e-3) / 1e9 / peak}},
+           "check": {"dropped": 0, "modes_counted": int(nm.sum()) + 1, "modes_expected": (N ** 3 - 8) // 2 + 8,
+                     "Pk_finite": bool(np.all(np.isfinite(np.asarray(o["Pk"]))))}}
+    if nf == 1:
+        P0 = np.asarray(o["Pk"])[:, 0, 0]
+        res["check"]["Pk0_mean_over_shot_noise"] = float(np.mean(P0[10:N // 4]) / (BOX ** 3 / npart))
+    del slabs, pos, Ws
+    return res
+
+
 def run_ours(args, wl, grid_n):
     import torch
     import torch.distributed as dist
@@ -517,6 +639,22 @@ def run_ours(args, wl, grid_n):
         ma_rates["workload"] = "BASELINE config 2 deposits: 512^3 uniform particles -> 512^3 grid, particles/s per MA call"
         del p2, w2
 
+    # ---- 8 GPUs: BASELINE configs 5 (4096^3 grid) and 4 (XPk of 3 fields at 2048^3) ride on the same launch ---------
+    extras = {}
+    if world == 8 and not args.no_extra and args.workload == "config3" and not args.grid:
+        del pos_host, W_host, slab
+        ctx._scratch.clear()
+        ctx._peer_slots.clear()
+        ctx._route = None
+        del ctx
+        for name in ("config5", "config4"):
+            try:
+                r = run_extra(name, world, rank, dev, 2)
+            except Exception as e:                           # never lose the main line to an extra workload
+                r = {"error": repr(e)[:300]}
+            if rank == 0:
+                extras[name] = r
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -584,11 +722,38 @@ def run_ours(args, wl, grid_n):
             "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
             "stages_ms": stages, "ma_particles_per_s": ma_rates, "check": check,
             "hbm_peak_allocated_GB_rank0": peak_hbm_gb, "particles_rank0": int(n_local)}
+    if extras:
+        line["extra_workloads"] = extras
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(wl)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extra_main(args):
+    """`--workload config4|config5`: the slab-only configs as the measured workload (multi-GPU launch required)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            emit({"impl": "reference", "unavailable": "configs 4/5 do not fit the host: see --workload config3"})
+        return
+    if world < 2:
+        raise SystemExit("%s is slab-sharded: launch with torchrun on >= %d GPUs" % (args.workload, EXTRA[args.workload]["min_world"]))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pyl_b200_nccl_%h_%p.log")
+    dist.init_process_group("nccl", device_id=dev)
+    res = run_extra(args.workload, world, rank, dev, max(1, args.steps), args.grid)
+    if rank == 0:
+        emit({"metric": "MA+Pk particles/sec, " + res["workload"], "value": res["particles_per_s"], "unit": "particles/s",
+              "n_gpus": world, "steps": res["steps"], "warmup": 2, "ms_per_step": res["ms_per_step"],
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": {"workload": res["workload"]}, "detail": res})
+    dist.destroy_process_group()
 
 
 def main():
@@ -597,12 +762,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + sorted(EXTRA))
+    ap.add_argument("--no-extra", action="store_true",
+                    help="at 8 GPUs the default run appends BASELINE configs 5 and 4 as `extra_workloads`; skip them")
     ap.add_argument("--grid", type=int, default=0, help="override the grid side / particle lattice side")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ma-rates", action="store_true", help="skip the config-2 per-scheme deposit rates")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.workload in EXTRA:
+        claim_stdout()
+        return run_extra_main(args)
     wl = WORKLOADS[args.workload]
     grid = args.grid or wl["grid"]
     WORKLOADS_GRID[0] = grid

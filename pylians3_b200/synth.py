@@ -40,9 +40,25 @@ def zeldovich_host(n_side, BoxSize, seed, rms_cells=1.5, slope=-1.5, kcut_frac=0
     return pos
 
 
+def slab_x_bounds(x0, x1, dims, BoxSize):
+    """Smallest and largest float32 x whose CIC cell floor(fl32(x * fl32(dims/BoxSize))) lies in planes [x0, x1):
+    positions generated "on their owner rank" must stay inside after the float32 product of the deposit, whose
+    rounding can carry a position one ulp below a slab boundary onto the next plane."""
+    inv = np.float32(dims) / np.float32(BoxSize)
+    lo = np.float32(x0 * (BoxSize / dims))
+    hi = np.float32(x1 * (BoxSize / dims))
+    while np.float32(lo * inv) < np.float32(x0):
+        lo = np.nextafter(lo, np.float32(np.inf))
+    hi = np.nextafter(hi, np.float32(-np.inf))
+    while np.float32(hi * inv) >= np.float32(x1):
+        hi = np.nextafter(hi, np.float32(-np.inf))
+    return float(lo), float(hi)
+
+
 def uniform_device(n, BoxSize, seed, device, x_range=None):
-    """Uniform positions on the device.  x_range=(lo,hi) restricts the first coordinate (per-slab
-    generation for multi-GPU runs: same density everywhere, particles already on their owner)."""
+    """Uniform positions on the device.  x_range=(lo,hi) restricts the first coordinate to the CLOSED interval
+    [lo, hi] (per-slab generation for multi-GPU runs: same density everywhere, particles already on their owner;
+    take the bounds from slab_x_bounds)."""
     g = torch.Generator(device=device)
     g.manual_seed(int(seed))
     pos = torch.rand((n, 3), generator=g, device=device, dtype=torch.float32)
@@ -50,7 +66,7 @@ def uniform_device(n, BoxSize, seed, device, x_range=None):
     if x_range is not None:
         lo, hi = x_range
         pos[:, 0].mul_((hi - lo) / float(BoxSize)).add_(lo)
-        pos[:, 0].clamp_(min=lo, max=float(np.nextafter(np.float32(hi), np.float32(lo))))
+        pos[:, 0].clamp_(min=lo, max=hi)
     return pos
 
 
