@@ -234,6 +234,11 @@ int pyl_route_scatter(int mas, const float *pos, const float *W, int64_t particl
                       int nranks, const int *x_offsets, void *const *peer_blocks, int64_t capacity, int64_t *lost,
                       pyl_stream_t stream);
 
+/* pyl_pk_bin keeps, per (device, dims, axis, ky window), a device copy of the field-independent sections of its
+ * result (mode counts, sum of |k| per shell) after the first call and skips their accumulation afterwards -- the
+ * counterpart of a cached FFT plan.  This frees the copies of the current device. */
+int pyl_pk_clear_cache(void);
+
 /* Slab-distributed spectra (no reference counterpart: the reference is one process): converts the
  * uint64 mode counts of an accumulator block (layout of pyl_pk_layout) to float64 in place -- exact below 2^53 -- so
  * that a single float64 SUM all-reduce covers the whole block; follow with pyl_pk_finalize(counts_are_f64 = 1). */

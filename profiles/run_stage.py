@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Tiny driver for ncu captures of one stage (kept small so ncu replays stay cheap).
 
-    python profiles/run_stage.py deposit CIC auto 512 [reps]
+    python profiles/run_stage.py deposit CIC auto 512 [reps] [uniform|zeldovich] [W]
     python profiles/run_stage.py pk 512 [axis] [reps]
     python profiles/run_stage.py step 512 [reps]          # the bench.py step: zero, MA(CIC), delta, Pk
     python profiles/run_stage.py shell 512 [reps]         # shell kernels (theta, dv, vv, xi) + mode passes
@@ -21,9 +21,10 @@ if what == "deposit":
     reps = int(sys.argv[5]) if len(sys.argv) > 5 else 2
     kind = sys.argv[6] if len(sys.argv) > 6 else "uniform"
     pos = synth.uniform_device(N ** 3, BOX, 1, dev) if kind == "uniform" else synth.zeldovich_device(N, BOX, 1, dev)
+    W = synth.weights_device(N ** 3, 1, dev) if len(sys.argv) > 7 and sys.argv[7] == "W" else None
     grid = torch.zeros((N, N, N), dtype=torch.float32, device=dev)
     for _ in range(reps):
-        MASL.MA(pos, grid, BOX, mas, mode=mode)
+        MASL.MA(pos, grid, BOX, mas, W, mode=mode)
     torch.cuda.synchronize()
     print("sum/N^3 =", float(grid.sum(dtype=torch.float64)) / N ** 3 / reps)
 elif what == "shell":

@@ -45,7 +45,10 @@ namespace pyl {
 
 constexpr int TX = 8, TY = 16, TZ = 32;         // tile extent in cells
 constexpr int TILE_CELLS = TX * TY * TZ;        // 4096
-constexpr int TNT = 256;                        // threads per tile CTA (8 warps)
+#ifndef PYL_TNT
+#define PYL_TNT 256
+#endif
+constexpr int TNT = PYL_TNT;                    // threads per tile CTA
 constexpr int SAMPLE = 8;                       // tile_count looks at one particle group in SAMPLE
 #ifndef PYL_PT
 #define PYL_PT 512

@@ -21,11 +21,20 @@
 //    before anything else happens, so the geometry math and the flushes are paid once per
 //    four modes.  The Hermitian-duplicate rule of the reference (:324-327) is applied per
 //    mode, so counts stay exact.
-//  * Flushes of the small, hot arrays (3D shells, 1D) go to NREP replicas selected by
-//    blockIdx to avoid same-address serialisation in L2; a second tiny kernel folds them.
+//  * SHELL WINDOW.  Measured (profiles/r2_pkbin.md): with per-lane red.global flushes the kernel was bound by the
+//    L2 atomic path -- 1% of its instructions, 58% of its stall samples -- because the 3D shell sums are few, hot
+//    addresses.  Every warp therefore owns a private window of PK_WBINS shells in shared memory.  A lane whose
+//    shell changes adds its register sums to the window with plain read-modify-writes; lanes of one warp that
+//    leave the SAME shell in the same step are neighbours (k grows with kz along the lanes) and take turns.  The
+//    window reaches global memory once per warp and walk segment, coalesced, through NREP replicas folded by a
+//    second tiny kernel.  The 2D (k_par,k_per) array is large and cold: its flushes stay direct.
 //
 // Counts are uint64, everything else float64, exactly as wide as the reference's accumulators.
 #include <math.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 
@@ -33,6 +42,8 @@ namespace pyl {
 
 constexpr int PK_BLOCK = 128;
 constexpr int PK_NREP = 8;
+constexpr int PK_WBINS = 96;          // shells a warp's private window covers: 31 (its kz span) + the walk segment
+constexpr int PK_MAX_SEG = 60;        // hence at most this many walk steps per segment
 
 template <int F>
 struct PkArgs {
@@ -51,7 +62,8 @@ struct PkArgs {
     int cross_imag;          // cross term: 0 = re_i re_j + im_i im_j (XPk), 1 = im_i re_j - re_i im_j (XPk_imag)
     int kmax_par1;           // kmax_par + 1
     int seg_len, nseg;       // walk range [0, m] cut into nseg segments of seg_len steps
-    long long T;             // threads per segment = n_other * nz
+    int nzp;                 // nz rounded up to a multiple of 32: a warp holds 32 consecutive kz of ONE row
+    long long T;             // threads per segment = n_other * nzp
     unsigned long long *out; // layout base (2D section is accumulated here directly)
     unsigned long long *rep; // NREP replicas of words [0, rep_words) (3D + 1D sections)
     long long rep_words;
@@ -74,31 +86,57 @@ __device__ __forceinline__ void red_u64(unsigned long long *base, long long word
 }
 
 // phase^2 of one mode, phase = atan2(re, |delta_k|) (Pk_library.pyx:358).  |delta_k| >= |re|,
-// so phase = sign(re) * atan(1/sqrt(1 + (im/re)^2)), evaluated in float32 (scale-free, no
-// overflow of re^2+im^2); the per-mode relative error ~1e-7 is far inside the 1e-4 bin tolerance.
+// so |phase| = atan(t) with t = 1/sqrt(1 + (im/re)^2) in (0,1], evaluated in float32 (scale-free, no
+// overflow of re^2+im^2).  atan on [0,1] is the 9-term odd polynomial of Abramowitz & Stegun 4.4.49
+// (|error| <= 2e-8, an order of magnitude inside float32 rounding): a third of libm atanf's instructions, which
+// were 13% of this kernel's.  The per-mode relative error ~1e-7 is far inside the 1e-4 bin tolerance.
 __device__ __forceinline__ double phase_sq(float re, float im) {
     if (re == 0.0f) return 0.0;
     const float q = __fdividef(im, re);
     const float t = rsqrtf(fmaf(q, q, 1.0f));
-    const float a = atanf(t);
+    const float u = t * t;
+    float p = 0.0028662257f;
+    p = fmaf(p, u, -0.0161657367f);
+    p = fmaf(p, u, 0.0429096138f);
+    p = fmaf(p, u, -0.0752896400f);
+    p = fmaf(p, u, 0.1065626393f);
+    p = fmaf(p, u, -0.1420889944f);
+    p = fmaf(p, u, 0.1999355085f);
+    p = fmaf(p, u, -0.3333314528f);
+    p = fmaf(p, u, 1.0f);
+    const float a = p * t;
     return (double)(a * a);
 }
 
 // Register cap: tried and dropped.  Built with __launch_bounds__(128, 8) (64 registers, 32 warps/SM instead of 24)
 // the kernel ran in the same 0.89 ms at 512^3 -- it is not bound by occupancy but by the LSU/L2 path of its
 // red.global flushes and table loads (profiles/r1_pkbin_hotlines.md).
-template <int F, bool PHASE>
+// GEOM = false: the mode counts and the sum of |k| per bin -- functions of the geometry alone -- are not
+// accumulated (the caller restores them from its per-geometry cache): a third fewer red.global per flush and no
+// float64 square root per step.
+template <int F, bool PHASE, bool GEOM>
 __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A) {
     constexpr int X = F * (F - 1) / 2;
     const int seg = blockIdx.y;
     const long long t = (long long)blockIdx.x * PK_BLOCK + threadIdx.x;
-    if (t >= A.T) return;
+    const int lane = threadIdx.x & 31;
 
     const int N = A.N, m = A.m, nz = A.nz;
     const bool even = A.even != 0;
-    const int oi = (int)(t / nz);          // index along the other axis (|k_o| or stored index)
-    const int kz = (int)(t - (long long)oi * nz);
+    int oi = (int)(t / A.nzp);             // index along the other axis (|k_o| or stored index)
+    int kz = (int)(t - (long long)oi * A.nzp);
+    // lanes past the end of a row (or of the thread range) stay in the loop for the warp-wide steps below but
+    // never load or accumulate anything
+    const bool active = (t < A.T) && (kz < nz);
+    if (!active) { oi = 0; kz = 0; }
     const bool zspecial = (kz == 0) || (kz == m && even);
+
+    // this warp's private shell window (see the header comment)
+    constexpr int NV = 3 * F + 3 * (F * (F - 1) / 2) + (PHASE ? 1 : 0);
+    extern __shared__ double pk_window[];
+    double *wwin = pk_window + (threadIdx.x >> 5) * (PK_WBINS * NV);
+    for (int i = lane; i < PK_WBINS * NV; i += 32) wwin[i] = 0.0;
+    __syncwarp();
 
     // ---- the (up to two) rows of the other axis handled by this thread ------------------
     int o_val[2], o_idx[2];
@@ -142,6 +180,8 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
     const int perp_base = par_is_walk ? base2 : (A.axis == other_axis ? kz * kz : a_abs * a_abs);
 
     int kidx = isqrt_fix(base2 + s0 * s0);
+    // shell of lane 0 at the first step of the segment: the base of the warp's window (k grows with kz and s)
+    const int bin0 = __shfl_sync(0xffffffffu, kidx, 0);
     int kper = isqrt_fix(perp_base + (par_is_walk ? 0 : s0 * s0));
     const int mm = m * m;
 
@@ -158,27 +198,60 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
 
     unsigned long long *rep = A.rep + (long long)(blockIdx.x % PK_NREP) * A.rep_words;
 
-    auto flush3 = [&]() {
-        if (cnt3 == 0) return;
-        red_u64(rep, A.o_Nm3D + cur3, cnt3);
-        red_f64(rep, A.o_k3D + cur3, ksum);
-#pragma unroll
-        for (int l = 0; l < 3; l++) {
-#pragma unroll
-            for (int f = 0; f < F; f++) red_f64(rep, A.o_Pk3D + ((long long)cur3 * 3 + l) * F + f, P3[l][f]);
-#pragma unroll
-            for (int x = 0; x < X; x++) red_f64(rep, A.o_PkX3D + ((long long)cur3 * 3 + l) * X + x, PX3[l][x]);
+    // `leaving`: this lane's shell changed (or the walk ended) and it holds sums for the shell it leaves.  Warp-wide.
+    auto flush3 = [&](bool leaving) {
+        leaving = leaving && cnt3 != 0;
+        const unsigned fl = __ballot_sync(0xffffffffu, leaving);
+        if (fl == 0) return;
+        if (GEOM && leaving) {                         // first call for a geometry only
+            red_u64(rep, A.o_Nm3D + cur3, cnt3);
+            red_f64(rep, A.o_k3D + cur3, ksum);
         }
-        if (PHASE) red_f64(rep, A.o_phase + cur3, ph3);
-        cnt3 = 0; ksum = 0.0; ph3 = 0.0;
+        // lanes leaving the same shell are neighbours: they take turns, in lane order
+        const int up = __shfl_up_sync(0xffffffffu, cur3, 1);
+        const bool head = leaving && !(lane > 0 && ((fl >> (lane - 1)) & 1u) && up == cur3);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+        const int turn = leaving ? lane - start : 0;
+        const int turns = __reduce_max_sync(0xffffffffu, turn);
+        const int wi = cur3 - bin0;
+        const bool inwin = wi >= 0 && wi < PK_WBINS;
+        double *cell = wwin + (inwin ? wi : 0) * NV;
+        for (int r = 0; r <= turns; r++) {
+            if (leaving && turn == r) {
+                if (inwin) {
 #pragma unroll
-        for (int f = 0; f < F; f++) P3[0][f] = P3[1][f] = P3[2][f] = 0.0;
+                    for (int l = 0; l < 3; l++) {
 #pragma unroll
-        for (int x = 0; x < X; x++) PX3[0][x] = PX3[1][x] = PX3[2][x] = 0.0;
+                        for (int f = 0; f < F; f++) cell[l * F + f] += P3[l][f];
+#pragma unroll
+                        for (int x = 0; x < X; x++) cell[3 * F + l * X + x] += PX3[l][x];
+                    }
+                    if (PHASE) cell[NV - 1] += ph3;
+                } else {                               // outside the window (cannot happen for seg_len <= PK_MAX_SEG)
+#pragma unroll
+                    for (int l = 0; l < 3; l++) {
+#pragma unroll
+                        for (int f = 0; f < F; f++) red_f64(rep, A.o_Pk3D + ((long long)cur3 * 3 + l) * F + f, P3[l][f]);
+#pragma unroll
+                        for (int x = 0; x < X; x++) red_f64(rep, A.o_PkX3D + ((long long)cur3 * 3 + l) * X + x, PX3[l][x]);
+                    }
+                    if (PHASE) red_f64(rep, A.o_phase + cur3, ph3);
+                }
+            }
+            __syncwarp();
+        }
+        if (leaving) {
+            cnt3 = 0; ksum = 0.0; ph3 = 0.0;
+#pragma unroll
+            for (int f = 0; f < F; f++) P3[0][f] = P3[1][f] = P3[2][f] = 0.0;
+#pragma unroll
+            for (int x = 0; x < X; x++) PX3[0][x] = PX3[1][x] = PX3[2][x] = 0.0;
+        }
     };
     auto flush2 = [&]() {
         if (cnt2 == 0) return;
-        red_u64(A.out, A.o_Nm2D + cur2, cnt2);
+        if (GEOM) red_u64(A.out, A.o_Nm2D + cur2, cnt2);
 #pragma unroll
         for (int f = 0; f < F; f++) red_f64(A.out, A.o_Pk2D + cur2 * F + f, P2[f]);
 #pragma unroll
@@ -191,7 +264,7 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
     };
     auto flush1 = [&]() {
         if (cnt1 == 0) return;
-        red_u64(rep, A.o_Nm1D + cur1, cnt1);
+        if (GEOM) red_u64(rep, A.o_Nm1D + cur1, cnt1);
 #pragma unroll
         for (int f = 0; f < F; f++) red_f64(rep, A.o_Pk1D + (long long)cur1 * F + f, P1[f]);
 #pragma unroll
@@ -230,7 +303,7 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
                 const int c = 2 * io + iw;
                 const int wv = iw ? -s : s;
                 const int widx = iw ? N - s : s;
-                const bool ok = o_ok[io] && (iw == 0 || wneg) && mode_ok(o_val[io], wv);
+                const bool ok = active && o_ok[io] && (iw == 0 || wneg) && mode_ok(o_val[io], wv);
                 if (ok) {
                     okmask |= 1u << c;
                     const long long r = row_of(o_idx[io], widx);
@@ -276,7 +349,8 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
         const long long i2 = (long long)A.kmax_par1 * kper + kpar;
         const int i1 = (k2 <= mm) ? kpar : -1;
 
-        if (kidx != cur3) { flush3(); cur3 = kidx; }
+        flush3(kidx != cur3);
+        cur3 = kidx;
         if (i2 != cur2) { flush2(); cur2 = i2; }
         if (i1 != cur1) { flush1(); cur1 = i1; }
 
@@ -319,12 +393,20 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
             }
 
             // ---- Legendre weights (:347-348, :374-376) ----------------------------------
-            const double k = sqrt((double)k2);
-            const double mu2 = (k2 == 0) ? 0.0 : (double)(kpar * kpar) / (double)k2;
+            // mu^2 = k_par^2 / k^2: reciprocal of the integer k^2 (exact in float32 up to 2^24) by one Newton step
+            // from the float32 seed -- relative error ~4e-15, a float64 division costs four times as much
+            double mu2 = 0.0;
+            if (k2 != 0) {
+                const double dk2 = (double)k2;
+                double r = (double)__frcp_rn((float)k2);
+                r = r * (2.0 - dk2 * r);
+                mu2 = (double)(kpar * kpar) * r;
+            }
             const double val1 = (3.0 * mu2 - 1.0) * 0.5;
             const double val2 = (35.0 * mu2 * mu2 - 30.0 * mu2 + 3.0) * 0.125;
 
-            cnt3 += mult; ksum += (double)mult * k;
+            cnt3 += mult;
+            if (GEOM) ksum += (double)mult * sqrt((double)k2);
             cnt2 += mult;
             if (PHASE) ph3 += PH;
 #pragma unroll
@@ -354,7 +436,22 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
 #pragma unroll
             for (int f = 0; f < F; f++) cur_v[c][f] = nxt_v[c][f];
     }
-    flush3(); flush2(); flush1();
+    flush3(true); flush2(); flush1();
+
+    // ---- the warp's window -> global replicas, consecutive lanes on consecutive shells ---------------------------
+    __syncwarp();
+    for (int i = lane; i < PK_WBINS * NV; i += 32) {
+        const int b = i % PK_WBINS, v = i / PK_WBINS;         // lanes run over shells for one value at a time
+        const double val = wwin[b * NV + v];
+        if (val != 0.0) {
+            const long long bin = bin0 + b;
+            long long word;
+            if (v < 3 * F) word = A.o_Pk3D + (bin * 3 + v / F) * F + v % F;
+            else if (v < 3 * F + 3 * X) word = A.o_PkX3D + (bin * 3 + (v - 3 * F) / (X > 0 ? X : 1)) * X + (v - 3 * F) % (X > 0 ? X : 1);
+            else word = A.o_phase + bin;
+            red_f64(rep, word, val);
+        }
+    }
 }
 
 // window table: win[f][i] = (x/sin x)^p, x = pi*i/N  (Pk_library.pyx:83-84; even in k)
@@ -517,6 +614,18 @@ static int mirrored_upper_rows(int dims, int ky_lo, int ny_lo, int *first) {
     return hi >= lo ? hi - lo + 1 : 0;
 }
 
+// ---- per-geometry cache of the field-independent sections ------------------------------------------------
+// Nmodes3D/1D/2D and the per-shell sum of |k| depend on (dims, axis, which ky rows the caller holds) only.  The
+// first call for a geometry accumulates them (GEOM kernel) and keeps a device copy; later calls run the lighter
+// kernel and copy the four sections back in -- like a cuFFT plan, the copy is made once per geometry and lives
+// until pyl_pk_clear_cache().
+struct GeomCache {
+    unsigned long long *data = nullptr;     // [k3D n3 | Nm3D n3 | Nm1D n1 | Nm2D n2]
+};
+using GeomKey = std::tuple<int, int, int, int, int, int>;   // device, dims, ky_lo, nky, mirrored, axis
+static std::map<GeomKey, GeomCache> g_geom;
+static std::mutex g_geom_mu;
+
 template <int F>
 static int launch_bin(const float *const *delta_k, const int *mas_index, int dims, int ky_lo,
                       int nky, int mirrored, int axis, int flags, void *out, void *ws, cudaStream_t stream) {
@@ -571,15 +680,19 @@ static int launch_bin(const float *const *delta_k, const int *mas_index, int dim
     A.axis = axis;
     A.cross_imag = (flags & PYL_PK_CROSS_IMAG) ? 1 : 0;
     A.kmax_par1 = L.kmax_par + 1;
-    A.T = (long long)A.n_other * nz;
+    A.nzp = (nz + 31) / 32 * 32;
+    A.T = (long long)A.n_other * A.nzp;
 
-    // cut the walk so that the grid has a few waves of warps even for small grids
+    // cut the walk so that the grid has a few waves of warps even for small grids, and so that a warp's shell
+    // window (PK_WBINS) covers its segment
     const long long warps_per_seg = (A.T + 31) / 32;
     const long long want_warps = (long long)sm_count() * 64;
     long long nseg = (want_warps + warps_per_seg - 1) / warps_per_seg;
     const int wlen = A.w_hi - A.w_lo;
     const long long max_seg = (wlen + 7) / 8;           // at least 8 steps per segment
     if (nseg > max_seg) nseg = max_seg;
+    const long long min_seg = (wlen + PK_MAX_SEG - 1) / PK_MAX_SEG;
+    if (nseg < min_seg) nseg = min_seg;
     if (nseg < 1) nseg = 1;
     A.seg_len = (int)((wlen + nseg - 1) / nseg);
     if (A.seg_len < 1) A.seg_len = 1;
@@ -591,15 +704,56 @@ static int launch_bin(const float *const *delta_k, const int *mas_index, int dim
     A.o_Nm1D = L.Nm1D; A.o_Pk1D = L.Pk1D; A.o_PkX1D = L.PkX1D;
     A.o_Nm2D = L.Nm2D; A.o_Pk2D = L.Pk2D; A.o_PkX2D = L.PkX2D;
 
+    int dev = 0;
+    PYL_CUDA_CHECK(cudaGetDevice(&dev));
+    const GeomKey key(dev, dims, ky_lo, nky, mirrored, axis);
+    const long long n3 = L.kmax + 1, n1 = L.kmax_par + 1, n2 = L.n2d;
+    unsigned long long *cached = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_geom_mu);
+        auto it = g_geom.find(key);
+        if (it != g_geom.end()) cached = it->second.data;
+    }
+
     if (A.T > 0 && A.nseg > 0) {
         dim3 grid((unsigned)((A.T + PK_BLOCK - 1) / PK_BLOCK), (unsigned)A.nseg);
-        if (want_phase) pk_bin_walk_kernel<F, true><<<grid, PK_BLOCK, 0, stream>>>(A);
-        else pk_bin_walk_kernel<F, false><<<grid, PK_BLOCK, 0, stream>>>(A);
-        PYL_LAUNCH_CHECK();
+        constexpr int X = F * (F - 1) / 2;
+        const size_t smem = (size_t)(PK_BLOCK / 32) * PK_WBINS * (3 * F + 3 * X + (want_phase ? 1 : 0)) * 8;
+        auto launch = [&](auto kernel) -> int {
+            if (smem > 48 * 1024)
+                PYL_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kernel<<<grid, PK_BLOCK, smem, stream>>>(A);
+            PYL_LAUNCH_CHECK();
+            return PYL_OK;
+        };
+        int st;
+        if (cached) st = want_phase ? launch(pk_bin_walk_kernel<F, true, false>) : launch(pk_bin_walk_kernel<F, false, false>);
+        else st = want_phase ? launch(pk_bin_walk_kernel<F, true, true>) : launch(pk_bin_walk_kernel<F, false, true>);
+        if (st != PYL_OK) return st;
     }
     pk_fold_replicas_kernel<<<(unsigned)((rep_words + 255) / 256), 256, 0, stream>>>(
         A.out, rep, rep_words, PK_NREP, L.Nm3D, (long long)L.kmax + 1, L.Nm1D, (long long)L.kmax_par + 1);
     PYL_LAUNCH_CHECK();
+
+    unsigned long long *o = A.out;
+    const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
+    if (cached) {
+        PYL_CUDA_CHECK(cudaMemcpyAsync(o + L.k3D, cached, (size_t)n3 * 8, d2d, stream));
+        PYL_CUDA_CHECK(cudaMemcpyAsync(o + L.Nm3D, cached + n3, (size_t)n3 * 8, d2d, stream));
+        PYL_CUDA_CHECK(cudaMemcpyAsync(o + L.Nm1D, cached + 2 * n3, (size_t)n1 * 8, d2d, stream));
+        PYL_CUDA_CHECK(cudaMemcpyAsync(o + L.Nm2D, cached + 2 * n3 + n1, (size_t)n2 * 8, d2d, stream));
+    } else {
+        unsigned long long *c = nullptr;
+        PYL_CUDA_CHECK(cudaMalloc(&c, (size_t)(2 * n3 + n1 + n2) * 8));
+        PYL_CUDA_CHECK(cudaMemcpyAsync(c, o + L.k3D, (size_t)n3 * 8, d2d, stream));
+        PYL_CUDA_CHECK(cudaMemcpyAsync(c + n3, o + L.Nm3D, (size_t)n3 * 8, d2d, stream));
+        PYL_CUDA_CHECK(cudaMemcpyAsync(c + 2 * n3, o + L.Nm1D, (size_t)n1 * 8, d2d, stream));
+        PYL_CUDA_CHECK(cudaMemcpyAsync(c + 2 * n3 + n1, o + L.Nm2D, (size_t)n2 * 8, d2d, stream));
+        PYL_CUDA_CHECK(cudaStreamSynchronize(stream));      // once per geometry: the copy is complete before it is published
+        std::lock_guard<std::mutex> lock(g_geom_mu);
+        if (g_geom.find(key) == g_geom.end()) g_geom[key].data = c;
+        else cudaFree(c);
+    }
     return PYL_OK;
 }
 
@@ -613,6 +767,22 @@ int pyl_pk_layout(int dims, int fields, pyl_pk_layout_t *layout) {
     PYL_REQUIRE(layout != nullptr, "pyl_pk_layout: layout is NULL");
     PYL_REQUIRE(dims > 0 && fields >= 1, "pyl_pk_layout: bad dims/fields");
     fill_layout(dims, fields, layout);
+    return PYL_OK;
+}
+
+int pyl_pk_clear_cache(void) {
+    int dev = 0;
+    PYL_CUDA_CHECK(cudaGetDevice(&dev));
+    PYL_CUDA_CHECK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lock(g_geom_mu);
+    for (auto it = g_geom.begin(); it != g_geom.end();) {
+        if (std::get<0>(it->first) == dev) {
+            cudaFree(it->second.data);
+            it = g_geom.erase(it);
+        } else {
+            ++it;
+        }
+    }
     return PYL_OK;
 }
 
