@@ -90,11 +90,16 @@ __device__ __forceinline__ void red_u64(unsigned long long *base, long long word
 // overflow of re^2+im^2).  atan on [0,1] is the 9-term odd polynomial of Abramowitz & Stegun 4.4.49
 // (|error| <= 2e-8, an order of magnitude inside float32 rounding): a third of libm atanf's instructions, which
 // were 13% of this kernel's.  The per-mode relative error ~1e-7 is far inside the 1e-4 bin tolerance.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ double phase_sq(float re, float im) {
     if (re == 0.0f) return 0.0;
-    const float q = __fdividef(im, re);
-    const float t = rsqrtf(fmaf(q, q, 1.0f));
-    const float u = t * t;
+    const float q = im * rcp_approx(re);
+    const float u = rcp_approx(fmaf(q, q, 1.0f));       // t^2, t = |re|/|delta_k|
     float p = 0.0028662257f;
     p = fmaf(p, u, -0.0161657367f);
     p = fmaf(p, u, 0.0429096138f);
@@ -104,8 +109,7 @@ __device__ __forceinline__ double phase_sq(float re, float im) {
     p = fmaf(p, u, 0.1999355085f);
     p = fmaf(p, u, -0.3333314528f);
     p = fmaf(p, u, 1.0f);
-    const float a = p * t;
-    return (double)(a * a);
+    return (double)(u * p * p);                           // (t * P(t^2))^2
 }
 
 // Register cap: tried and dropped.  Built with __launch_bounds__(128, 8) (64 registers, 32 warps/SM instead of 24)
@@ -114,8 +118,11 @@ __device__ __forceinline__ double phase_sq(float re, float im) {
 // GEOM = false: the mode counts and the sum of |k| per bin -- functions of the geometry alone -- are not
 // accumulated (the caller restores them from its per-geometry cache): a third fewer red.global per flush and no
 // float64 square root per step.
+#ifndef PYL_PK_MINB
+#define PYL_PK_MINB 1
+#endif
 template <int F, bool PHASE, bool GEOM>
-__global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A) {
+__global__ void __launch_bounds__(PK_BLOCK, PYL_PK_MINB) pk_bin_walk_kernel(const PkArgs<F> A) {
     constexpr int X = F * (F - 1) / 2;
     const int seg = blockIdx.y;
     const long long t = (long long)blockIdx.x * PK_BLOCK + threadIdx.x;
@@ -185,8 +192,7 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
     int kper = isqrt_fix(perp_base + (par_is_walk ? 0 : s0 * s0));
     const int mm = m * m;
 
-    int cur3 = -1, cur1 = -1;
-    long long cur2 = -1;
+    int cur3 = -1, cur1 = -1, cur2 = -1;
     unsigned int cnt3 = 0, cnt2 = 0, cnt1 = 0;
     double ksum = 0.0, ph3 = 0.0;
     double P3[3][F], P2[F], P1[F];
@@ -251,11 +257,11 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
     };
     auto flush2 = [&]() {
         if (cnt2 == 0) return;
-        if (GEOM) red_u64(A.out, A.o_Nm2D + cur2, cnt2);
+        if (GEOM) red_u64(A.out, A.o_Nm2D + (long long)cur2, cnt2);
 #pragma unroll
-        for (int f = 0; f < F; f++) red_f64(A.out, A.o_Pk2D + cur2 * F + f, P2[f]);
+        for (int f = 0; f < F; f++) red_f64(A.out, A.o_Pk2D + (long long)cur2 * F + f, P2[f]);
 #pragma unroll
-        for (int x = 0; x < X; x++) red_f64(A.out, A.o_PkX2D + cur2 * X + x, PX2[x]);
+        for (int x = 0; x < X; x++) red_f64(A.out, A.o_PkX2D + (long long)cur2 * X + x, PX2[x]);
         cnt2 = 0;
 #pragma unroll
         for (int f = 0; f < F; f++) P2[f] = 0.0;
@@ -277,7 +283,10 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
     };
 
     // ---- loads: the 2x2 sign combinations of (other, walk) at walk step s ----------------
-    // slot c = 2*io + iw.  ok[c] carries existence AND the Hermitian-duplicate rule.
+    // slot c = 2*io + iw.  The element of slot c at step s sits at off[c] + s*dstep[c] (affine in s: the walk index is
+    // s or N-s, and stored ky rows are contiguous in both halves of a mirrored slab), so the loop advances four
+    // offsets instead of rebuilding four 64-bit addresses.  ok carries existence AND the Hermitian-duplicate rule;
+    // it depends on s only at s = 0 and at the Nyquist step, which take the generic path.
     // o_index is a kx index (walk_y) or an already translated stored ky row (walk x)
     auto row_of = [&](int o_index, int w_index) -> long long {
         const int kxx = A.walk_y ? o_index : w_index;
@@ -293,24 +302,38 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
         }
         return true;
     };
-    auto fetch = [&](int s, float2 (&v)[4][F], unsigned &okmask) {
-        okmask = 0;
+    auto ok_mask = [&](int s) -> unsigned {
+        unsigned mask = 0;
         const bool wneg = (s != 0) && !(even && s == m);
 #pragma unroll
+        for (int io = 0; io < 2; io++)
+#pragma unroll
+            for (int iw = 0; iw < 2; iw++)
+                if (active && o_ok[io] && (iw == 0 || wneg) && mode_ok(o_val[io], iw ? -s : s)) mask |= 1u << (2 * io + iw);
+        return mask;
+    };
+    const int wstride = A.walk_y ? nz : A.nky * nz;
+    long long off[4];
+    {
+        const int sref = s0 > 0 ? s0 : 1;               // N - s is a stored index for s >= 1
+#pragma unroll
         for (int io = 0; io < 2; io++) {
+            off[2 * io] = row_of(o_idx[io], s0);
+            off[2 * io + 1] = row_of(o_idx[io], N - sref) + (long long)(sref - s0) * wstride;
+        }
+    }
+    const unsigned mask_mid = ok_mask(1 < m || !even ? 1 : 0);         // any interior step: s != 0, s != Nyquist
+    auto step_mask = [&](int s) -> unsigned {
+        return (s == 0 || (even && s == m)) ? ok_mask(s) : mask_mid;
+    };
+    auto fetch = [&](unsigned okmask, float2 (&v)[4][F]) {
 #pragma unroll
-            for (int iw = 0; iw < 2; iw++) {
-                const int c = 2 * io + iw;
-                const int wv = iw ? -s : s;
-                const int widx = iw ? N - s : s;
-                const bool ok = active && o_ok[io] && (iw == 0 || wneg) && mode_ok(o_val[io], wv);
-                if (ok) {
-                    okmask |= 1u << c;
-                    const long long r = row_of(o_idx[io], widx);
+        for (int c = 0; c < 4; c++) {
+            if (okmask & (1u << c)) {
 #pragma unroll
-                    for (int f = 0; f < F; f++) v[c][f] = __ldg(A.dk[f] + r);
-                }
+                for (int f = 0; f < F; f++) v[c][f] = __ldg(A.dk[f] + off[c]);
             }
+            off[c] += (c & 1) ? -wstride : wstride;
         }
     };
 
@@ -318,7 +341,8 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
     unsigned cur_ok = 0;
     double cur_w[F];                       // window factor of the walk coordinate, fetched one step ahead like the rows
     if (s0 < s1) {
-        fetch(s0, cur_v, cur_ok);
+        cur_ok = step_mask(s0);
+        fetch(cur_ok, cur_v);
 #pragma unroll
         for (int f = 0; f < F; f++) cur_w[f] = A.win[f][s0];
     }
@@ -332,21 +356,23 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
 #pragma unroll
         for (int f = 0; f < F; f++) nxt_w[f] = cur_w[f];
         if (s + 1 < s1) {
-            fetch(s + 1, nxt_v, nxt_ok);
+            nxt_ok = step_mask(s + 1);
+            fetch(nxt_ok, nxt_v);
 #pragma unroll
             for (int f = 0; f < F; f++) nxt_w[f] = A.win[f][s + 1];
         }
 
         // ---- geometry of this step (shared by the folded modes) -------------------------
+        // one step raises k by less than one: the shell index (and k_per) moves by at most one
         const int ss = s * s;
         const int k2 = base2 + ss;
-        while ((kidx + 1) * (kidx + 1) <= k2) kidx++;
+        if ((kidx + 1) * (kidx + 1) <= k2) kidx++;
         if (!par_is_walk) {
             const int p2 = perp_base + ss;
-            while ((kper + 1) * (kper + 1) <= p2) kper++;
+            if ((kper + 1) * (kper + 1) <= p2) kper++;
         }
         const int kpar = par_is_walk ? s : kpar_fixed;
-        const long long i2 = (long long)A.kmax_par1 * kper + kpar;
+        const int i2 = A.kmax_par1 * kper + kpar;
         const int i1 = (k2 <= mm) ? kpar : -1;
 
         flush3(kidx != cur3);
@@ -393,8 +419,8 @@ __global__ void __launch_bounds__(PK_BLOCK) pk_bin_walk_kernel(const PkArgs<F> A
             }
 
             // ---- Legendre weights (:347-348, :374-376) ----------------------------------
-            // mu^2 = k_par^2 / k^2: reciprocal of the integer k^2 (exact in float32 up to 2^24) by one Newton step
-            // from the float32 seed -- relative error ~4e-15, a float64 division costs four times as much
+            // mu^2 = k_par^2 / k^2: reciprocal of the integer k^2 by one Newton step from the float32 seed --
+            // relative error ~4e-15, a float64 division costs four times as much
             double mu2 = 0.0;
             if (k2 != 0) {
                 const double dk2 = (double)k2;
