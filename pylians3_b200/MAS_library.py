@@ -24,7 +24,7 @@ from . import _device as D
 from . import _lib as L
 from .errors import reference_exit
 
-__all__ = ["MA", "CIC_interp", "FLOAT_type",
+__all__ = ["MA", "CIC_interp", "FLOAT_type", "NGP", "CIC", "TSC", "PCS", "NGPW", "CICW", "TSCW", "PCSW",
            "NGPc3D", "NGPWc3D", "NGPc2D", "NGPWc2D", "CICc3D", "CICWc3D", "CICc2D", "CICWc2D",
            "TSCc3D", "TSCWc3D", "TSCc2D", "TSCWc2D", "PCSc3D", "PCSWc3D", "PCSc2D", "PCSWc2D"]
 
@@ -210,6 +210,33 @@ def CIC_interp(density, BoxSize, pos, den):
             den.copy_(den_d)
         else:
             den[...] = den_d.cpu().numpy()
+
+
+# ---- the per-scheme entry points, MAS_library.pyx:123-545 ------------------------------------------------
+# MASL.CIC(pos, number, BoxSize), MASL.CICW(pos, number, BoxSize, W), ...: cpdef functions of the reference that
+# MA dispatches to and that scripts also call directly.  Same arguments; the deposit accumulates into `number`.
+# Called directly on a plane they do NOT renormalise (the reference divides only inside MA, :84-110).
+def _scheme(mas, weighted):
+    def plane(pos, number):
+        # the reference's 2D form of these functions takes the (dims, dims, 1) view MA builds (:84)
+        return number[:, :, 0] if number.ndim == 3 and pos.shape[1] == 2 and number.shape[2] == 1 else number
+
+    if weighted:
+        def fn(pos, number, BoxSize, W):
+            MA(pos, plane(pos, number), BoxSize, mas, W, renormalize_2D=False)
+    else:
+        def fn(pos, number, BoxSize):
+            MA(pos, plane(pos, number), BoxSize, mas, None, renormalize_2D=False)
+    fn.__name__ = mas + ("W" if weighted else "")
+    fn.__doc__ = "MAS_library.%s (MAS_library.pyx): %s deposit%s, accumulated into `number`." % (
+        fn.__name__, mas, " with weights" if weighted else "")
+    return fn
+
+
+for _m in ("NGP", "CIC", "TSC", "PCS"):
+    globals()[_m] = _scheme(_m, False)
+    globals()[_m + "W"] = _scheme(_m, True)
+del _m
 
 
 # ---- MAS_c (OpenMP C core) wrappers, MAS_library.pyx:1305-1389 ---------------------------

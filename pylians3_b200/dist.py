@@ -199,24 +199,42 @@ class SlabContext:
             self._peer = self._setup_peer()
 
     def _setup_peer(self):
+        """Peer-memory plumbing (symmetric allocations mapped into every rank), or None -> NCCL all-to-all.  The
+        probe allocates and maps a small symmetric buffer right here, so that hosts without P2P, multi-node groups or
+        more ranks than the transpose kernel takes fall back now instead of failing inside fft(); the ranks agree
+        on the outcome (a rendezvous is collective)."""
+        state, why = None, ""
         try:
+            import warnings
             import torch.distributed._symmetric_memory as symm
             grp = self.group if self.group is not None else dist.group.WORLD
-            try:
-                symm.enable_symm_mem_for_group(grp.group_name)
-            except Exception:
-                pass
+            if self.world > 16:
+                raise RuntimeError("pyl_transpose_scatter takes at most 16 ranks")
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                try:
+                    symm.enable_symm_mem_for_group(grp.group_name)
+                except Exception:
+                    pass
+            probe = symm.empty(1024, dtype=torch.uint8, device=self.device)
+            symm.rendezvous(probe, grp)
             owner = torch.empty(self.dims, dtype=torch.int32)
             row = torch.empty(self.dims, dtype=torch.int32)
             for r, rows in enumerate(self.ky_rows):
                 idx = torch.tensor(rows, dtype=torch.long)
                 owner[idx] = r
                 row[idx] = torch.arange(len(rows), dtype=torch.int32)
-            return {"symm": symm, "group": grp, "owner": owner.to(self.device), "row": row.to(self.device),
-                    "nky": [len(r) for r in self.ky_rows]}
+            state = {"symm": symm, "group": grp, "owner": owner.to(self.device), "row": row.to(self.device),
+                     "nky": [len(r) for r in self.ky_rows]}
         except Exception as e:                                   # symmetric memory unusable: NCCL all-to-all
-            print("pylians3_b200.dist: peer-memory transpose unavailable (%s); using NCCL all-to-all" % e)
+            why = str(e)
+        ok = torch.tensor([1 if state is not None else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            if self.rank == 0:
+                print("pylians3_b200.dist: peer-memory transpose unavailable (%s); using NCCL all-to-all" % (why or "on another rank"))
             return None
+        return state
 
     def _peer_slot(self, slot):
         """Symmetric receive buffer number `slot` (one per field that must stay alive at the same time)."""

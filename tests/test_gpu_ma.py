@@ -406,3 +406,29 @@ def test_device_pipeline_redshift_space_to_pk(env, oracle):
     # spectra compared on the delta the device holds (deposit order noise is checked elsewhere)
     assert np.max(np.abs(grid.cpu().numpy() - ref)) < 1e-5 * np.max(np.abs(ref))
     check_pk(got, oracle.Pk(grid.cpu().numpy(), BOX, 2, "CIC", 1, False))
+
+
+def test_per_scheme_entry_points(env, oracle):
+    """MASL.CIC(pos, number, BoxSize) / MASL.PCSW(pos, number, BoxSize, W) ...: the reference's cpdef functions
+    (MAS_library.pyx:123-545), which existing scripts call directly."""
+    torch, MASL, _ = env
+    N = 32
+    pos, W = make_particles(5, 20000)
+    for mas in MAS:
+        for w in (None, W):
+            ref = np.zeros((N, N, N), np.float32)
+            oracle.MA(pos, ref, BOX, mas, w)
+            got = np.zeros((N, N, N), np.float32)
+            if w is None:
+                getattr(MASL, mas)(pos, got, BOX)
+            else:
+                getattr(MASL, mas + "W")(pos, got, BOX, w)
+            assert cell_err(got, ref) < TOL, (mas, w is not None)
+    # the (dims, dims, 1) plane view of the reference's 2D calls: no renormalisation outside MA
+    p2 = np.ascontiguousarray(pos[:, :2])
+    got = np.zeros((N, N, 1), np.float32)
+    MASL.CIC(p2, got, BOX)
+    ref = np.zeros((N, N), np.float32)
+    oracle.MA(p2, ref, BOX, "CIC", None, renormalize_2D=False)
+    assert cell_err(got[:, :, 0], ref) < TOL
+    assert abs(float(got.sum()) / (2.0 * len(p2)) - 1.0) < 1e-5          # every particle lands twice (:138-139)
