@@ -3,7 +3,8 @@
 
     python profiles/run_stage.py deposit CIC auto 512 [reps] [uniform|zeldovich] [W]
     python profiles/run_stage.py pk 512 [axis] [reps]
-    python profiles/run_stage.py step 512 [reps]          # the bench.py step: zero, MA(CIC), delta, Pk
+    python profiles/run_stage.py step 512 [reps]          # config 2 step: zero, MA(CIC), delta, Pk
+    python profiles/run_stage.py step3 1024 [reps]        # the bench.py step (config 3): Zel'dovich + W, PCS, Pk
     python profiles/run_stage.py shell 512 [reps]         # shell kernels (theta, dv, vv, xi) + mode passes
 """
 import os
@@ -43,6 +44,21 @@ elif what == "shell":
         PM._modes("power", cplx[1], cplx[2], N, 2, 4)
     torch.cuda.synchronize()
     print("xi Nm sum =", r["Nm"].sum())
+elif what == "step3":
+    # the bench.py step on BASELINE config 3: Zel'dovich particles + W, PCS, Pk incl. Pk2D
+    N = int(sys.argv[2])
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    pos = synth.zeldovich_device(N, BOX, 3, dev)
+    W = synth.weights_device(N ** 3, 3, dev)
+    torch.cuda.empty_cache()
+    grid = torch.zeros((N, N, N), dtype=torch.float32, device=dev)
+    for _ in range(reps):
+        grid.zero_()
+        MASL.MA(pos, grid, BOX, "PCS", W)
+        overdensity_(grid)
+        pk = PKL.Pk(grid, BOX, 0, "PCS", verbose=False)
+    torch.cuda.synchronize()
+    print("Pk0[:3] =", pk.Pk[:3, 0])
 elif what == "step":
     N = int(sys.argv[2])
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2

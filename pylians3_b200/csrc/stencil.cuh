@@ -35,13 +35,21 @@ __device__ __forceinline__ float cell_coordinate(float pos, float inv_cell_size)
     return __fmul_rn(pos, inv_cell_size);
 }
 
-// First (unwrapped) cell of the stencil along one axis.
+// First (unwrapped) cell of the stencil along one axis.  The reference promotes to float64 before it adds the
+// (half-)integer offset; a float32 -> float64 conversion is exact, so its results are functions of floor(dist) and of
+// the exact fraction dist - floor(dist), and are formed here without the float64 pipe:
+//   NGP  (int)(dist + 0.5)          = floor(dist) + [frac >= 0.5]        (MAS_library.pyx:290; dist >= 0)
+//   TSC  (int)floor(dist - 1.5) + 1 = floor(dist) - 1 + [frac >= 0.5]    (:392)
+//   PCS  (int)floor(dist - 2.0) + 1 = floor(dist) - 1                    (:485)
 template <int MAS>
 __device__ __forceinline__ int axis_base(float dist) {
-    if (MAS == PYL_MAS_NGP) return __double2int_rz(__dadd_rn((double)dist, 0.5));   // the 0.5 is a double in the reference
     if (MAS == PYL_MAS_CIC) return __float2int_rz(dist);
-    if (MAS == PYL_MAS_TSC) return __double2int_rd(__dadd_rn((double)dist, -1.5)) + 1;
-    return __double2int_rd(__dadd_rn((double)dist, -2.0)) + 1;
+    if (MAS == PYL_MAS_NGP && dist < 0.0f)      // outside the documented domain: C truncation, as the reference does
+        return __double2int_rz(__dadd_rn((double)dist, 0.5));
+    const int fl = __float2int_rd(dist);
+    if (MAS == PYL_MAS_PCS) return fl - 1;
+    const int up = __fsub_rn(dist, (float)fl) >= 0.5f ? 1 : 0;      // dist - floor(dist) is exact in float32
+    return MAS == PYL_MAS_NGP ? fl + up : fl - 1 + up;
 }
 
 // The S weights of the cells base, base+1, ... in the reference's own arithmetic (float64 where the reference

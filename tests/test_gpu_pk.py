@@ -311,3 +311,30 @@ def test_pk_full_size_properties(env):
     pk2 = PKL.Pk(grid, BOX, 0, "CIC", verbose=False)
     assert rel_err(pk2.Pk[:, 0], 4.0 * pk.Pk[:, 0], 1e-300) < 1e-12
     assert rel_err(pk2.Pk2D, 4.0 * pk.Pk2D, 1e-300) < 1e-12
+
+
+def test_full_size_512_against_the_compiled_reference(env):
+    """one 512^3 CIC + Pk run of BASELINE config 2's shape against the COMPILED, UNMODIFIED
+    reference (oracle/_ref) on identical host arrays: deposited grid 1e-5 per cell, mode counts bit-exact, spectra
+    inside the north_star bars.  About a minute of host time for the reference's serial loops."""
+    torch, MASL, PKL, _ = env
+    from oracle import ref_loader
+    if not ref_loader.have_ref():
+        pytest.skip("oracle/_ref (the compiled reference) is not present")
+    RM, RP = ref_loader.ref_MASL(), ref_loader.ref_PKL()
+    N = 512
+    pos = np.random.default_rng(2).random((N ** 3, 3), dtype=np.float32) * np.float32(BOX)
+    ref = np.zeros((N, N, N), np.float32)
+    RM.MA(pos, ref, BOX, "CIC")
+    grid = torch.zeros((N, N, N), dtype=torch.float32, device="cuda")
+    MASL.MA(torch.from_numpy(pos).cuda(), grid, BOX, "CIC")
+    got = grid.cpu().numpy()
+    assert abs(float(got.sum(dtype=np.float64)) / N ** 3 - 1.0) < 1e-5          # library/tests/test.py:30
+    assert rel_err(got, ref, floor=float(ref.mean())) < 1e-5
+    del pos, got
+    # both sides transform the SAME delta (the reference's grid), so only FFT + binning are compared here
+    ref /= np.mean(ref, dtype=np.float64)
+    ref -= 1.0
+    want = quiet(RP.Pk, ref, BOX, 0, "CIC", 8, False)
+    have = PKL.Pk(torch.from_numpy(ref).cuda(), BOX, 0, "CIC", verbose=False)
+    check_pk(have, want, phase_min_modes=64)
