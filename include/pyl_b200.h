@@ -158,6 +158,14 @@ int pyl_fft_slab_x(float *cols_k, int dims, int nky, void *ws, size_t ws_bytes,
 int pyl_transpose_scatter(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
                           const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
                           pyl_stream_t stream);
+/* The same transpose into receive buffers laid out (nky[r], dims, dims/2+1), and the 1D transforms along x of such a
+ * buffer (one strided cuFFT call per ky plane).  With x in the middle the x transforms stay inside one
+ * (dims, dims/2+1) plane per ky; with x outermost they touch a different 2 MB page per element at 4096^3. */
+int pyl_transpose_scatter_kymajor(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
+                                  const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
+                                  pyl_stream_t stream);
+size_t pyl_fft_slab_x_kymajor_workspace_bytes(int dims);
+int pyl_fft_slab_x_kymajor(float *cols_k, int dims, int nky, void *ws, size_t ws_bytes, pyl_stream_t stream);
 /* Unnormalised inverse c2r, (dims,dims,dims/2+1) complex64 -> (dims,dims,dims) float32, out of place; cuFFT may
  * OVERWRITE delta_k.  The reference's IFFT3Dr_f (Pk_library.pyx:149-163) returns the NORMALISED inverse (pyfftw
  * scales inverse transforms by 1/N^3 by default): callers follow with pyl_scale_inplace(delta, N^3, 1/N^3) or
@@ -209,6 +217,9 @@ size_t pyl_pk_bin_workspace_bytes(int dims, int fields);
 #define PYL_MAX_FIELDS 4
 #define PYL_PK_PHASE 1
 #define PYL_PK_CROSS_IMAG 2
+/* PYL_PK_KY_MAJOR: the fields are laid out (nky, dims, dims/2+1) -- stored ky row outermost, x in the middle -- as
+ * pyl_transpose_scatter_kymajor / pyl_fft_slab_x_kymajor produce them (slab-distributed spectra only). */
+#define PYL_PK_KY_MAJOR 4
 int pyl_pk_bin(const float *const *delta_k, int fields, const int *mas_index, int dims,
                int ky_lo, int nky, int axis, int want_phase, void *out, void *ws,
                size_t ws_bytes, pyl_stream_t stream);

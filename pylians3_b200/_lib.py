@@ -25,7 +25,7 @@ class PylError(RuntimeError):
 
 
 SHELL_KINDS = {"theta": 0, "dv": 1, "vv": 2, "expected": 3, "plane": 4, "xplane": 5, "xi": 6}
-PK_PHASE, PK_CROSS_IMAG = 1, 2
+PK_PHASE, PK_CROSS_IMAG, PK_KY_MAJOR = 1, 2, 4
 
 
 class ShellTable(ctypes.Structure):
@@ -71,6 +71,9 @@ PROTOTYPES = {
     "pyl_fft_slab_yz": (_i, [_vp, _vp, _i, _i, _vp, _sz, _vp]),
     "pyl_fft_slab_x": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
     "pyl_transpose_scatter": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i), _vp, _vp, _i, _i, _i, _i, _vp]),
+    "pyl_transpose_scatter_kymajor": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i), _vp, _vp, _i, _i, _i, _i, _vp]),
+    "pyl_fft_slab_x_kymajor_workspace_bytes": (_sz, [_i]),
+    "pyl_fft_slab_x_kymajor": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
     "pyl_fft_clear_plans": (_i, []),
     "pyl_pk_layout": (_i, [_i, _i, ctypes.POINTER(PkLayout)]),
     "pyl_pk_bin_workspace_bytes": (_sz, [_i, _i]),

@@ -45,6 +45,9 @@ namespace pyl {
 
 constexpr int TX = 8, TY = 16, TZ = 32;         // tile extent in cells
 constexpr int TILE_CELLS = TX * TY * TZ;        // 4096
+#ifndef PYL_P2_GROUP
+#define PYL_P2_GROUP 4
+#endif
 #ifndef PYL_TNT
 #define PYL_TNT 256
 #endif
@@ -287,8 +290,11 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
             // CTAs that run at the same time (neighbouring blockIdx) take chunks of DIFFERENT super-tiles: the
             // chunks of one super-tile all reserve runs on the same few hundred bucket cursors, and same-address
             // atomics serialise (the straight order made this pass as slow as its atomics)
+            // ... in groups of PYL_P2_GROUP consecutive chunks per super-tile, so that the runs written at the same time
+            // still fall into a limited set of buckets (L2 write combining)
             const unsigned rows = gridDim.x / g.nsuper;
-            const unsigned b = (blockIdx.x % g.nsuper) * rows + blockIdx.x / g.nsuper;
+            const unsigned grp = blockIdx.x / PYL_P2_GROUP, in_grp = blockIdx.x % PYL_P2_GROUP;
+            const unsigned b = (grp % g.nsuper) * rows + (grp / g.nsuper) * PYL_P2_GROUP + in_grp;
             // largest s with repl*spre[s] <= b: spre is non-decreasing, so it is (number of such s) - 1; the lanes
             // count in parallel (a binary search by one thread was ~10 dependent L2 round trips per CTA)
             unsigned below = 0;
@@ -784,7 +790,8 @@ static int run_tiled_w(const float *pos, float *number, const float *W, int64_t 
     PYL_LAUNCH_CHECK();
     a.out = w.buf2;
     // upper bound of the chunk count, rounded up to a multiple of nsuper (pass 2 walks it transposed)
-    const unsigned ctas2 = (unsigned)((w.slots / PP + (size_t)g.repl * g.nsuper + g.nsuper) / g.nsuper * g.nsuper);
+    const unsigned unit = g.nsuper * PYL_P2_GROUP;
+    const unsigned ctas2 = (unsigned)((w.slots / PP + (size_t)g.repl * g.nsuper + unit) / unit * unit);
     partition_kernel<MAS, WEIGHTED, 2><<<ctas2, PT, part_smem_bytes(1 << g.tps_shift), stream>>>(a, g);
     PYL_LAUNCH_CHECK();
     // bulk reductions need 16-byte aligned 128-byte rows: whole tiles along z and an aligned grid

@@ -4,6 +4,7 @@
 // Plans are created with auto-allocation OFF so that cuFFT's work area comes from the
 // caller's workspace (torch's caching allocator owns all memory).
 #include <cufft.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -13,7 +14,7 @@
 
 namespace pyl {
 
-enum PlanKind { PLAN_R2C_3D = 0, PLAN_R2C_YZ = 1, PLAN_C2C_X = 2, PLAN_C2R_3D = 3, PLAN_C2R_2D = 4 };
+enum PlanKind { PLAN_R2C_3D = 0, PLAN_R2C_YZ = 1, PLAN_C2C_X = 2, PLAN_C2R_3D = 3, PLAN_C2R_2D = 4, PLAN_C2C_XMID = 5 };
 
 struct Plan {
     cufftHandle handle = 0;
@@ -23,8 +24,10 @@ struct Plan {
 using PlanKey = std::tuple<int, int, int, int, int>;   // device, kind, dims, batch, nky (x plans: row stride)
 // slab transforms run in batches so that cuFFT's work area (which grows with the batch) stays bounded at
 // 4096^3-class grids: at most this many (y,z) planes / x columns per cufftExec call
-constexpr int YZ_BATCH = 16;
-constexpr int X_BATCH = 1 << 16;
+// (smaller batches were measured and lose: 4096^3 over 8 ranks, x transforms 83 ms at 65536 columns per call, 95 ms at
+// 2049; 2D transforms 38 ms at 16 planes per call, 44 ms at 1 -- profiles/r2_config5_pieces.md)
+static int yz_batch(int) { return 16; }
+static int x_batch(int) { return 1 << 16; }
 static std::map<PlanKey, Plan> g_plans;
 static std::mutex g_plans_mu;
 
@@ -84,6 +87,11 @@ static int get_plan(PlanKind kind, int dims, int extent, Plan *out, int nky = 0)
             long long n[2] = {N, N};
             r = cufftMakePlanMany64(p.handle, 2, n, nullptr, 1, N * N, nullptr, 1, N * nz, CUFFT_R2C,
                                     (long long)extent, &p.work);
+        } else if (kind == PLAN_C2C_XMID) {
+            // in-place 1D transforms along the FIRST axis of one (N, nz) plane: element stride nz, nz columns
+            long long n[1] = {N};
+            long long embed[1] = {N};
+            r = cufftMakePlanMany64(p.handle, 1, n, embed, nz, 1, embed, nz, 1, CUFFT_C2C, nz, &p.work);
         } else {
             // in-place 1D transforms along x of a (N, nky, nz) array: element stride nky*nz, `extent` columns
             long long n[1] = {N};
@@ -187,6 +195,7 @@ size_t pyl_fft_slab_workspace_bytes(int dims, int nx, int nky) {
     size_t need = 0;
     Plan p;
     if (nx > 0) {
+        const int YZ_BATCH = yz_batch(dims);
         const int full = nx < YZ_BATCH ? nx : YZ_BATCH, rest = nx % full;
         if (get_plan(PLAN_R2C_YZ, dims, full, &p) != PYL_OK) return (size_t)-1;
         need = p.work;
@@ -197,6 +206,7 @@ size_t pyl_fft_slab_workspace_bytes(int dims, int nx, int nky) {
     }
     if (nky > 0) {
         const long long cols = (long long)nky * (dims / 2 + 1);
+        const int X_BATCH = x_batch(dims);
         const int full = cols < X_BATCH ? (int)cols : X_BATCH, rest = (int)(cols % full);
         if (get_plan(PLAN_C2C_X, dims, full, &p, nky) != PYL_OK) return (size_t)-1;
         if (p.work > need) need = p.work;
@@ -214,6 +224,7 @@ int pyl_fft_slab_yz(const float *slab, float *slab_k, int dims, int nx, void *ws
     if (nx == 0) return PYL_OK;
     PYL_REQUIRE(slab != nullptr && slab_k != nullptr, "pyl_fft_slab_yz: NULL pointer");
     const long long plane_in = (long long)dims * dims, plane_out = (long long)dims * (dims / 2 + 1);
+    const int YZ_BATCH = yz_batch(dims);
     for (int x = 0; x < nx; x += YZ_BATCH) {
         const int b = nx - x < YZ_BATCH ? nx - x : YZ_BATCH;
         Plan p;
@@ -234,6 +245,7 @@ int pyl_fft_slab_x(float *cols_k, int dims, int nky, void *ws, size_t ws_bytes,
     PYL_REQUIRE(cols_k != nullptr, "pyl_fft_slab_x: NULL pointer");
     const long long cols = (long long)nky * (dims / 2 + 1);
     cufftComplex *c = reinterpret_cast<cufftComplex *>(cols_k);
+    const int X_BATCH = x_batch(dims);
     for (long long j = 0; j < cols; j += X_BATCH) {
         const int b = cols - j < X_BATCH ? (int)(cols - j) : X_BATCH;
         Plan p;
@@ -243,6 +255,28 @@ int pyl_fft_slab_x(float *cols_k, int dims, int nky, void *ws, size_t ws_bytes,
         if (st != PYL_OK) return st;
         PYL_CUFFT_CHECK(cufftExecC2C(p.handle, c + j, c + j, CUFFT_FORWARD));
     }
+    return PYL_OK;
+}
+
+size_t pyl_fft_slab_x_kymajor_workspace_bytes(int dims) {
+    if (dims <= 0) return 0;
+    Plan p;
+    if (get_plan(PLAN_C2C_XMID, dims, 0, &p) != PYL_OK) return (size_t)-1;
+    return p.work;
+}
+
+int pyl_fft_slab_x_kymajor(float *cols_k, int dims, int nky, void *ws, size_t ws_bytes, pyl_stream_t stream) {
+    PYL_REQUIRE(dims > 0 && nky >= 0, "pyl_fft_slab_x_kymajor: bad sizes");
+    if (nky == 0) return PYL_OK;
+    PYL_REQUIRE(cols_k != nullptr, "pyl_fft_slab_x_kymajor: NULL pointer");
+    Plan p;
+    int st = get_plan(PLAN_C2C_XMID, dims, 0, &p);
+    if (st != PYL_OK) return st;
+    st = bind(p, ws, ws_bytes, as_stream(stream));
+    if (st != PYL_OK) return st;
+    cufftComplex *c = reinterpret_cast<cufftComplex *>(cols_k);
+    const long long plane = (long long)dims * (dims / 2 + 1);
+    for (int j = 0; j < nky; j++) PYL_CUFFT_CHECK(cufftExecC2C(p.handle, c + j * plane, c + j * plane, CUFFT_FORWARD));
     return PYL_OK;
 }
 

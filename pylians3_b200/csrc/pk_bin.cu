@@ -59,6 +59,7 @@ struct PkArgs {
     int o_lo;                // fold: first |k_o| (0 unless the other axis is a mirrored ky window)
     int w_lo, w_hi;          // walk range |k_w| in [w_lo, w_hi)
     int axis;                // line of sight
+    int ky_major;            // fields are (nky, N, nz) -- stored ky row outermost -- instead of (N, nky, nz)
     int cross_imag;          // cross term: 0 = re_i re_j + im_i im_j (XPk), 1 = im_i re_j - re_i im_j (XPk_imag)
     int kmax_par1;           // kmax_par + 1
     int seg_len, nseg;       // walk range [0, m] cut into nseg segments of seg_len steps
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(PK_BLOCK, PYL_PK_MINB) pk_bin_walk_kernel(cons
     auto row_of = [&](int o_index, int w_index) -> long long {
         const int kxx = A.walk_y ? o_index : w_index;
         const int yrow = A.walk_y ? ystore(w_index) : o_index;
-        return ((long long)kxx * A.nky + yrow) * nz + kz;
+        return A.ky_major ? ((long long)yrow * N + kxx) * nz + kz : ((long long)kxx * A.nky + yrow) * nz + kz;
     };
     auto mode_ok = [&](int ov, int wv) -> bool {
         const int kx = A.walk_y ? ov : wv;
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(PK_BLOCK, PYL_PK_MINB) pk_bin_walk_kernel(cons
                 if (active && o_ok[io] && (iw == 0 || wneg) && mode_ok(o_val[io], iw ? -s : s)) mask |= 1u << (2 * io + iw);
         return mask;
     };
-    const int wstride = A.walk_y ? nz : A.nky * nz;
+    const int wstride = A.ky_major ? (A.walk_y ? N * nz : nz) : (A.walk_y ? nz : A.nky * nz);
     long long off[4];
     {
         const int sref = s0 > 0 ? s0 : 1;               // N - s is a stored index for s >= 1
@@ -705,6 +706,7 @@ static int launch_bin(const float *const *delta_k, const int *mas_index, int dim
     }
     A.axis = axis;
     A.cross_imag = (flags & PYL_PK_CROSS_IMAG) ? 1 : 0;
+    A.ky_major = (flags & PYL_PK_KY_MAJOR) ? 1 : 0;
     A.kmax_par1 = L.kmax_par + 1;
     A.nzp = (nz + 31) / 32 * 32;
     A.T = (long long)A.n_other * A.nzp;

@@ -24,13 +24,15 @@ struct TransposeArgs {
     const int *ky_owner;               // [N] rank owning global row ky
     const int *ky_row;                 // [N] stored row index of ky on its owner
     int N, nz, nx, x0;
+    int ky_major;                      // receive buffers are (nky[r], N, nz) instead of (N, nky[r], nz)
 };
 
 __global__ void __launch_bounds__(TR_THREADS) transpose_scatter_kernel(const TransposeArgs A) {
     const int ky = blockIdx.x, ix = blockIdx.y;
     const int r = __ldg(A.ky_owner + ky), j = __ldg(A.ky_row + ky);
     const float2 *src = A.src + ((int64_t)ix * A.N + ky) * A.nz;
-    float2 *dst = A.peer[r] + ((int64_t)(A.x0 + ix) * A.nky[r] + j) * A.nz;
+    float2 *dst = A.ky_major ? A.peer[r] + ((int64_t)j * A.N + (A.x0 + ix)) * A.nz
+                             : A.peer[r] + ((int64_t)(A.x0 + ix) * A.nky[r] + j) * A.nz;
     for (int kz = threadIdx.x; kz < A.nz; kz += TR_THREADS) dst[kz] = __ldg(src + kz);
 }
 
@@ -38,9 +40,9 @@ __global__ void __launch_bounds__(TR_THREADS) transpose_scatter_kernel(const Tra
 
 using namespace pyl;
 
-extern "C" int pyl_transpose_scatter(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
-                                     const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
-                                     pyl_stream_t stream) {
+static int transpose_scatter(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
+                             const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
+                             int ky_major, pyl_stream_t stream) {
     PYL_REQUIRE(nranks >= 1 && nranks <= TR_MAX_RANKS, "pyl_transpose_scatter: 1..16 ranks");
     PYL_REQUIRE(dims > 0 && nx >= 0 && x0 >= 0 && x0 + nx <= dims, "pyl_transpose_scatter: bad plane range");
     if (nx == 0) return PYL_OK;
@@ -55,8 +57,24 @@ extern "C" int pyl_transpose_scatter(const float *slab_k, void *const *peer_recv
         A.nky[r] = nky_of_rank[r];
     }
     A.ky_owner = ky_owner; A.ky_row = ky_row;
-    A.N = dims; A.nz = dims / 2 + 1; A.nx = nx; A.x0 = x0;
+    A.N = dims; A.nz = dims / 2 + 1; A.nx = nx; A.x0 = x0; A.ky_major = ky_major;
     transpose_scatter_kernel<<<dim3((unsigned)dims, (unsigned)nx), TR_THREADS, 0, as_stream(stream)>>>(A);
     PYL_LAUNCH_CHECK();
     return PYL_OK;
+}
+
+extern "C" int pyl_transpose_scatter(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
+                                     const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
+                                     pyl_stream_t stream) {
+    return transpose_scatter(slab_k, peer_recv, nky_of_rank, ky_owner, ky_row, dims, nx, x0, nranks, 0, stream);
+}
+
+// Same, into receive buffers laid out (nky[r], N, nz): the x axis in the MIDDLE.  The 1D transforms along x then
+// stride by one row (nz elements) inside one (N, nz) plane per ky instead of by nky*nz elements across the whole
+// buffer -- at 4096^3 over 8 ranks the latter touches a different 2 MB page for every x (TLB-bound: 83 ms for the
+// x transforms, profiles/r2_config5_pieces.md).
+extern "C" int pyl_transpose_scatter_kymajor(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
+                                             const int *ky_owner, const int *ky_row, int dims, int nx, int x0,
+                                             int nranks, pyl_stream_t stream) {
+    return transpose_scatter(slab_k, peer_recv, nky_of_rank, ky_owner, ky_row, dims, nx, x0, nranks, 1, stream);
 }

@@ -138,17 +138,32 @@ class DeviceOps:
         L.check(self.lib.pyl_fft_slab_x(D.ptr(cols), dims, nky, D.ptr(ws), need, self._s()), "pyl_fft_slab_x")
         return cols
 
-    def transpose_scatter(self, a, peer_ptrs, nky_of_rank, ky_owner, ky_row, dims, x0):
-        """Rows of the local (nx, dims, nz) stage-1 output -> receive buffers of their owner ranks (peer stores)."""
+    def transpose_scatter(self, a, peer_ptrs, nky_of_rank, ky_owner, ky_row, dims, x0, ky_major=False):
+        """Rows of the local (nx, dims, nz) stage-1 output -> receive buffers of their owner ranks (peer stores).
+        ky_major: the receive buffers are (nky, dims, nz) instead of (dims, nky, nz)."""
         P = len(peer_ptrs)
         ptrs = (ctypes.c_void_p * P)(*[int(p) for p in peer_ptrs])
         nky = (ctypes.c_int * P)(*[int(n) for n in nky_of_rank])
-        L.check(self.lib.pyl_transpose_scatter(D.ptr(a), ptrs, nky, D.ptr(ky_owner), D.ptr(ky_row), dims,
-                                               a.shape[0], int(x0), P, self._s()), "pyl_transpose_scatter")
+        fn = self.lib.pyl_transpose_scatter_kymajor if ky_major else self.lib.pyl_transpose_scatter
+        L.check(fn(D.ptr(a), ptrs, nky, D.ptr(ky_owner), D.ptr(ky_row), dims, a.shape[0], int(x0), P, self._s()),
+                "pyl_transpose_scatter")
+
+    def fft_x_kymajor_(self, cols, dims):
+        """In-place 1D transforms along x of a (nky, dims, nz) complex64 array (x is the MIDDLE axis)."""
+        need = self.lib.pyl_fft_slab_x_kymajor_workspace_bytes(dims)
+        if need == ctypes.c_size_t(-1).value:
+            L.check(-3, "pyl_fft_slab_x_kymajor_workspace_bytes")
+        ws = D.workspace(need, cols.device, "fft")
+        L.check(self.lib.pyl_fft_slab_x_kymajor(D.ptr(cols), dims, cols.shape[0], D.ptr(ws), need, self._s()),
+                "pyl_fft_slab_x_kymajor")
+        return cols
 
     def bin(self, dk_list, mas_index, dims, axis, want_phase, ky_lo, ny_lo):
-        """Bins the mirrored slab (rows as in mirrored_rows(dims, ky_lo, ny_lo))."""
-        return PKL.bin_device(dk_list, mas_index, dims, axis, want_phase, ky_lo, ny_lo, mirrored=True)
+        """Bins the mirrored slab (rows as in mirrored_rows(dims, ky_lo, ny_lo)).  A field whose FIRST axis is not
+        dims long is laid out (nky, dims, nz) -- what the peer-memory transpose produces."""
+        ky_major = dk_list[0].shape[0] != dims or getattr(dk_list[0], "_pyl_ky_major", False)
+        return PKL.bin_device(dk_list, mas_index, dims, axis, want_phase, ky_lo, ny_lo, mirrored=True,
+                              flags=L.PK_KY_MAJOR if ky_major else 0)
 
 
 class _Result:
@@ -466,7 +481,7 @@ class SlabContext:
                     side.wait_event(ready)
                     ea = mark(stream=side)
                     self.ops.transpose_scatter(a, ptrs, self._peer["nky"], self._peer["owner"], self._peer["row"], N,
-                                               self.x_range[0] + b0)
+                                               self.x_range[0] + b0, ky_major=True)
                     eb = mark(stream=side)
                     if ea is not None:
                         marks.setdefault("pairs", []).append((ea, eb))
@@ -475,7 +490,10 @@ class SlabContext:
             main.wait_stream(side)
             hdl.barrier(channel=0)                                     # every row has landed
             mark("t1")
-            return self.ops.fft_x_(buf[:N * self.nky * nz].view(N, self.nky, nz), N)
+            # (nky, N, nz): x in the middle, so that the x transforms stay inside one plane per ky row
+            out = self.ops.fft_x_kymajor_(buf[:N * self.nky * nz].view(self.nky, N, nz), N)
+            out._pyl_ky_major = True                                   # nky == N cannot happen for P > 1, but be explicit
+            return out
         a = self.ops.fft_yz(slab, N)                                   # (nx, N, nz)
         send = self._buf("send", (self.nx * N * nz,), a.dtype)
         send_sizes, off = [], 0                                        # (complex64 on the GPU path)

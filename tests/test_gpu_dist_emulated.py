@@ -70,10 +70,16 @@ def test_rank_by_rank_emulation(oracle, P, N, mas):
         want = full[:, torch.tensor(ky_rows[r], device=dev), :]
         assert float((cols[r] - want).abs().max()) <= 2e-5 * float(full.abs().max())
 
-    for axis in (0, 1, 2):
+    # the peer-memory transpose delivers (nky, N, nz) -- x in the middle -- and the x transforms run per ky plane
+    cols_ky = [ops.fft_x_kymajor_(a[:, torch.tensor(ky_rows[r], device=dev), :].permute(1, 0, 2).contiguous(), N)
+               for r in range(P)]
+    for r in range(P):
+        assert float((cols_ky[r] - cols[r].permute(1, 0, 2)).abs().max()) <= 2e-5 * float(full.abs().max())
+
+    for axis, use in ((0, cols), (1, cols), (2, cols), (0, cols_ky), (1, cols_ky), (2, cols_ky)):
         acc, lay = None, None
         for r in range(P):
-            out, lay = ops.bin([cols[r]], [PKL.MAS_function(mas)], N, axis, True, ylo_offs[r], ylo_sizes[r])
+            out, lay = ops.bin([use[r]], [PKL.MAS_function(mas)], N, axis, True, ylo_offs[r], ylo_sizes[r])
             L.check(lib.pyl_pk_counts_to_f64(D.ptr(out), N, 1, D.stream_ptr(dev)), "pyl_pk_counts_to_f64")
             f = out.view(torch.float64)
             acc = f.clone() if acc is None else acc + f                     # the all-reduce
