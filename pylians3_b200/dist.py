@@ -281,6 +281,11 @@ class SlabContext:
 
     # ---- helpers ----------------------------------------------------------------------------------
     FFT_BATCH_PLANES = 16       # x-planes per 2D-FFT / transpose batch of the pipelined slab FFT
+    # From this grid size on the transposed spectrum is laid out (nky, N, nz), x in the middle: the x transforms then
+    # run per ky plane instead of striding across the whole buffer.  Measured per GPU (profiles/r2_config5_pieces.md):
+    # 4096^3 over 8 ranks 31 vs 83 ms, 2048^3 4.2 vs 5.0 ms; at 1024^3 the per-plane calls are launch-bound and the
+    # x-outermost layout wins (0.33 vs 1.06 ms).
+    KY_MAJOR_MIN_DIMS = 2048
     GHOST_PLANES = 3            # PCS: the stencil reaches three planes above the particle's first plane
 
     def new_slab(self):
@@ -463,6 +468,7 @@ class SlabContext:
             # owners of its ky rows (side stream, one kernel storing over NVLink).  Two batch buffers replace the
             # slab-sized stage-1 array.
             buf, hdl, ptrs = self._peer_slot(slot)
+            ky_major = N >= self.KY_MAJOR_MIN_DIMS
             nb = max(1, min(self.nx, self.FFT_BATCH_PLANES))
             ring = self._buf("fft_ring", (2, nb, N, nz), torch.complex64)
             main = torch.cuda.current_stream(self.device)
@@ -481,7 +487,7 @@ class SlabContext:
                     side.wait_event(ready)
                     ea = mark(stream=side)
                     self.ops.transpose_scatter(a, ptrs, self._peer["nky"], self._peer["owner"], self._peer["row"], N,
-                                               self.x_range[0] + b0, ky_major=True)
+                                               self.x_range[0] + b0, ky_major=ky_major)
                     eb = mark(stream=side)
                     if ea is not None:
                         marks.setdefault("pairs", []).append((ea, eb))
@@ -490,6 +496,8 @@ class SlabContext:
             main.wait_stream(side)
             hdl.barrier(channel=0)                                     # every row has landed
             mark("t1")
+            if not ky_major:
+                return self.ops.fft_x_(buf[:N * self.nky * nz].view(N, self.nky, nz), N)
             # (nky, N, nz): x in the middle, so that the x transforms stay inside one plane per ky row
             out = self.ops.fft_x_kymajor_(buf[:N * self.nky * nz].view(self.nky, N, nz), N)
             out._pyl_ky_major = True                                   # nky == N cannot happen for P > 1, but be explicit

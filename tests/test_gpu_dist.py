@@ -23,6 +23,8 @@ def _free_port():
 
 def _worker(rank, world, port, N, q, transpose="peer"):
     try:
+        ky_major = transpose == "peer-kymajor"
+        transpose = "peer" if ky_major else transpose
         os.environ["PYL_TRANSPOSE"] = transpose
         import torch
         import torch.distributed as dist
@@ -36,6 +38,8 @@ def _worker(rank, world, port, N, q, transpose="peer"):
         from pylians3_b200 import dist as PD
         from oracle import cpu as O
         ctx = PD.SlabContext(N, BOX)
+        if ky_major:
+            ctx.KY_MAJOR_MIN_DIMS = 0           # the (nky, N, nz) spectrum layout of the large grids, forced here
         assert (ctx._peer is not None) == (transpose == "peer"), "peer-memory transpose not active"
         pos, W = make_particles(77, 4 * N ** 3, True)
         mine = slice(rank, None, world)
@@ -81,11 +85,13 @@ def _worker(rank, world, port, N, q, transpose="peer"):
         q.put((rank, "fail", traceback.format_exc()))
 
 
-@pytest.mark.parametrize("world,N,transpose", [(2, 64, "peer"), (2, 45, "peer"), (2, 45, "nccl"), (4, 64, "peer"),
-                                               (4, 45, "peer"), (8, 64, "peer")])
+@pytest.mark.parametrize("world,N,transpose", [(2, 64, "peer"), (2, 45, "peer"), (2, 45, "nccl"), (2, 64, "peer-kymajor"),
+                                               (4, 64, "peer"), (4, 45, "peer-kymajor"), (8, 64, "peer"),
+                                               (8, 72, "peer-kymajor")])
 def test_multi_gpu_slab_pipeline(oracle, world, N, transpose):
     """transpose="peer": the slab-FFT transpose is one kernel storing into the owners' symmetric receive buffers
-    over NVLink (pyl_transpose_scatter); "nccl": pack + all_to_all_single."""
+    over NVLink (pyl_transpose_scatter); "peer-kymajor": the same with the (nky, N, nz) layout used from 2048^3 on;
+    "nccl": pack + all_to_all_single."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
