@@ -387,6 +387,8 @@ def run_extra(name, world, rank, dev, steps, grid_override=0):
                 times[k] = times.get(k, 0.0) + a.elapsed_time(b)
             times["transpose_kernels_field0"] = times.get("transpose_kernels_field0", 0.0) + \
                 sum(a.elapsed_time(b) for a, b in marks.get("pairs", []))
+            if "t0" in marks and "t1" in marks:
+                times["fft_yz+transpose_field0(pipelined)"] = marks["t0"].elapsed_time(marks["t1"])
         return o
 
     step()                                                   # warm-up: plans, workspaces, symmetric buffers

@@ -33,7 +33,21 @@ __global__ void __launch_bounds__(TR_THREADS) transpose_scatter_kernel(const Tra
     const float2 *src = A.src + ((int64_t)ix * A.N + ky) * A.nz;
     float2 *dst = A.ky_major ? A.peer[r] + ((int64_t)j * A.N + (A.x0 + ix)) * A.nz
                              : A.peer[r] + ((int64_t)(A.x0 + ix) * A.nky[r] + j) * A.nz;
-    for (int kz = threadIdx.x; kz < A.nz; kz += TR_THREADS) dst[kz] = __ldg(src + kz);
+    // four loads in flight per thread before the first peer store: a store over NVLink costs microseconds of latency,
+    // and with one element per iteration the row (16 KB at 4096^3) was latency-bound
+    for (int kz0 = threadIdx.x; kz0 < A.nz; kz0 += 4 * TR_THREADS) {
+        float2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int kz = kz0 + u * TR_THREADS;
+            if (kz < A.nz) v[u] = __ldg(src + kz);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int kz = kz0 + u * TR_THREADS;
+            if (kz < A.nz) dst[kz] = v[u];
+        }
+    }
 }
 
 }  // namespace pyl
