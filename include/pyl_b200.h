@@ -327,6 +327,14 @@ size_t pyl_modes_workspace_bytes(int dims);
 int pyl_modes_deconvolve(float *delta_k, int dims, int mas_index, void *ws, size_t ws_bytes, pyl_stream_t stream);
 int pyl_modes_power(float *a_k, const float *b_k, int dims, int mas_a, int mas_b, void *ws, size_t ws_bytes,
                     pyl_stream_t stream);
+/* XXi_projected (Pk_library.pyx:2684-2789), the 2D forms: pyl_modes_power_2d deconvolves EVERY stored mode of two
+ * (dims, dims/2+1) half-spectra (the reference's 2D loop has no duplicate-mode rule, :2735-2758) and leaves
+ * a_k = (re_a*re_b + im_a*im_b, 0) in float32; pyl_radial_bin_2d bins every cell of a (dims, dims) float32 image
+ * (times `scale`, a float32 product) by int(sqrt(kx^2+ky^2)) (:2776-2787) into out = [sum |k| (float64) |
+ * count (uint64) | sum value (float64)], each kmax+1 = int((dims/2)*sqrt(2))+1 words. */
+int pyl_modes_power_2d(float *a_k, const float *b_k, int dims, int mas_a, int mas_b, void *ws, size_t ws_bytes,
+                       pyl_stream_t stream);
+int pyl_radial_bin_2d(const float *image, int dims, float scale, void *out, pyl_stream_t stream);
 /* a_k[i] *= b_k[i], complex64 (smoothing_library.pyx:227-232, field_k * filter_k) */
 int pyl_cmul_inplace(float *a_k, const float *b_k, int64_t n_complex, pyl_stream_t stream);
 /* Smoothing filters placed on a grid (smoothing_library.pyx:37-100 FT_filter, :141-191 FT_filter_2D), axes = 3 | 2:

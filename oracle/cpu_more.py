@@ -314,6 +314,48 @@ class XXi:
         _xi_finish(self, ifft3d_c2r(d1, grid, threads), grid, BoxSize, axis)
 
 
+class XXi_projected:
+    """Pk_library.pyx:2684-2789: projected cross-correlation function of two images.  Every stored mode of the 2D
+    half-spectrum is deconvolved (no duplicate-mode rule here, :2735-2758), the product re1*re2 + im1*im2 is formed
+    in float32, the inverse transform is the normalised 2D c2r and every cell of the (grid, grid) result is binned
+    by int(sqrt(kx^2 + ky^2)) (:2776-2787).  Attributes: r_p, xi_p, Nmodes_p (bin 0 dropped)."""
+
+    def __init__(self, delta1, delta2, BoxSize, MAS=["CIC", "CIC"], threads=1):
+        BoxSize = float(np.float32(BoxSize))
+        grid = delta1.shape[0]
+        middle = grid // 2
+        if grid != delta2.shape[0]:
+            raise Exception("grid sizes differ!!!")
+        kmax = int((grid // 2) * np.sqrt(2))
+        i1, i2 = _c.MAS_function(MAS[0]), _c.MAS_function(MAS[1])
+        d1, d2 = fft2d_r2c(delta1, threads), fft2d_r2c(delta2, threads)
+        prefact = np.pi / grid
+        kx = _signed(grid)[:, None]
+        ky = np.arange(middle + 1)[None, :]
+
+        def corr(k, p):
+            x = prefact * k
+            with np.errstate(invalid="ignore", divide="ignore"):
+                return np.where(k == 0, 1.0, (x / np.sin(x)) ** p)
+        f1 = (corr(kx, i1) * corr(ky, i1)).astype(np.float32)          # cdef float MAS_factor (:2697)
+        f2 = (corr(kx, i2) * corr(ky, i2)).astype(np.float32)
+        a = (d1 * f1).astype(np.complex64)
+        b = (d2 * f2).astype(np.complex64)
+        prod = (a.real * b.real + a.imag * b.imag).astype(np.float32)  # float32 products and sum (:2752-2757)
+        xi_grid = _sfft.irfft2(prod.astype(np.complex64), s=(grid, grid)).astype(np.float32)
+        kxf = _signed(grid)[:, None]
+        kyf = _signed(grid)[None, :]
+        k = np.sqrt((kxf * kxf + kyf * kyf).astype(np.float64))
+        idx = k.astype(np.int64).ravel()
+        r_p = np.bincount(idx, weights=k.ravel(), minlength=kmax + 1)[1:]
+        xi_p = np.bincount(idx, weights=xi_grid.astype(np.float64).ravel(), minlength=kmax + 1)[1:]
+        Nm = np.bincount(idx, minlength=kmax + 1).astype(np.float64)[1:]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            self.r_p = (r_p / Nm) * (BoxSize * 1.0 / grid)
+            self.xi_p = (xi_p / Nm) * (1.0 / grid ** 2)
+        self.Nmodes_p = Nm
+
+
 def field_smoothing(field, filter_k, threads=1):
     """smoothing_library.pyx:215-235: IFFT(FFT(field) * filter_k), complex64 product."""
     dims = field.shape[0]

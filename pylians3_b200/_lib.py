@@ -91,6 +91,8 @@ PROTOTYPES = {
     "pyl_modes_workspace_bytes": (_sz, [_i]),
     "pyl_modes_deconvolve": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
     "pyl_modes_power": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "pyl_modes_power_2d": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "pyl_radial_bin_2d": (_i, [_vp, _i, _f, _vp, _vp]),
     "pyl_cmul_inplace": (_i, [_vp, _vp, _i64, _vp]),
     "pyl_mul_one_plus": (_i, [_vp, _vp, _i64, _vp]),
     "pyl_filter_fill": (_i, [_i, _vp, _i, _i, _f, _f, _f, _f, _vp]),

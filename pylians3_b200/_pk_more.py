@@ -25,7 +25,7 @@ from . import Pk_library as _P
 from .errors import reference_exit
 
 __all__ = ["frequencies_2D", "check_number_modes_2D", "IFFT3Dr_f", "FFT2Dr_f", "Pk_plane", "XPk_imag", "XPk_plane",
-           "Pk_theta", "XPk_dv", "XPk_vv", "XPk_2D", "correct_MAS", "expected_Pk", "Xi", "XXi", "XXi_multi", "field_smoothing"]
+           "Pk_theta", "XPk_dv", "XPk_vv", "XPk_2D", "correct_MAS", "expected_Pk", "Xi", "XXi", "XXi_multi", "XXi_projected", "field_smoothing"]
 
 
 def frequencies_2D(BoxSize, dims):
@@ -478,6 +478,53 @@ class XXi:
         start2 = time.time()
         _xi_results(self, d1, grid, BoxSize, axis)
         print("Time to complete loop = %.2f" % (time.time() - start2))
+        print("Time taken = %.2f seconds" % (time.time() - start))
+
+
+class XXi_projected:
+    """Projected cross-correlation function of two images (Pk_library.pyx:2684-2789).  Attributes: r_p, xi_p,
+    Nmodes_p.  2D r2c of both images -> pyl_modes_power_2d -> 2D c2r -> pyl_radial_bin_2d, all on the device."""
+
+    def __init__(self, delta1, delta2, BoxSize, MAS=["CIC", "CIC"], threads=1):
+        start = time.time()
+        print("\nComputing correlation function of the field...")
+        D.require_cuda()
+        BoxSize = float(np.float32(BoxSize))
+        grid = delta1.shape[0]
+        if grid != delta2.shape[0]:
+            raise Exception("grid sizes differ!!!")
+        dev = D.pick_device(delta1, delta2)
+        lib = L.load()
+        d1 = fft2d_r2c_device(_as_image(delta1, dev, "delta1"))
+        d2 = fft2d_r2c_device(_as_image(delta2, dev, "delta2"))
+        with torch.cuda.device(dev):
+            need = lib.pyl_modes_workspace_bytes(int(grid))
+            ws = D.workspace(need, dev, "modes")
+            L.check(lib.pyl_modes_power_2d(D.ptr(d1), D.ptr(d2), int(grid), _P.MAS_function(MAS[0]),
+                                           _P.MAS_function(MAS[1]), D.ptr(ws), need, D.stream_ptr(dev)),
+                    "pyl_modes_power_2d")
+            del d2
+            xi_grid = torch.empty((grid, grid), dtype=torch.float32, device=dev)
+            need = lib.pyl_fft2d_c2r_workspace_bytes(int(grid))
+            if need == ctypes.c_size_t(-1).value:
+                L.check(-3, "pyl_fft2d_c2r_workspace_bytes")
+            ws = D.workspace(need, dev, "fft")
+            L.check(lib.pyl_fft2d_c2r(D.ptr(d1), D.ptr(xi_grid), int(grid), D.ptr(ws), need, D.stream_ptr(dev)),
+                    "pyl_fft2d_c2r")
+            start2 = time.time()
+            nb = int((grid // 2) * np.sqrt(2)) + 1
+            out = torch.empty(3 * nb, dtype=torch.int64, device=dev)
+            # the 1/grid^2 of the normalised inverse transform is applied to each value as it is read
+            L.check(lib.pyl_radial_bin_2d(D.ptr(xi_grid), int(grid), float(np.float32(1.0) / np.float32(grid ** 2)),
+                                          D.ptr(out), D.stream_ptr(dev)), "pyl_radial_bin_2d")
+            words = D.to_host_numpy(out).copy()
+        print("Time to complete loop = %.2f" % (time.time() - start2))
+        f64 = words.view(np.float64)
+        Nm = words[nb + 1:2 * nb].astype(np.float64)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            self.r_p = (f64[1:nb] / Nm) * (BoxSize * 1.0 / grid)                 # :2783
+            self.xi_p = (f64[2 * nb + 1:3 * nb] / Nm) * (1.0 / grid ** 2)         # :2784
+        self.Nmodes_p = Nm
         print("Time taken = %.2f seconds" % (time.time() - start))
 
 

@@ -115,6 +115,61 @@ static unsigned grid_for(long long n, int block) {
     return (unsigned)b;
 }
 
+
+// ---- XXi_projected (Pk_library.pyx:2684-2789): the 2D forms of the mode pass and of the real-space binning -------
+// mode pass: every stored mode of the (grid, grid/2+1) half-spectra is deconvolved (no duplicate-mode rule in the
+// reference's 2D loop, :2735-2758) and a_k <- (re_a*re_b + im_a*im_b, 0), products and sum in float32
+__global__ void __launch_bounds__(256) modes_power_2d_kernel(float2 *__restrict__ a, const float2 *__restrict__ b,
+                                                             const double *__restrict__ wa, const double *__restrict__ wb,
+                                                             int N, int m) {
+    const int m1 = m + 1;
+    const long long total = (long long)N * m1;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int kxx = (int)(t / m1), kyy = (int)(t - (long long)kxx * m1);
+        const int ax = kxx > m ? N - kxx : kxx;                   // the window is even in k
+        const float fa = __double2float_rn(wa[ax] * wa[kyy]);    // cdef float MAS_factor = corr_x * corr_y (:2745-2748)
+        const float fb = __double2float_rn(wb[ax] * wb[kyy]);
+        const float2 va = a[t], vb = b[t];
+        const float r1 = __fmul_rn(va.x, fa), i1 = __fmul_rn(va.y, fa);
+        const float r2 = __fmul_rn(vb.x, fb), i2 = __fmul_rn(vb.y, fb);
+        a[t] = make_float2(__fadd_rn(__fmul_rn(r1, r2), __fmul_rn(i1, i2)), 0.0f);
+    }
+}
+
+// binning of every cell of the (grid, grid) image by int(sqrt(kx^2 + ky^2)) (:2776-2787): out = [sum k | count | sum xi]
+// per bin, float64 / uint64; a block keeps private sums in shared memory when the bins fit
+__global__ void __launch_bounds__(256) radial_bin_2d_kernel(const float *__restrict__ img, int N, int m, int nb,
+                                                            float scale, unsigned long long *__restrict__ out,
+                                                            int use_smem) {
+    extern __shared__ unsigned long long rb_smem[];
+    if (use_smem) {
+        for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) rb_smem[i] = 0ull;
+        __syncthreads();
+    }
+    unsigned long long *acc = use_smem ? rb_smem : out;
+    const long long total = (long long)N * N;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int kxx = (int)(t / N), kyy = (int)(t - (long long)kxx * N);
+        const int kx = kxx > m ? kxx - N : kxx, ky = kyy > m ? kyy - N : kyy;
+        const double k = sqrt((double)(kx * kx + ky * ky));
+        const int bin = (int)k;
+        if (bin >= nb) continue;
+        const float v = __fmul_rn(__ldg(img + t), scale);
+        atomicAdd(reinterpret_cast<double *>(acc + bin), k);
+        atomicAdd(acc + nb + bin, 1ull);
+        atomicAdd(reinterpret_cast<double *>(acc + 2 * nb + bin), (double)v);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) {
+            const unsigned long long w = rb_smem[i];
+            if (w == 0ull) continue;
+            if (i >= nb && i < 2 * nb) atomicAdd(out + i, w);
+            else atomicAdd(reinterpret_cast<double *>(out + i), __longlong_as_double((long long)w));
+        }
+    }
+}
+
 }  // namespace pyl
 
 using namespace pyl;
@@ -287,6 +342,45 @@ int pyl_mul_one_plus(float *v, const float *delta, int64_t n, pyl_stream_t strea
     if (n == 0) return PYL_OK;
     PYL_REQUIRE(v != nullptr && delta != nullptr, "pyl_mul_one_plus: NULL pointer");
     mul_one_plus_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(v, delta, n);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
+
+int pyl_modes_power_2d(float *a_k, const float *b_k, int dims, int mas_a, int mas_b, void *ws, size_t ws_bytes,
+                       pyl_stream_t stream) {
+    PYL_REQUIRE(dims > 0 && a_k != nullptr && b_k != nullptr, "pyl_modes_power_2d: bad dims or NULL field");
+    PYL_REQUIRE(mas_a >= 0 && mas_a <= 4 && mas_b >= 0 && mas_b <= 4, "pyl_modes_power_2d: mas_index must be 0..4");
+    const size_t need = pyl_modes_workspace_bytes(dims);
+    if (ws == nullptr || ws_bytes < need) {
+        set_last_error("pyl_modes_power_2d: workspace of %zu bytes required, %zu given", need, ws_bytes);
+        return PYL_ERR_WORKSPACE;
+    }
+    cudaStream_t s = as_stream(stream);
+    const int m = dims / 2, m1 = m + 1;
+    double *tab = reinterpret_cast<double *>(ws);
+    shell_window_kernel<<<(m1 + 127) / 128, 128, 0, s>>>(tab, m1, dims, mas_a, mas_b);
+    PYL_LAUNCH_CHECK();
+    const long long total = (long long)dims * m1;
+    modes_power_2d_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<float2 *>(a_k),
+                                                               reinterpret_cast<const float2 *>(b_k), tab, tab + m1, dims, m);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
+int pyl_radial_bin_2d(const float *image, int dims, float scale, void *out, pyl_stream_t stream) {
+    PYL_REQUIRE(dims > 0 && image != nullptr && out != nullptr, "pyl_radial_bin_2d: bad dims or NULL pointer");
+    const int nb = (int)((dims / 2) * sqrt(2.0)) + 1;                  // kmax + 1, kmax = int((grid//2)*sqrt(2)) (:2722)
+    cudaStream_t s = as_stream(stream);
+    PYL_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)3 * nb * 8, s));
+    const size_t smem = (size_t)3 * nb * 8;
+    const int use_smem = smem <= 40 * 1024;
+    long long blocks = ((long long)dims * dims + 256 * 16 - 1) / (256 * 16);
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    radial_bin_2d_kernel<<<(unsigned)blocks, 256, use_smem ? smem : 0, s>>>(
+        image, dims, dims / 2, nb, scale, reinterpret_cast<unsigned long long *>(out), use_smem);
     PYL_LAUNCH_CHECK();
     return PYL_OK;
 }

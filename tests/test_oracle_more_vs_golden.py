@@ -52,3 +52,24 @@ def test_inverse_transform_is_normalised(oracle, golden):
     assert np.max(np.abs(back - I["d1"])) < 1e-5 * np.abs(I["d1"]).max()
     # and the reference's deconvolved field is of the same order as the input, not dims^3 larger
     assert np.abs(golden["N12_cmas"]).max() < 10 * np.abs(I["d1"]).max()
+
+
+def test_xxi_projected_restatement_matches_the_compiled_reference():
+    """XXi_projected (Pk_library.pyx:2684-2789): counts and r_p exact, xi_p to float32 round-off of its peak (the
+    reference's float32 products may be fused by its compiler)."""
+    import contextlib
+    import io
+    import os
+
+    import numpy as np
+    from conftest import BOX, GOLDEN
+    from golden.make_golden_more import inputs
+    from oracle import cpu_more as OM
+    g = np.load(os.path.join(GOLDEN, "xxi_projected_golden.npz"))
+    for N in (12, 9, 32):
+        I = inputs(N)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = OM.XXi_projected(I["img1"], I["img2"], BOX, ["CIC", "PCS"], 1)
+        assert np.array_equal(r.Nmodes_p, g["N%d_Nm" % N])
+        assert np.max(np.abs(r.r_p - g["N%d_r" % N]) / g["N%d_r" % N]) < 1e-12
+        assert np.max(np.abs(r.xi_p - g["N%d_xi" % N])) < 2e-6 * np.max(np.abs(g["N%d_xi" % N]))
