@@ -64,6 +64,8 @@ constexpr int PPER = PYL_PPER;                  // particles per thread
 constexpr int PP = PT * PPER;                   // 4096 particles per partition CTA
 constexpr int MAX_BINS = 2048;                  // bins per partition pass
 constexpr int MAX_REPL = 64;                    // cursor replicas of the first pass
+constexpr int DIRECT_SLOTS = 1024;              // a CTA of pass 1 goes straight to the tile buckets if the bounding box of
+                                                // its particles' tiles holds at most this many tiles
 constexpr int OUT_ROW = 36;                     // floats per flushed row (32 + halo, 16-byte multiple)
 
 struct TileGeom {
@@ -92,7 +94,8 @@ __device__ __forceinline__ int wrap_once(int i, int dims) {
 }
 
 template <int MAS>
-__device__ __forceinline__ unsigned tile_and_local(const float d[3], const TileGeom &g, int local[3]) {
+__device__ __forceinline__ unsigned tile_and_local(const float d[3], const TileGeom &g, int local[3],
+                                                   unsigned *tcoord = nullptr) {
     static_assert(TX == 8 && TY == 16 && TZ == 32, "shifts below");
     int wb[3];
 #pragma unroll
@@ -109,6 +112,7 @@ __device__ __forceinline__ unsigned tile_and_local(const float d[3], const TileG
     local[0] = wb[0] & (TX - 1);
     local[1] = wb[1] & (TY - 1);
     local[2] = wb[2] & (TZ - 1);
+    if (tcoord != nullptr) *tcoord = (t0 << 20) | (t1 << 10) | t2;       // tile coordinates, 10 bits each
     return mine ? (t0 * g.nty + t1) * g.ntz + t2 : NO_TILE;
 }
 
@@ -244,6 +248,7 @@ struct PartArgs {
     int64_t particles;
     const float4 *in;            // pass 2 input (buf1)
     float4 *out;                 // output records (dist.x, dist.y, dist.z, W): buf1 in pass 1, buf2 in pass 2
+    float4 *out2;                // pass 1: buf2, written directly by CTAs whose particles touch few tiles
     const unsigned *starts;      // ntiles + 1 bucket starts
     unsigned *cur1;              // [repl][nsuper]
     unsigned *cur2;              // [ntiles]
@@ -257,6 +262,7 @@ struct PartArgs {
 
 // dynamic shared memory of a partition CTA: PP staged records + three words per bin + the bin of every staged record
 static size_t part_smem_bytes(int nb) {
+    if (nb < DIRECT_SLOTS) nb = DIRECT_SLOTS;
     return (size_t)PP * 16 + 3 * (size_t)((nb + 3) & ~3) * 4 + (size_t)PP * 2 + 64 * 4;
 }
 
@@ -264,8 +270,8 @@ template <int MAS, bool WEIGHTED, int LEVEL>
 __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, TileGeom g) {
     constexpr int S = StencilWidth<MAS>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int nb = LEVEL == 1 ? (int)g.nsuper : (1 << g.tps_shift);
-    const int nb4 = (nb + 3) & ~3;
+    int nb = LEVEL == 1 ? (int)g.nsuper : (1 << g.tps_shift);
+    const int nb4 = ((nb < DIRECT_SLOTS ? DIRECT_SLOTS : nb) + 3) & ~3;
     float4 *stage = reinterpret_cast<float4 *>(smem_raw);                      // PP records in bin order
     unsigned *cnt = reinterpret_cast<unsigned *>(stage + PP);                  // nb: counts -> bin starts
     unsigned *goff = cnt + nb4;                                                // global slot of sorted index 0 of a bin
@@ -325,7 +331,8 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         first = misc[17];
     }
 
-    for (int i = tid; i < nb; i += PT) cnt[i] = 0u;
+    for (int i = tid; i < nb4; i += PT) cnt[i] = 0u;
+    if (LEVEL == 1 && tid < 6) misc[24 + tid] = tid < 3 ? 0x7fffffffu : 0x80000000u;   // bounding box: 3 minima, 3 maxima (int)
     __syncthreads();
 
     // ---- load, bin, rank ------------------------------------------------------------------------------------
@@ -352,19 +359,109 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
             }
         }
     }
+    // tile of every particle
+    unsigned tl[PPER], tc[PPER];
 #pragma unroll
     for (int q = 0; q < PPER; q++) {
         const int i = q * PT + tid;
-        int bin = -1;
+        tl[q] = NO_TILE;
+        tc[q] = 0u;
         if (i < n_in) {
             if (LEVEL == 1) {
 #pragma unroll
                 for (int k = 0; k < 3; k++) d[q][k] = cell_coordinate(d[q][k], g.inv_cell_size);
             }
             int local[3];
-            const unsigned t = tile_and_local<MAS>(d[q], g, local);
-            if (t == NO_TILE) dropped += S * S * S;      // not routed to this slab: nothing of it is deposited here
-            else bin = LEVEL == 1 ? (int)(t >> g.tps_shift) : (int)(t - (super << g.tps_shift));
+            tl[q] = tile_and_local<MAS>(d[q], g, local, LEVEL == 1 ? &tc[q] : nullptr);
+            if (tl[q] == NO_TILE) dropped += S * S * S;  // not routed to this slab: nothing of it is deposited here
+        }
+    }
+    // ---- pass 1, spatially ordered input (lattice order, Peano-Hilbert order: snapshots usually are): the 4096
+    // consecutive particles of a CTA sit in a small box of tiles, so their runs are long enough to go STRAIGHT to
+    // the tile buckets (buf2) and pass 2 has nothing left to do for them.  The CTA takes the bounding box of its
+    // particles' tile coordinates (relative to its first particle, periodic) and uses the position inside the box
+    // as the bin; a box of more than DIRECT_SLOTS tiles (random order: always) keeps the super-tile bins.
+    bool direct = false;
+    int box_lo[3] = {0, 0, 0}, box_n[3] = {1, 1, 1}, ref[3] = {0, 0, 0};
+    const int nt[3] = {g.ntx, g.nty, g.ntz};
+    bool ordered = false;
+    if (LEVEL == 1 && g.ntx < 1024 && g.nty < 1024 && g.ntz < 1024) {
+        // cheap vote first: in three warps out of four, a quarter of the lanes share lane 0's tile
+        const unsigned lead = __shfl_sync(0xffffffffu, tl[0], 0);
+        const int agree = __popc(__ballot_sync(0xffffffffu, tl[0] == lead));
+        ordered = __syncthreads_count(lane == 0 && agree >= 8) >= PT / 32 * 3 / 4;
+    }
+    if (ordered) {
+        if (tid == 0) misc[30] = tc[0];                     // reference tile: the first particle's (any tile does)
+        __syncthreads();
+        const unsigned rc = misc[30];
+        ref[0] = (int)(rc >> 20); ref[1] = (int)((rc >> 10) & 1023u); ref[2] = (int)(rc & 1023u);
+        int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
+#pragma unroll
+        for (int q = 0; q < PPER; q++) {
+            if (tl[q] != NO_TILE) {
+                const int c[3] = {(int)(tc[q] >> 20), (int)((tc[q] >> 10) & 1023u), (int)(tc[q] & 1023u)};
+                unsigned packed = 0;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    int r = c[k] - ref[k];                  // periodic distance from the reference tile
+                    if (2 * r >= nt[k]) r -= nt[k];
+                    else if (2 * r < -nt[k]) r += nt[k];
+                    lo[k] = min(lo[k], r);
+                    hi[k] = max(hi[k], r);
+                    packed = (packed << 10) | (unsigned)(r + 512);
+                }
+                tc[q] = packed;                             // relative coordinates, biased by 512
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lo[k] = __reduce_min_sync(0xffffffffu, lo[k]);
+            hi[k] = __reduce_max_sync(0xffffffffu, hi[k]);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                atomicMin(reinterpret_cast<int *>(misc) + 24 + k, lo[k]);
+                atomicMax(reinterpret_cast<int *>(misc) + 27 + k, hi[k]);
+            }
+        }
+        __syncthreads();
+        long long vol = 1;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            box_lo[k] = reinterpret_cast<int *>(misc)[24 + k];
+            box_n[k] = reinterpret_cast<int *>(misc)[27 + k] - box_lo[k] + 1;
+            if (box_n[k] < 1 || box_n[k] > nt[k]) box_n[k] = DIRECT_SLOTS + 1;      // empty CTA / wraps onto itself
+            vol *= box_n[k];
+        }
+        direct = vol <= DIRECT_SLOTS;
+    }
+    // tile of bin b of the box (direct mode)
+    auto box_tile = [&](int b) -> unsigned {
+        const int rz = b % box_n[2], ry = (b / box_n[2]) % box_n[1], rx = b / (box_n[2] * box_n[1]);
+        int c[3] = {ref[0] + box_lo[0] + rx, ref[1] + box_lo[1] + ry, ref[2] + box_lo[2] + rz};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (c[k] < 0) c[k] += nt[k];
+            else if (c[k] >= nt[k]) c[k] -= nt[k];
+        }
+        return ((unsigned)c[0] * g.nty + c[1]) * g.ntz + c[2];
+    };
+    if (direct) nb = box_n[0] * box_n[1] * box_n[2];
+#pragma unroll
+    for (int q = 0; q < PPER; q++) {
+        int bin = -1;
+        if (tl[q] != NO_TILE) {
+            if (LEVEL == 2) {
+                bin = (int)(tl[q] - (super << g.tps_shift));
+            } else if (!direct) {
+                bin = (int)(tl[q] >> g.tps_shift);
+            } else {
+                const int r0 = (int)(tc[q] >> 20) - 512 - box_lo[0], r1 = (int)((tc[q] >> 10) & 1023u) - 512 - box_lo[1],
+                          r2 = (int)(tc[q] & 1023u) - 512 - box_lo[2];
+                bin = (r0 * box_n[1] + r1) * box_n[2] + r2;
+            }
         }
         // rank within the bin.  Ordered inputs (lattice / Peano-Hilbert order) send whole warps to one bin, and
         // same-address shared atomics serialise: when neighbouring lanes agree, the lanes of the leading bin share
@@ -374,7 +471,7 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         const int nbin = __shfl_down_sync(0xffffffffu, bin, 1);
         if (__popc(__ballot_sync(0xffffffffu, todo && nbin == bin && lane < 31)) >= 8) {
 #pragma unroll 1
-            for (int it = 0; it < 2; it++) {
+            for (int it = 0; it < 4; it++) {
                 const unsigned pending = __ballot_sync(0xffffffffu, todo);
                 if (pending == 0) break;
                 const int leader = __ffs(pending) - 1;
@@ -417,13 +514,16 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         for (int w = 0; w < PT / 32; w++) run += (w < warp) ? misc[w] : 0u;
         // the reservations of this thread's bins are issued back to back (their results are consumed afterwards):
         // returning global atomics take microseconds under load
-        unsigned got[EPT], end[EPT];
+        unsigned got[EPT], end[EPT], btile[EPT];
 #pragma unroll
         for (int i = 0; i < EPT; i++) {
             const int b = tid * EPT + i;
-            got[i] = end[i] = 0u;
+            got[i] = end[i] = btile[i] = 0u;
             if (b < nb && c[i] > 0) {
-                if (LEVEL == 1) {
+                if (LEVEL == 1 && direct) {
+                    btile[i] = box_tile(b);
+                    end[i] = __ldg(a.starts + btile[i] + 1);
+                } else if (LEVEL == 1) {
                     const Segment sg = super_segment(a.starts, g, (unsigned)b, repl);
                     end[i] = sg.begin + sg.cap;
                 } else {
@@ -435,7 +535,8 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         for (int i = 0; i < EPT; i++) {
             const int b = tid * EPT + i;
             if (b < nb && c[i] > 0) {
-                if (LEVEL == 1) got[i] = atomicAdd(a.cur1 + repl * g.nsuper + b, c[i]);
+                if (LEVEL == 1 && direct) got[i] = atomicAdd(a.cur2 + btile[i], c[i]);
+                else if (LEVEL == 1) got[i] = atomicAdd(a.cur1 + repl * g.nsuper + b, c[i]);
                 else got[i] = atomicAdd(a.cur2 + (super << g.tps_shift) + b, c[i]);
             }
         }
@@ -481,7 +582,7 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         const unsigned b = sbin[j];
         const unsigned slot = goff[b] + (unsigned)j;
         const float4 v = stage[j];
-        if (slot < lim[b]) a.out[slot] = v;
+        if (slot < lim[b]) (LEVEL == 1 && direct ? a.out2 : a.out)[slot] = v;
         else overflow_deposit<MAS, WEIGHTED>(v.x, v.y, v.z, v.w, g, a.number, &dropped);
     }
     if (a.dropped != nullptr && dropped != 0) atomicAdd(a.dropped, dropped);
@@ -780,7 +881,7 @@ static int run_tiled_w(const float *pos, float *number, const float *W, int64_t 
         attr_done = true;
     }
     PartArgs a;
-    a.pos = pos; a.W = W; a.particles = particles; a.in = w.buf1; a.out = w.buf1;
+    a.pos = pos; a.W = W; a.particles = particles; a.in = w.buf1; a.out = w.buf1; a.out2 = w.buf2;
     a.starts = w.starts; a.cur1 = w.cur1; a.cur2 = w.cur2; a.spre = w.spre; a.number = number; a.dropped = dropped;
     a.wsum = w.wsum;
     a.n_dev = n_dev;
