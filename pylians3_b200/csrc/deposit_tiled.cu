@@ -126,9 +126,15 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t groups = vec_ok ? (particles >> 2) : 0;
     int local[3];
-    // every SAMPLE-th group of 4 particles
+    // one group of 4 particles out of every SAMPLE consecutive groups, at a pseudo-random place: a FIXED stride aliases
+    // with lattice-ordered input (a stride of 32 particles is one tile length at Np = N^3: every sampled particle then
+    // sits at the same offset inside its tile, the estimate follows the displacement across the tile boundary
+    // instead of the density, and ~0.5% of the particles overflowed their buckets)
     for (int64_t sg = tid; sg * SAMPLE < groups; sg += stride) {
-        const int64_t grp = sg * SAMPLE;
+        unsigned h = (unsigned)sg * 0x9E3779B1u;
+        h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13;
+        int64_t grp = sg * SAMPLE + (h % SAMPLE);
+        if (grp >= groups) grp = sg * SAMPLE;
         float p[12];
         const float4 *src = reinterpret_cast<const float4 *>(pos + grp * 12);
 #pragma unroll
@@ -147,7 +153,10 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const float *__restrict
     }
     // unaligned input / tail: every SAMPLE-th particle
     for (int64_t si = tid; (groups << 2) + si * SAMPLE < particles; si += stride) {
-        const int64_t i = (groups << 2) + si * SAMPLE;
+        unsigned h = (unsigned)si * 0x9E3779B1u;
+        h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13;
+        int64_t i = (groups << 2) + si * SAMPLE + (h % SAMPLE);
+        if (i >= particles) i = (groups << 2) + si * SAMPLE;
         float d[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) d[a] = cell_coordinate(__ldg(pos + i * 3 + a), g.inv_cell_size);
@@ -331,9 +340,6 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         first = misc[17];
     }
 
-    for (int i = tid; i < nb4; i += PT) cnt[i] = 0u;
-    if (LEVEL == 1 && tid < 6) misc[24 + tid] = tid < 3 ? 0x7fffffffu : 0x80000000u;   // bounding box: 3 minima, 3 maxima (int)
-    __syncthreads();
 
     // ---- load, bin, rank ------------------------------------------------------------------------------------
     float d[PPER][3], wv[PPER];
@@ -384,16 +390,18 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
     bool direct = false;
     int box_lo[3] = {0, 0, 0}, box_n[3] = {1, 1, 1}, ref[3] = {0, 0, 0};
     const int nt[3] = {g.ntx, g.nty, g.ntz};
+    for (int i = tid; i < nb4; i += PT) cnt[i] = 0u;
+    if (LEVEL == 1 && tid < 6) misc[24 + tid] = tid < 3 ? 0x7fffffffu : 0x80000000u;   // bounding box: 3 minima, 3 maxima (int)
+    if (LEVEL == 1 && tid == 0) misc[30] = tc[0];           // reference tile of the box: the first particle's (any tile does)
+    __syncthreads();
     bool ordered = false;
     if (LEVEL == 1 && g.ntx < 1024 && g.nty < 1024 && g.ntz < 1024) {
-        // cheap vote first: in three warps out of four, a quarter of the lanes share lane 0's tile
+        // cheap vote first: in half of the warps at least three lanes share lane 0's tile (random order: none does)
         const unsigned lead = __shfl_sync(0xffffffffu, tl[0], 0);
         const int agree = __popc(__ballot_sync(0xffffffffu, tl[0] == lead));
-        ordered = __syncthreads_count(lane == 0 && agree >= 8) >= PT / 32 * 3 / 4;
+        ordered = __syncthreads_count(lane == 0 && agree >= 3) >= PT / 32 / 2;
     }
     if (ordered) {
-        if (tid == 0) misc[30] = tc[0];                     // reference tile: the first particle's (any tile does)
-        __syncthreads();
         const unsigned rc = misc[30];
         ref[0] = (int)(rc >> 20); ref[1] = (int)((rc >> 10) & 1023u); ref[2] = (int)(rc & 1023u);
         int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
@@ -471,7 +479,7 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         const int nbin = __shfl_down_sync(0xffffffffu, bin, 1);
         if (__popc(__ballot_sync(0xffffffffu, todo && nbin == bin && lane < 31)) >= 8) {
 #pragma unroll 1
-            for (int it = 0; it < 4; it++) {
+            for (int it = 0; it < 2; it++) {
                 const unsigned pending = __ballot_sync(0xffffffffu, todo);
                 if (pending == 0) break;
                 const int leader = __ffs(pending) - 1;
