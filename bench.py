@@ -282,7 +282,7 @@ def small_parity_check(world, rank, dev):
     here, never the thing measured."""
     import torch
     import torch.distributed as dist
-    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, overdensity_
+    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL
     N = 64
     rng = np.random.default_rng(11)
     pos = rng.random((2 * N ** 3, 3), dtype=np.float32) * np.float32(BOX)
@@ -295,8 +295,7 @@ def small_parity_check(world, rank, dev):
         g = torch.zeros((N, N, N), dtype=torch.float32, device=dev)
         MASL.MA(torch.from_numpy(pos).to(dev), g, BOX, "PCS", torch.from_numpy(W).to(dev), mode="tiled")
         got = g.cpu().numpy()
-        overdensity_(g)
-        pk = PKL.Pk(g, BOX, 0, "PCS", verbose=False)
+        pk = PKL.Pk(g, BOX, 0, "PCS", verbose=False, density=True)
     else:
         from pylians3_b200 import dist as PD
         ctx = PD.SlabContext(N, BOX)
@@ -307,8 +306,7 @@ def small_parity_check(world, rank, dev):
         parts = [torch.empty((s, N, N), dtype=torch.float32, device=dev) for s in ctx.x_sizes]
         dist.all_gather(parts, slab)
         got = torch.cat(parts).cpu().numpy()
-        ctx.overdensity_(slab)
-        pk = ctx.Pk(slab, 0, "PCS")
+        pk = ctx.Pk(slab, 0, "PCS", density=True)
     if rank == 0:
         from oracle import build as obuild
         obuild.build()
@@ -385,17 +383,14 @@ def run_extra(name, world, rank, dev, steps, grid_override=0):
             s_.zero_()
             ctx.MA(pos, s_, "CIC", W=w, routed=True)
         e.append(ev())
-        for s_ in slabs:
-            ctx.overdensity_(s_)
-        e.append(ev())
         marks = {}
         dks = [ctx.fft(s_, slot=i, marks=marks if i == 0 else None) for i, s_ in enumerate(slabs)]
         e.append(ev())
-        o = ctx._spectra(dks, [PKL.MAS_function("CIC")] * nf, 0, nf == 1)
+        o = ctx._spectra(dks, [PKL.MAS_function("CIC")] * nf, 0, nf == 1, density=True)
         e.append(ev())
         if times is not None:
             torch.cuda.synchronize()
-            for k, (a, b) in zip(("zero+deposit+halo", "overdensity", "slab_fft", "bin+allreduce+finalise+d2h"),
+            for k, (a, b) in zip(("zero+deposit+halo", "slab_fft", "bin+allreduce+finalise+d2h"),
                                  zip(e[:-1], e[1:])):
                 times[k] = times.get(k, 0.0) + a.elapsed_time(b)
             times["transpose_kernels_field0"] = times.get("transpose_kernels_field0", 0.0) + \
@@ -470,7 +465,7 @@ def run_ours(args, wl, grid_n):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pyl_b200_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
-    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, _device as D, _lib, overdensity_, synth
+    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, _device as D, _lib, synth
     lib = _lib.load()
     MAS, AXIS = wl["mas"], wl["axis"]
     npart = grid_n ** 3
@@ -492,16 +487,14 @@ def run_ours(args, wl, grid_n):
         def step(p, w):
             slab.zero_()
             ctx.MA(p, slab, MAS, W=w, routed=False)
-            ctx.overdensity_(slab)
-            return ctx.Pk(slab, AXIS, MAS)
+            return ctx.Pk(slab, AXIS, MAS, density=True)     # spectrum of n/<n> - 1: the normalisation is a scale
     else:
         grid = torch.zeros((grid_n, grid_n, grid_n), dtype=torch.float32, device=dev)
 
         def step(p, w):
             grid.zero_()
             MASL.MA(p, grid, BOX, MAS, w)
-            overdensity_(grid)
-            return PKL.Pk(grid, BOX, AXIS, MAS, verbose=False)
+            return PKL.Pk(grid, BOX, AXIS, MAS, verbose=False, density=True)   # n/<n> - 1 folded into the scale
 
     def barrier():
         if world > 1:
@@ -557,15 +550,14 @@ def run_ours(args, wl, grid_n):
     reps = 3
     stages = {}
     if world == 1:
-        acc = {k: 0.0 for k in ("zero", "deposit", "overdensity", "fft", "bin+finalise+d2h")}
+        acc = {k: 0.0 for k in ("zero", "deposit", "fft", "bin+finalise+d2h")}
         for _ in range(reps):
             e0 = ev(); grid.zero_()
             e1 = ev(); MASL.MA(pos, grid, BOX, MAS, W)
-            e2 = ev(); overdensity_(grid)
-            e3 = ev(); dk = PKL.fft3d_r2c_device(grid)
-            e4 = ev(); PKL.spectra([dk], [PKL.MAS_function(MAS)], grid_n, AXIS, BOX, want_phase=True)
-            e5 = ev(); torch.cuda.synchronize()
-            for k, (a, b) in zip(acc, ((e0, e1), (e1, e2), (e2, e3), (e3, e4), (e4, e5))):
+            e2 = ev(); dk = PKL.fft3d_r2c_device(grid)
+            e3 = ev(); PKL.spectra([dk], [PKL.MAS_function(MAS)], grid_n, AXIS, BOX, want_phase=True, density=True)
+            e4 = ev(); torch.cuda.synchronize()
+            for k, (a, b) in zip(acc, ((e0, e1), (e1, e2), (e2, e3), (e3, e4))):
                 acc[k] += a.elapsed_time(b) / reps
             del dk
         stages = {k: round(v, 4) for k, v in acc.items()}
@@ -577,7 +569,7 @@ def run_ours(args, wl, grid_n):
         stages["bin_kernels_only"] = round(a.elapsed_time(b) / reps, 4)
         del dk
     else:
-        names = ("zero", "route", "deposit+halo", "overdensity", "fft_yz+transpose(pipelined)", "transpose_kernels",
+        names = ("zero", "route", "deposit+halo", "fft_yz+transpose(pipelined)", "transpose_kernels",
                  "fft_x", "bin+allreduce+finalise+d2h")
         acc = {k: 0.0 for k in names}
         peer_route = ctx._peer is not None and ctx._route_mode == "peer"
@@ -590,12 +582,11 @@ def run_ours(args, wl, grid_n):
             else:
                 (p_r, w_r), cnt = ctx.route(pos, MAS, W), None
             e2 = ev(); ctx.MA(p_r, slab, MAS, W=w_r, routed=True, count=cnt)
-            e3 = ev(); ctx.overdensity_(slab)
             e4 = ev(); marks = {}
             dk = ctx.fft(slab, marks=marks)
-            e5 = ev(); ctx._spectra([dk], [PKL.MAS_function(MAS)], AXIS, True)
+            e5 = ev(); ctx._spectra([dk], [PKL.MAS_function(MAS)], AXIS, True, density=True)
             e6 = ev(); torch.cuda.synchronize()
-            pairs = {"zero": (e0, e1), "route": (e1, e2), "deposit+halo": (e2, e3), "overdensity": (e3, e4),
+            pairs = {"zero": (e0, e1), "route": (e1, e2), "deposit+halo": (e2, e4),
                      "bin+allreduce+finalise+d2h": (e5, e6)}
             if "t1" in marks:
                 pairs.update({"fft_yz+transpose(pipelined)": (e4, marks["t1"]), "fft_x": (marks["t1"], e5)})
@@ -699,8 +690,8 @@ def run_ours(args, wl, grid_n):
                                 stages["fft"], traffic=None)
         rooflines["bin"] = roof("pk_bin_walk_kernel + fold (device time, no D2H)", 8 * half,
                                 stages["bin_kernels_only"], traffic=None)
-        rooflines["step"] = roof("whole step: deposit + delta RMW + FFT + bin",
-                                 npart * bpp + 8 * grid_n ** 3 + 8 * grid_n ** 3 + 4 * grid_n ** 3 + 8 * half + 8 * half,
+        rooflines["step"] = roof("whole step: deposit + FFT + bin (n/<n> - 1 is a scale of the binned sums)",
+                                 npart * bpp + 8 * grid_n ** 3 + 4 * grid_n ** 3 + 8 * half + 8 * half,
                                  ms_step, traffic=None)
     else:
         per = 1.0 / world

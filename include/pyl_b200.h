@@ -265,6 +265,16 @@ int pyl_pk_counts_to_f64(void *acc, int dims, int fields, pyl_stream_t stream);
 int pyl_pk_finalize(void *acc, int dims, int fields, double BoxSize, int counts_are_f64, double *kpar,
                     double *kper, pyl_stream_t stream);
 
+/* Spectra of delta = n/<n> - 1 from the transform of the DENSITY n (fuses Pk_snapshot.py:88-89, the caller's
+ * `delta /= mean; delta -= 1`, into the spectrum): FFT(delta) = FFT(n)/<n> away from k = 0, and <n> =
+ * Re FFT(n)[0] / dims^3.  pyl_pk_take_dc stores the DC mode of every field in dc[fields] (DEVICE float64) and
+ * zeroes it in the spectrum (holds_dc = 0: this rank's rows do not contain k = 0; dc is set to 0 so that a SUM
+ * all-reduce delivers it everywhere).  pyl_pk_density_scale multiplies the RAW sums of pyl_pk_bin (call it
+ * before pyl_pk_finalize) by dims^6 / (dc_i dc_j): autos by 1/<n>_i^2, crosses (pairs i<j in lexicographic
+ * order) by 1/(<n>_i <n>_j); counts, k sums and the phase sums are untouched. */
+int pyl_pk_take_dc(float *const *delta_k, int fields, int holds_dc, double *dc, pyl_stream_t stream);
+int pyl_pk_density_scale(void *acc, int dims, int fields, const double *dc, pyl_stream_t stream);
+
 /* Mirrored slab form (multi-GPU): the rank holds the rows |ky| in [ky_lo, ky_lo+ny_lo) of the half-range
  * 0..dims/2 AND their mirrors N-ky, as (dims, nky, dims/2+1) complex64 with the ky axis ordered: first the
  * ny_lo lower rows (ascending ky), then the mirrors that exist as separate modes (ky != 0, ky != Nyquist) in

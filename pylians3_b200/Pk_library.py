@@ -250,12 +250,45 @@ def finalize_device(out, lay, BoxSize, dims, counts_are_f64=False):
     return o
 
 
-def spectra(dk_list, mas_index, dims, axis, BoxSize, want_phase=False, flags=0):
-    """bin + finalise: device finalisation for up to L.MAX_FIELDS fields, host assembly beyond."""
+def take_dc(dk_list, holds_dc=True):
+    """pyl_pk_take_dc: DC modes of the half-spectra as a float64 CUDA tensor (one per field), zeroed in the
+    spectra.  With the transform of a DENSITY n this is dims^3 <n> (see `density=` of Pk / XPk)."""
+    dev = dk_list[0].device
+    dc = torch.empty(len(dk_list), dtype=torch.float64, device=dev)
+    for b in range(0, len(dk_list), L.MAX_FIELDS):
+        part = dk_list[b:b + L.MAX_FIELDS]
+        ptrs = (ctypes.c_void_p * len(part))(*[D.ptr(t) for t in part])
+        with torch.cuda.device(dev):
+            L.check(L.load().pyl_pk_take_dc(ptrs, len(part), 1 if holds_dc else 0, D.ptr(dc[b:]), D.stream_ptr(dev)),
+                    "pyl_pk_take_dc")
+    return dc
+
+
+def density_scale_(out, lay, dims, dc):
+    """pyl_pk_density_scale on the raw accumulators: sums of |FFT(n)|^2 become sums of |FFT(n/<n> - 1)|^2."""
+    with torch.cuda.device(out.device):
+        L.check(L.load().pyl_pk_density_scale(D.ptr(out), int(dims), int(lay.fields), D.ptr(dc),
+                                              D.stream_ptr(out.device)), "pyl_pk_density_scale")
+
+
+def spectra(dk_list, mas_index, dims, axis, BoxSize, want_phase=False, flags=0, density=False):
+    """bin + finalise: device finalisation for up to L.MAX_FIELDS fields, host assembly beyond.
+    density=True: the fields are transforms of densities n; the spectra are those of n/<n> - 1."""
+    dc = take_dc(dk_list) if density else None
     if len(dk_list) <= L.MAX_FIELDS:
         out, lay = bin_device(dk_list, mas_index, dims, axis, want_phase and len(dk_list) == 1, flags=flags)
+        if density:
+            density_scale_(out, lay, dims, dc)
         return finalize_device(out, lay, BoxSize, dims)
-    return _finalize(bin_fields(dk_list, mas_index, dims, axis, want_phase, flags=flags), BoxSize, dims)
+    raw = bin_fields(dk_list, mas_index, dims, axis, want_phase, flags=flags)
+    if density:
+        inv = float(dims) ** 3 / dc.cpu().numpy()
+        pairs = np.array([inv[i] * inv[j] for i in range(len(inv)) for j in range(i + 1, len(inv))])
+        for k in ("Pk3D", "Pk1D", "Pk2D"):
+            raw[k] = raw[k] * (inv * inv)
+        for k in ("PkX3D", "PkX1D", "PkX2D"):
+            raw[k] = raw[k] * pairs
+    return _finalize(raw, BoxSize, dims)
 
 
 # ---- host finalisation (vectorised restatement of :384-418 / :735-791) --------------------
@@ -314,9 +347,14 @@ class Pk:
     """1D, 2D and 3D power spectrum of a density field (Pk_library.pyx:263-420).
 
     Attributes: k3D, Pk (kmax,3: l=0,2,4), Nmodes3D, Pkphase, k1D, Pk1D, Nmodes1D, kpar, kper,
-    Pk2D, Nmodes2D."""
+    Pk2D, Nmodes2D.
 
-    def __init__(self, delta, BoxSize, axis=2, MAS="CIC", threads=1, verbose=True):
+    density=True (not in the reference): `delta` is a DENSITY n (what MA deposited), and the result is the
+    spectrum of n/<n> - 1 -- the caller's `delta /= np.mean(delta); delta -= 1` (Pk_snapshot.py:88-89) folded into
+    the scale of the binned sums, <n> read from the DC mode, which is then dropped (its Pk2D[0] slot reads 0
+    where the reference leaves the squared rounding residue of sum(delta))."""
+
+    def __init__(self, delta, BoxSize, axis=2, MAS="CIC", threads=1, verbose=True, density=False):
         start = time.time()
         if verbose:
             print("\nComputing power spectrum of the field...")
@@ -328,7 +366,7 @@ class Pk:
         dims = delta_d.shape[0]
         delta_k = fft3d_r2c_device(delta_d)
         start2 = time.time()
-        o = spectra([delta_k], [MAS_function(MAS)], dims, axis, BoxSize, want_phase=True)
+        o = spectra([delta_k], [MAS_function(MAS)], dims, axis, BoxSize, want_phase=True, density=density)
         if verbose:
             print("Time to complete loop = %.2f" % (time.time() - start2))
         self.k1D, self.Pk1D, self.Nmodes1D = o["k1D"], o["Pk1D"][:, 0], o["Nmodes1D"]
@@ -344,9 +382,10 @@ class XPk:
     """Auto- and cross-power spectra of several fields (Pk_library.pyx:529-793).
 
     Attributes: k3D, Nmodes3D, Pk (kmax,3,F), XPk (kmax,3,X), k1D, Nmodes1D, Pk1D (.,F),
-    PkX1D (.,X), kpar, kper, Nmodes2D, Pk2D (.,F), PkX2D (.,X); pairs i<j in lexicographic order."""
+    PkX1D (.,X), kpar, kper, Nmodes2D, Pk2D (.,F), PkX2D (.,X); pairs i<j in lexicographic order.
+    density=True: the fields are densities, the spectra those of n_i/<n_i> - 1 (see Pk)."""
 
-    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1):
+    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1, density=False):
         start = time.time()
         print("\nComputing power spectra of the fields...")
         D.require_cuda()
@@ -365,7 +404,7 @@ class XPk:
             torch.cuda.synchronize(dev)
         print("Time FFTS = %.2f" % (time.time() - start))
         start2 = time.time()
-        o = spectra(dk, [MAS_function(m) for m in MAS], dims, axis, BoxSize)
+        o = spectra(dk, [MAS_function(m) for m in MAS], dims, axis, BoxSize, density=density)
         del dk
         print("Time loop = %.2f" % (time.time() - start2))
         self.k1D, self.Nmodes1D = o["k1D"], o["Nmodes1D"]

@@ -598,6 +598,62 @@ __global__ void __launch_bounds__(256) pk_finalize_kernel(const FinalizeArgs A) 
     }
 }
 
+// ---- spectra of delta = n/<n> - 1 straight from the transform of n (Pk_snapshot.py:88-89 fused away) -----------
+// FFT(delta) = FFT(n)/<n> except for the DC mode, which the -1 cancels, and <n> = Re FFT(n)[0] / dims^3: taking
+// the DC mode out of the spectrum and scaling the binned sums by 1/(<n>_i <n>_j) gives every spectrum of delta
+// without the two passes over the grid (a float64 sum and the in-place n/<n> - 1).
+struct DcArgs {
+    float *dk[PYL_MAX_FIELDS];
+    int F, owner;
+    double *dc;
+};
+
+__global__ void pk_take_dc_kernel(const DcArgs A) {
+    const int f = threadIdx.x;
+    if (f >= A.F) return;
+    double v = 0.0;
+    if (A.owner) {
+        v = (double)A.dk[f][0];
+        A.dk[f][0] = 0.0f;
+        A.dk[f][1] = 0.0f;
+    }
+    A.dc[f] = v;
+}
+
+struct DensityScaleArgs {
+    double *f;
+    const double *dc;
+    double cells;
+    int F, X;
+    long long o[6], n[6];          // Pk3D, PkX3D, Pk1D, PkX1D, Pk2D, PkX2D: first word, words
+};
+
+__global__ void __launch_bounds__(256) pk_density_scale_kernel(const DensityScaleArgs A) {
+    __shared__ double s_auto[PYL_MAX_FIELDS], s_cross[PYL_MAX_FIELDS * (PYL_MAX_FIELDS - 1) / 2 + 1];
+    if (threadIdx.x == 0) {
+        double inv[PYL_MAX_FIELDS];
+        for (int c = 0; c < A.F; c++) inv[c] = A.cells / A.dc[c];         // 1 / <n>_c
+        int x = 0;
+        for (int i = 0; i < A.F; i++) {
+            s_auto[i] = inv[i] * inv[i];
+            for (int j = i + 1; j < A.F; j++) s_cross[x++] = inv[i] * inv[j];
+        }
+    }
+    __syncthreads();
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        if (t < A.n[r]) {
+            const bool cross = r & 1;
+            const int per = cross ? A.X : A.F;
+            const int c = (int)(t % per);
+            A.f[A.o[r] + t] *= cross ? s_cross[c] : s_auto[c];
+            return;
+        }
+        t -= A.n[r];
+    }
+}
+
 static void fill_layout(int dims, int F, pyl_pk_layout_t *L) {
     const int m = dims / 2;
     const int X = F * (F - 1) / 2;
@@ -850,6 +906,40 @@ int pyl_pk_finalize(void *acc, int dims, int fields, double BoxSize, int counts_
     long long n = A.n2 > A.n3 ? A.n2 : A.n3;
     if (A.n1 > n) n = A.n1;
     pk_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(A);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
+int pyl_pk_take_dc(float *const *delta_k, int fields, int holds_dc, double *dc, pyl_stream_t stream) {
+    PYL_REQUIRE(fields >= 1 && fields <= PYL_MAX_FIELDS, "pyl_pk_take_dc: fields must be 1..PYL_MAX_FIELDS");
+    PYL_REQUIRE(delta_k != nullptr && dc != nullptr, "pyl_pk_take_dc: NULL pointer");
+    DcArgs A;
+    A.F = fields; A.owner = holds_dc ? 1 : 0; A.dc = dc;
+    for (int f = 0; f < fields; f++) {
+        PYL_REQUIRE(delta_k[f] != nullptr || !holds_dc, "pyl_pk_take_dc: NULL field pointer");
+        A.dk[f] = delta_k[f];
+    }
+    pk_take_dc_kernel<<<1, 32, 0, as_stream(stream)>>>(A);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
+int pyl_pk_density_scale(void *acc, int dims, int fields, const double *dc, pyl_stream_t stream) {
+    PYL_REQUIRE(acc != nullptr && dc != nullptr, "pyl_pk_density_scale: NULL pointer");
+    PYL_REQUIRE(dims > 0 && fields >= 1 && fields <= PYL_MAX_FIELDS, "pyl_pk_density_scale: bad dims/fields");
+    pyl_pk_layout_t L;
+    fill_layout(dims, fields, &L);
+    DensityScaleArgs A;
+    A.f = reinterpret_cast<double *>(acc);
+    A.dc = dc;
+    A.cells = (double)dims * (double)dims * (double)dims;
+    A.F = L.fields; A.X = L.xfields;
+    const long long n3 = L.kmax + 1, n1 = L.kmax_par + 1;
+    const long long off[6] = {L.Pk3D, L.PkX3D, L.Pk1D, L.PkX1D, L.Pk2D, L.PkX2D};
+    const long long cnt[6] = {n3 * 3 * A.F, n3 * 3 * A.X, n1 * A.F, n1 * A.X, L.n2d * A.F, L.n2d * A.X};
+    long long total = 0;
+    for (int r = 0; r < 6; r++) { A.o[r] = off[r]; A.n[r] = cnt[r]; total += cnt[r]; }
+    pk_density_scale_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(A);
     PYL_LAUNCH_CHECK();
     return PYL_OK;
 }

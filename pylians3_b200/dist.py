@@ -524,7 +524,7 @@ class SlabContext:
         return self.ops.fft_x_(recv, N)
 
     # ---- spectra -----------------------------------------------------------------------------------
-    def _reduce(self, out, lay):
+    def _reduce(self, out, lay, extra=0):
         """All-reduce the raw accumulators.  Counts (uint64 words) become float64 first -- exact below
         2^53 -- so that one float64 SUM covers the whole buffer."""
         f64 = out.view(torch.float64)
@@ -535,7 +535,8 @@ class SlabContext:
         else:
             for off, n in ((lay.Nm3D, lay.kmax + 1), (lay.Nm1D, lay.kmax_par + 1), (lay.Nm2D, lay.n2d)):
                 f64[off:off + n] = out[off:off + n].to(torch.float64)
-        dist.all_reduce(f64[:lay.total_words], group=self.group)     # (kpar/kper scratch behind it is not reduced)
+        # (the kpar/kper scratch behind the accumulators is not reduced, but for `extra` words the caller put there)
+        dist.all_reduce(f64[:lay.total_words + extra], group=self.group)
         return f64
 
     def _raw(self, dk_list, mas_index, axis, want_phase):
@@ -546,19 +547,31 @@ class SlabContext:
             words[off:off + n] = np.rint(f64[off:off + n]).astype(np.int64)
         return PKL.unpack_raw(words, lay)
 
-    def _spectra(self, dk_list, mas_index, axis, want_phase):
+    def _spectra(self, dk_list, mas_index, axis, want_phase, density=False):
         """bin -> all-reduce -> finalisation.  On GPUs the finalisation runs on the device (pyl_pk_finalize)
-        and only the finished arrays cross PCIe; the CPU stand-ins of the tests finalise on the host."""
+        and only the finished arrays cross PCIe; the CPU stand-ins of the tests finalise on the host.
+        density=True: the slabs held densities n; the rank that holds k = 0 takes dims^3 <n> from the DC modes,
+        the values ride the all-reduce behind the accumulators, and the sums are scaled to those of n/<n> - 1."""
         if self.device.type != "cuda":
+            if density:
+                raise NotImplementedError("density=True needs the CUDA path")
             return PKL._finalize(self._raw(dk_list, mas_index, axis, want_phase), self.BoxSize, self.dims)
+        dc = PKL.take_dc(dk_list, holds_dc=(self.ky_lo == 0 and self.ny_lo > 0)) if density else None
         out, lay = self.ops.bin(dk_list, mas_index, self.dims, axis, want_phase, self.ky_lo, self.ny_lo)
-        f64 = self._reduce(out, lay)
+        extra = 0
+        if density:
+            extra = len(dk_list)                   # (kpar/kper scratch: finalisation overwrites it afterwards)
+            out.view(torch.float64)[lay.total_words:lay.total_words + extra].copy_(dc)
+        f64 = self._reduce(out, lay, extra)
+        if density:
+            PKL.density_scale_(out, lay, self.dims, f64[lay.total_words:lay.total_words + extra].clone())
         return PKL.finalize_device(f64.view(torch.int64), lay, self.BoxSize, self.dims, counts_are_f64=True)
 
-    def Pk(self, slab, axis=2, MAS="CIC"):
-        """Pk_library.Pk of the slab-distributed field; every rank gets the full result."""
+    def Pk(self, slab, axis=2, MAS="CIC", density=False):
+        """Pk_library.Pk of the slab-distributed field; every rank gets the full result.
+        density=True: the slab holds the density n, the spectrum is that of n/<n> - 1 (no overdensity_ pass)."""
         dk = self.fft(slab)
-        o = self._spectra([dk], [PKL.MAS_function(MAS)], axis, True)
+        o = self._spectra([dk], [PKL.MAS_function(MAS)], axis, True, density)
         r = _Result()
         r.k1D, r.Pk1D, r.Nmodes1D = o["k1D"], o["Pk1D"][:, 0], o["Nmodes1D"]
         r.kpar, r.kper, r.Pk2D, r.Nmodes2D = o["kpar"], o["kper"], o["Pk2D"][:, 0], o["Nmodes2D"]
@@ -566,14 +579,14 @@ class SlabContext:
         r.Pk, r.Pkphase = np.ascontiguousarray(o["Pk"][:, :, 0]), o["Pkphase"]
         return r
 
-    def XPk(self, slabs, axis=2, MAS=None):
+    def XPk(self, slabs, axis=2, MAS=None, density=False):
         """Pk_library.XPk of several slab-distributed fields (<= L.MAX_FIELDS per launch)."""
         if MAS is None or len(MAS) != len(slabs):
             raise TypeError("MAS must be a list with one scheme per field")
         if len(slabs) > L.MAX_FIELDS:
             raise ValueError("the distributed XPk bins at most %d fields per call" % L.MAX_FIELDS)
         dk = [self.fft(s, slot=i) for i, s in enumerate(slabs)]
-        o = self._spectra(dk, [PKL.MAS_function(m) for m in MAS], axis, False)
+        o = self._spectra(dk, [PKL.MAS_function(m) for m in MAS], axis, False, density)
         r = _Result()
         r.k1D, r.Nmodes1D, r.Pk1D, r.PkX1D = o["k1D"], o["Nmodes1D"], o["Pk1D"], o["PkX1D"]
         r.kpar, r.kper, r.Nmodes2D, r.Pk2D, r.PkX2D = o["kpar"], o["kper"], o["Nmodes2D"], o["Pk2D"], o["PkX2D"]

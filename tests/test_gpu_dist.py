@@ -56,6 +56,7 @@ def _worker(rank, world, port, N, q, transpose="peer"):
             res["ma_" + mas] = rel_err(got, ref[x0:x1], floor=float(np.mean(np.abs(ref))))
             slabs[mas], refs[mas] = slab, ref
         ctx.check_dropped()
+        dens = {mas: slabs[mas].clone() for mas in ("CIC", "PCS")}
         for mas in ("CIC", "PCS"):
             ref = refs[mas]
             ref /= np.mean(ref, dtype=np.float64)
@@ -79,6 +80,9 @@ def _worker(rank, world, port, N, q, transpose="peer"):
         gx = ctx.XPk([slabs["PCS"], slabs["CIC"]], 0, ["PCS", "CIC"])
         wx = quiet(O.XPk, [refs["PCS"], refs["CIC"]], BOX, 0, ["PCS", "CIC"], 1)
         check_pk(gx, wx, cross=True)
+        # density=True: the slabs keep n, the normalisation is the scale of the binned sums (DC mode all-reduced)
+        check_pk(ctx.Pk(dens["PCS"], 1, "PCS", density=True), O.Pk(refs["PCS"], BOX, 1, "PCS", 1, False))
+        check_pk(ctx.XPk([dens["PCS"], dens["CIC"]], 0, ["PCS", "CIC"], density=True), wx, cross=True)
         q.put((rank, "ok", res))
         dist.destroy_process_group()
     except Exception:

@@ -57,6 +57,7 @@ def test_rank_by_rank_emulation(oracle, P, N, mas):
     assert rel_err(got, ref, floor=float(np.mean(np.abs(ref)))) < 1e-5
 
     # delta with the global float64 sum (the all-reduce)
+    dens = [s.clone() for s in slabs]
     total = sum(ops.sum_f64(s) for s in slabs)
     for s in slabs:
         ops.overdensity_(s, total, float(N) ** 3)
@@ -90,6 +91,29 @@ def test_rank_by_rank_emulation(oracle, P, N, mas):
         g.k3D, g.Nmodes3D = o["k3D"], o["Nmodes3D"]
         g.Pk, g.Pkphase = np.ascontiguousarray(o["Pk"][:, :, 0]), o["Pkphase"]
         check_pk(g, oracle.Pk(delta, BOX, axis, mas, 1, False), phase_min_modes=64)
+
+    # density=True of SlabContext._spectra: the slabs keep the density, the rank with ky = 0 takes the DC mode, the
+    # value rides the all-reduce behind the accumulators, the sums are scaled before the finalisation
+    a = torch.cat([ops.fft_yz(s, N) for s in dens])
+    acc, lay = None, None
+    for r in range(P):
+        col = ops.fft_x_(a[:, torch.tensor(ky_rows[r], device=dev), :].contiguous(), N)
+        dc = PKL.take_dc([col], holds_dc=(ylo_offs[r] == 0 and ylo_sizes[r] > 0))
+        assert (float(dc[0]) != 0.0) == (r == 0)
+        out, lay = ops.bin([col], [PKL.MAS_function(mas)], N, 1, True, ylo_offs[r], ylo_sizes[r])
+        L.check(lib.pyl_pk_counts_to_f64(D.ptr(out), N, 1, D.stream_ptr(dev)), "pyl_pk_counts_to_f64")
+        f = out.view(torch.float64)
+        f[lay.total_words:lay.total_words + 1] = dc
+        acc = f.clone() if acc is None else acc + f
+    assert abs(float(acc[lay.total_words]) / float(total) - 1.0) < 1e-6          # dims^3 <n> = sum of the cells
+    PKL.density_scale_(acc.view(torch.int64), lay, N, acc[lay.total_words:lay.total_words + 1].clone())
+    o = PKL.finalize_device(acc.view(torch.int64), lay, BOX, N, counts_are_f64=True)
+    g = _Res()
+    g.k1D, g.Pk1D, g.Nmodes1D = o["k1D"], o["Pk1D"][:, 0], o["Nmodes1D"]
+    g.kpar, g.kper, g.Pk2D, g.Nmodes2D = o["kpar"], o["kper"], o["Pk2D"][:, 0], o["Nmodes2D"]
+    g.k3D, g.Nmodes3D = o["k3D"], o["Nmodes3D"]
+    g.Pk, g.Pkphase = np.ascontiguousarray(o["Pk"][:, :, 0]), o["Pkphase"]
+    check_pk(g, oracle.Pk(delta, BOX, 1, mas, 1, False), phase_min_modes=64)
 
 
 def test_single_rank_group_deposits_into_the_whole_grid():

@@ -338,3 +338,46 @@ def test_full_size_512_against_the_compiled_reference(env):
     want = quiet(RP.Pk, ref, BOX, 0, "CIC", 8, False)
     have = PKL.Pk(torch.from_numpy(ref).cuda(), BOX, 0, "CIC", verbose=False)
     check_pk(have, want, phase_min_modes=64)
+    # and the fused form: OUR density grid, n/<n> - 1 folded into the scale of the binned sums
+    fused = PKL.Pk(grid, BOX, 0, "CIC", verbose=False, density=True)
+    check_pk(fused, want, phase_min_modes=64)
+
+
+def make_densities(oracle, N, nfields, seed):
+    """The fields of make_fields BEFORE `g /= mean; g -= 1` (densities with different means), and after."""
+    pos, W = make_particles(seed, 3 * N ** 3, True)
+    specs = [("PCS", None), ("CIC", W), ("NGP", None), ("TSC", W * W), ("CIC", None), ("PCS", W)]
+    dens, delta, mas = [], [], []
+    for m, w in specs[:nfields]:
+        g = np.zeros((N, N, N), np.float32)
+        oracle.MA(pos, g, BOX, m, w)
+        dens.append(g.copy())
+        g /= np.mean(g, dtype=np.float64)
+        g -= 1.0
+        delta.append(g)
+        mas.append(m)
+    return dens, delta, mas
+
+
+@pytest.mark.parametrize("N,axis", [(64, 0), (48, 2), (33, 1), (128, 0)])
+def test_pk_of_a_density_equals_pk_of_its_overdensity(env, oracle, N, axis):
+    """density=True (pyl_pk_take_dc + pyl_pk_density_scale): the caller's `delta /= mean; delta -= 1`
+    (Pk_snapshot.py:88-89) folded into the spectrum.  Checked against the oracle's Pk of the normalised field."""
+    torch, MASL, PKL, _ = env
+    dens, delta, mas = make_densities(oracle, N, 2, 7 * N + axis)
+    for fi in (0, 1):
+        ref = oracle.Pk(delta[fi], BOX, axis, mas[fi], 1, False)
+        d = torch.from_numpy(dens[fi]).cuda()
+        got = PKL.Pk(d, BOX, axis, mas[fi], verbose=False, density=True)
+        check_pk(got, ref)
+        assert torch.equal(d.cpu(), torch.from_numpy(dens[fi]))            # the density is not modified
+        assert got.Pk2D[0] == 0.0                                          # the DC mode is dropped, not binned
+
+
+@pytest.mark.parametrize("N,F", [(48, 2), (40, 3), (32, 4), (24, 6)])
+def test_xpk_of_densities(env, oracle, N, F):
+    torch, MASL, PKL, _ = env
+    dens, delta, mas = make_densities(oracle, N, F, 300 + N + F)
+    ref = quiet(oracle.XPk, delta, BOX, 2, mas, 1)
+    got = quiet(PKL.XPk, dens, BOX, 2, mas, 1, density=True)
+    check_pk(got, ref, cross=True)
