@@ -282,7 +282,7 @@ def small_parity_check(world, rank, dev):
     here, never the thing measured."""
     import torch
     import torch.distributed as dist
-    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL
+    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, prebias_
     N = 64
     rng = np.random.default_rng(11)
     pos = rng.random((2 * N ** 3, 3), dtype=np.float32) * np.float32(BOX)
@@ -292,21 +292,25 @@ def small_parity_check(world, rank, dev):
     W = rng.random(len(pos), dtype=np.float32)
     out = {}
     if world == 1:
-        g = torch.zeros((N, N, N), dtype=torch.float32, device=dev)
-        MASL.MA(torch.from_numpy(pos).to(dev), g, BOX, "PCS", torch.from_numpy(W).to(dev), mode="tiled")
-        got = g.cpu().numpy()
-        pk = PKL.Pk(g, BOX, 0, "PCS", verbose=False, density=True)
+        g = torch.empty((N, N, N), dtype=torch.float32, device=dev)
+        W_d = torch.from_numpy(W).to(dev)
+        c = prebias_(g, len(pos), W_d)
+        MASL.MA(torch.from_numpy(pos).to(dev), g, BOX, "PCS", W_d, mode="tiled")
+        got = (g.double() + c).float().cpu().numpy()
+        pk = PKL.Pk(g, BOX, 0, "PCS", verbose=False, density=True, offset=c)
     else:
         from pylians3_b200 import dist as PD
         ctx = PD.SlabContext(N, BOX)
         lo, hi = rank * len(pos) // world, (rank + 1) * len(pos) // world
         slab = ctx.new_slab()
-        ctx.MA(torch.from_numpy(pos[lo:hi]).to(dev), slab, "PCS", W=torch.from_numpy(W[lo:hi]).to(dev))
+        W_d = torch.from_numpy(W[lo:hi]).to(dev)
+        c = ctx.prebias_(slab, hi - lo, W_d)
+        ctx.MA(torch.from_numpy(pos[lo:hi]).to(dev), slab, "PCS", W=W_d)
         ctx.check_dropped()
         parts = [torch.empty((s, N, N), dtype=torch.float32, device=dev) for s in ctx.x_sizes]
         dist.all_gather(parts, slab)
-        got = torch.cat(parts).cpu().numpy()
-        pk = ctx.Pk(slab, 0, "PCS", density=True)
+        got = (torch.cat(parts).double() + c).float().cpu().numpy()
+        pk = ctx.Pk(slab, 0, "PCS", density=True, offset=c)
     if rank == 0:
         from oracle import build as obuild
         obuild.build()
@@ -379,18 +383,19 @@ def run_extra(name, world, rank, dev, steps, grid_override=0):
 
     def step(times=None):
         e = [ev()]
+        cs = []
         for s_, w in zip(slabs, Ws):
-            s_.zero_()
+            cs.append(ctx.prebias_(s_, pos.shape[0], w))     # -c instead of 0: the transform sees n - c
             ctx.MA(pos, s_, "CIC", W=w, routed=True)
         e.append(ev())
         marks = {}
         dks = [ctx.fft(s_, slot=i, marks=marks if i == 0 else None) for i, s_ in enumerate(slabs)]
         e.append(ev())
-        o = ctx._spectra(dks, [PKL.MAS_function("CIC")] * nf, 0, nf == 1, density=True)
+        o = ctx._spectra(dks, [PKL.MAS_function("CIC")] * nf, 0, nf == 1, density=True, offset=cs)
         e.append(ev())
         if times is not None:
             torch.cuda.synchronize()
-            for k, (a, b) in zip(("zero+deposit+halo", "slab_fft", "bin+allreduce+finalise+d2h"),
+            for k, (a, b) in zip(("fill+deposit+halo", "slab_fft", "bin+allreduce+finalise+d2h"),
                                  zip(e[:-1], e[1:])):
                 times[k] = times.get(k, 0.0) + a.elapsed_time(b)
             times["transpose_kernels_field0"] = times.get("transpose_kernels_field0", 0.0) + \
@@ -427,8 +432,8 @@ def run_extra(name, world, rank, dev, steps, grid_override=0):
            "stages_ms_max_over_ranks": {k: round(v, 3) for k, v in stage.items()},
            "hbm_peak_allocated_GB_max_over_ranks": peak_gb,
            "rooflines_per_gpu": {
-               "deposit": {"bound": "hbm", "achieved": dep_bytes / (stage["zero+deposit+halo"] * 1e-3) / 1e9, "peak": peak,
-                           "unit": "GB/s", "frac": dep_bytes / (stage["zero+deposit+halo"] * 1e-3) / 1e9 / peak,
+               "deposit": {"bound": "hbm", "achieved": dep_bytes / (stage["fill+deposit+halo"] * 1e-3) / 1e9, "peak": peak,
+                           "unit": "GB/s", "frac": dep_bytes / (stage["fill+deposit+halo"] * 1e-3) / 1e9 / peak,
                            "algorithmic_bytes": dep_bytes, "note": "includes zeroing the slab and the halo exchange"},
                "slab_fft": {"bound": "hbm+nvlink", "lower_bound_bytes": nf * (4 * N ** 3 + 8 * half) / world,
                             "achieved": nf * (4 * N ** 3 + 8 * half) / world / (stage["slab_fft"] * 1e-3) / 1e9,
@@ -465,7 +470,7 @@ def run_ours(args, wl, grid_n):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pyl_b200_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
-    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, _device as D, _lib, synth
+    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, _device as D, _lib, prebias_, synth
     lib = _lib.load()
     MAS, AXIS = wl["mas"], wl["axis"]
     npart = grid_n ** 3
@@ -485,16 +490,16 @@ def run_ours(args, wl, grid_n):
         slab = ctx.new_slab()
 
         def step(p, w):
-            slab.zero_()
+            c = ctx.prebias_(slab, p.shape[0], w)            # -c instead of 0: the transform sees n - c, not n
             ctx.MA(p, slab, MAS, W=w, routed=False)
-            return ctx.Pk(slab, AXIS, MAS, density=True)     # spectrum of n/<n> - 1: the normalisation is a scale
+            return ctx.Pk(slab, AXIS, MAS, density=True, offset=c)   # spectrum of n/<n> - 1: a scale of the sums
     else:
         grid = torch.zeros((grid_n, grid_n, grid_n), dtype=torch.float32, device=dev)
 
         def step(p, w):
-            grid.zero_()
+            c = prebias_(grid, p.shape[0], w)                # -c instead of 0: the transform sees n - c, not n
             MASL.MA(p, grid, BOX, MAS, w)
-            return PKL.Pk(grid, BOX, AXIS, MAS, verbose=False, density=True)   # n/<n> - 1 folded into the scale
+            return PKL.Pk(grid, BOX, AXIS, MAS, verbose=False, density=True, offset=c)   # n/<n> - 1 as a scale
 
     def barrier():
         if world > 1:
@@ -550,12 +555,13 @@ def run_ours(args, wl, grid_n):
     reps = 3
     stages = {}
     if world == 1:
-        acc = {k: 0.0 for k in ("zero", "deposit", "fft", "bin+finalise+d2h")}
+        acc = {k: 0.0 for k in ("fill", "deposit", "fft", "bin+finalise+d2h")}
         for _ in range(reps):
-            e0 = ev(); grid.zero_()
+            e0 = ev(); c = prebias_(grid, pos.shape[0], W)
             e1 = ev(); MASL.MA(pos, grid, BOX, MAS, W)
             e2 = ev(); dk = PKL.fft3d_r2c_device(grid)
-            e3 = ev(); PKL.spectra([dk], [PKL.MAS_function(MAS)], grid_n, AXIS, BOX, want_phase=True, density=True)
+            e3 = ev(); PKL.spectra([dk], [PKL.MAS_function(MAS)], grid_n, AXIS, BOX, want_phase=True, density=True,
+                                   offset=c)
             e4 = ev(); torch.cuda.synchronize()
             for k, (a, b) in zip(acc, ((e0, e1), (e1, e2), (e2, e3), (e3, e4))):
                 acc[k] += a.elapsed_time(b) / reps
@@ -569,13 +575,13 @@ def run_ours(args, wl, grid_n):
         stages["bin_kernels_only"] = round(a.elapsed_time(b) / reps, 4)
         del dk
     else:
-        names = ("zero", "route", "deposit+halo", "fft_yz+transpose(pipelined)", "transpose_kernels",
+        names = ("fill", "route", "deposit+halo", "fft_yz+transpose(pipelined)", "transpose_kernels",
                  "fft_x", "bin+allreduce+finalise+d2h")
         acc = {k: 0.0 for k in names}
         peer_route = ctx._peer is not None and ctx._route_mode == "peer"
         for _ in range(reps):
             barrier()                      # ranks start each repetition together: no inter-rank skew in the stage times
-            e0 = ev(); slab.zero_()
+            e0 = ev(); c = ctx.prebias_(slab, pos.shape[0], W)
             e1 = ev()
             if peer_route:
                 p_r, w_r, cnt = ctx.route_peer(pos, MAS, W)
@@ -584,9 +590,9 @@ def run_ours(args, wl, grid_n):
             e2 = ev(); ctx.MA(p_r, slab, MAS, W=w_r, routed=True, count=cnt)
             e4 = ev(); marks = {}
             dk = ctx.fft(slab, marks=marks)
-            e5 = ev(); ctx._spectra([dk], [PKL.MAS_function(MAS)], AXIS, True, density=True)
+            e5 = ev(); ctx._spectra([dk], [PKL.MAS_function(MAS)], AXIS, True, density=True, offset=c)
             e6 = ev(); torch.cuda.synchronize()
-            pairs = {"zero": (e0, e1), "route": (e1, e2), "deposit+halo": (e2, e4),
+            pairs = {"fill": (e0, e1), "route": (e1, e2), "deposit+halo": (e2, e4),
                      "bin+allreduce+finalise+d2h": (e5, e6)}
             if "t1" in marks:
                 pairs.update({"fft_yz+transpose(pipelined)": (e4, marks["t1"]), "fft_x": (marks["t1"], e5)})

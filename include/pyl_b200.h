@@ -271,9 +271,13 @@ int pyl_pk_finalize(void *acc, int dims, int fields, double BoxSize, int counts_
  * zeroes it in the spectrum (holds_dc = 0: this rank's rows do not contain k = 0; dc is set to 0 so that a SUM
  * all-reduce delivers it everywhere).  pyl_pk_density_scale multiplies the RAW sums of pyl_pk_bin (call it
  * before pyl_pk_finalize) by dims^6 / (dc_i dc_j): autos by 1/<n>_i^2, crosses (pairs i<j in lexicographic
- * order) by 1/(<n>_i <n>_j); counts, k sums and the phase sums are untouched. */
+ * order) by 1/(<n>_i <n>_j); counts, k sums and the phase sums are untouched.
+ * offset (DEVICE float64 [fields], or NULL = zeros): the grids held n_i - offset_i, i.e. the deposit started from
+ * -offset_i instead of 0; <n>_i = offset_i + dc_i / dims^3.  Any constant near <n> keeps the DC mode, and with
+ * it the float32 rounding noise a large DC mode leaves on the axes through k = 0, small. */
 int pyl_pk_take_dc(float *const *delta_k, int fields, int holds_dc, double *dc, pyl_stream_t stream);
-int pyl_pk_density_scale(void *acc, int dims, int fields, const double *dc, pyl_stream_t stream);
+int pyl_pk_density_scale(void *acc, int dims, int fields, const double *dc, const double *offset,
+                         pyl_stream_t stream);
 
 /* Mirrored slab form (multi-GPU): the rank holds the rows |ky| in [ky_lo, ky_lo+ny_lo) of the half-range
  * 0..dims/2 AND their mirrors N-ky, as (dims, nky, dims/2+1) complex64 with the ky axis ordered: first the

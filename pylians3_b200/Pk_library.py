@@ -264,25 +264,48 @@ def take_dc(dk_list, holds_dc=True):
     return dc
 
 
-def density_scale_(out, lay, dims, dc):
-    """pyl_pk_density_scale on the raw accumulators: sums of |FFT(n)|^2 become sums of |FFT(n/<n> - 1)|^2."""
+def _offsets(offset, fields, dev):
+    """`offset=` of Pk/XPk as a float64 CUDA tensor [fields] (None stays None): a number, a sequence of numbers
+    and/or CUDA tensors (what field.prebias_ returned, one per field), or one tensor."""
+    if offset is None:
+        return None
+    if torch.is_tensor(offset):
+        t = offset.to(device=dev, dtype=torch.float64).reshape(-1)
+    elif np.isscalar(offset):
+        t = torch.full((fields,), float(offset), dtype=torch.float64, device=dev)
+    else:
+        t = torch.cat([o.to(device=dev, dtype=torch.float64).reshape(-1) if torch.is_tensor(o)
+                       else torch.full((1,), float(o), dtype=torch.float64, device=dev) for o in offset])
+    if t.numel() == 1 and fields > 1:
+        t = t.expand(fields)
+    if t.numel() != fields:
+        raise ValueError("offset must give one constant per field")
+    return t.contiguous()
+
+
+def density_scale_(out, lay, dims, dc, offset=None):
+    """pyl_pk_density_scale on the raw accumulators: sums of |FFT(n - c)|^2 become sums of |FFT(n/<n> - 1)|^2,
+    <n> = c + dc/dims^3 (offset = c per field as a float64 CUDA tensor, None = 0)."""
     with torch.cuda.device(out.device):
         L.check(L.load().pyl_pk_density_scale(D.ptr(out), int(dims), int(lay.fields), D.ptr(dc),
+                                              D.ptr(offset) if offset is not None else None,
                                               D.stream_ptr(out.device)), "pyl_pk_density_scale")
 
 
-def spectra(dk_list, mas_index, dims, axis, BoxSize, want_phase=False, flags=0, density=False):
+def spectra(dk_list, mas_index, dims, axis, BoxSize, want_phase=False, flags=0, density=False, offset=None):
     """bin + finalise: device finalisation for up to L.MAX_FIELDS fields, host assembly beyond.
-    density=True: the fields are transforms of densities n; the spectra are those of n/<n> - 1."""
+    density=True: the fields are transforms of densities n (minus the constants `offset`); the spectra are those
+    of n/<n> - 1."""
     dc = take_dc(dk_list) if density else None
+    off = _offsets(offset, len(dk_list), dk_list[0].device) if density else None
     if len(dk_list) <= L.MAX_FIELDS:
         out, lay = bin_device(dk_list, mas_index, dims, axis, want_phase and len(dk_list) == 1, flags=flags)
         if density:
-            density_scale_(out, lay, dims, dc)
+            density_scale_(out, lay, dims, dc, off)
         return finalize_device(out, lay, BoxSize, dims)
     raw = bin_fields(dk_list, mas_index, dims, axis, want_phase, flags=flags)
     if density:
-        inv = float(dims) ** 3 / dc.cpu().numpy()
+        inv = 1.0 / ((off.cpu().numpy() if off is not None else 0.0) + dc.cpu().numpy() / float(dims) ** 3)
         pairs = np.array([inv[i] * inv[j] for i in range(len(inv)) for j in range(i + 1, len(inv))])
         for k in ("Pk3D", "Pk1D", "Pk2D"):
             raw[k] = raw[k] * (inv * inv)
@@ -352,9 +375,12 @@ class Pk:
     density=True (not in the reference): `delta` is a DENSITY n (what MA deposited), and the result is the
     spectrum of n/<n> - 1 -- the caller's `delta /= np.mean(delta); delta -= 1` (Pk_snapshot.py:88-89) folded into
     the scale of the binned sums, <n> read from the DC mode, which is then dropped (its Pk2D[0] slot reads 0
-    where the reference leaves the squared rounding residue of sum(delta))."""
+    where the reference leaves the squared rounding residue of sum(delta)).
+    offset=c: the grid holds n - c (the deposit started from -c: `c = prebias_(grid, particles, W)` instead of
+    zeroing it), <n> = c + DC/dims^3.  Recommended from 256^3 on: a float32 transform of a field whose mass sits in
+    the DC mode leaves rounding noise ~1e-7 dims/sigma (relative amplitude) on the axes through k = 0."""
 
-    def __init__(self, delta, BoxSize, axis=2, MAS="CIC", threads=1, verbose=True, density=False):
+    def __init__(self, delta, BoxSize, axis=2, MAS="CIC", threads=1, verbose=True, density=False, offset=None):
         start = time.time()
         if verbose:
             print("\nComputing power spectrum of the field...")
@@ -366,7 +392,8 @@ class Pk:
         dims = delta_d.shape[0]
         delta_k = fft3d_r2c_device(delta_d)
         start2 = time.time()
-        o = spectra([delta_k], [MAS_function(MAS)], dims, axis, BoxSize, want_phase=True, density=density)
+        o = spectra([delta_k], [MAS_function(MAS)], dims, axis, BoxSize, want_phase=True, density=density,
+                    offset=offset)
         if verbose:
             print("Time to complete loop = %.2f" % (time.time() - start2))
         self.k1D, self.Pk1D, self.Nmodes1D = o["k1D"], o["Pk1D"][:, 0], o["Nmodes1D"]
@@ -385,7 +412,7 @@ class XPk:
     PkX1D (.,X), kpar, kper, Nmodes2D, Pk2D (.,F), PkX2D (.,X); pairs i<j in lexicographic order.
     density=True: the fields are densities, the spectra those of n_i/<n_i> - 1 (see Pk)."""
 
-    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1, density=False):
+    def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1, density=False, offset=None):
         start = time.time()
         print("\nComputing power spectra of the fields...")
         D.require_cuda()
@@ -404,7 +431,7 @@ class XPk:
             torch.cuda.synchronize(dev)
         print("Time FFTS = %.2f" % (time.time() - start))
         start2 = time.time()
-        o = spectra(dk, [MAS_function(m) for m in MAS], dims, axis, BoxSize, density=density)
+        o = spectra(dk, [MAS_function(m) for m in MAS], dims, axis, BoxSize, density=density, offset=offset)
         del dk
         print("Time loop = %.2f" % (time.time() - start2))
         self.k1D, self.Nmodes1D = o["k1D"], o["Nmodes1D"]

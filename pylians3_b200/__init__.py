@@ -13,4 +13,4 @@ without a CUDA device, the entry points raise.
 __version__ = "0.1.0"
 
 from . import MAS_library, Pk_library, redshift_space_library, smoothing_library  # noqa: E402,F401
-from .field import overdensity_  # noqa: E402,F401
+from .field import overdensity_, prebias_  # noqa: E402,F401

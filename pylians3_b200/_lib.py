@@ -81,7 +81,7 @@ PROTOTYPES = {
     "pyl_pk_finalize": (_i, [_vp, _i, _i, ctypes.c_double, _i, _vp, _vp, _vp]),
     "pyl_pk_counts_to_f64": (_i, [_vp, _i, _i, _vp]),
     "pyl_pk_take_dc": (_i, [_vp, _i, _i, _vp, _vp]),
-    "pyl_pk_density_scale": (_i, [_vp, _i, _i, _vp, _vp]),
+    "pyl_pk_density_scale": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "pyl_pk_clear_cache": (_i, []),
     "pyl_pk_mirrored_rows": (_i, [_i, _i, _i, ctypes.POINTER(_i)]),
     "pyl_pk_bin_mirrored": (_i, [ctypes.POINTER(_vp), _i, ctypes.POINTER(_i), _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),

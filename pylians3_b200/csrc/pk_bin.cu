@@ -602,6 +602,10 @@ __global__ void __launch_bounds__(256) pk_finalize_kernel(const FinalizeArgs A) 
 // FFT(delta) = FFT(n)/<n> except for the DC mode, which the -1 cancels, and <n> = Re FFT(n)[0] / dims^3: taking
 // the DC mode out of the spectrum and scaling the binned sums by 1/(<n>_i <n>_j) gives every spectrum of delta
 // without the two passes over the grid (a float64 sum and the in-place n/<n> - 1).
+// A float32 transform carries rounding noise proportional to its largest partial sums, and with the whole mass in
+// the DC mode those sit on the three axes through k = 0 (relative amplitude error ~1e-7 dims/sigma there: 1e-4 at
+// 512^3 of unclustered particles).  So the grid may hold n - c for any constant c near <n> (the deposit starts
+// from -c instead of 0, see field.prebias_): then <n> = c + Re FFT[0]/dims^3 exactly, and the DC mode is small.
 struct DcArgs {
     float *dk[PYL_MAX_FIELDS];
     int F, owner;
@@ -622,7 +626,7 @@ __global__ void pk_take_dc_kernel(const DcArgs A) {
 
 struct DensityScaleArgs {
     double *f;
-    const double *dc;
+    const double *dc, *offset;
     double cells;
     int F, X;
     long long o[6], n[6];          // Pk3D, PkX3D, Pk1D, PkX1D, Pk2D, PkX2D: first word, words
@@ -632,7 +636,8 @@ __global__ void __launch_bounds__(256) pk_density_scale_kernel(const DensityScal
     __shared__ double s_auto[PYL_MAX_FIELDS], s_cross[PYL_MAX_FIELDS * (PYL_MAX_FIELDS - 1) / 2 + 1];
     if (threadIdx.x == 0) {
         double inv[PYL_MAX_FIELDS];
-        for (int c = 0; c < A.F; c++) inv[c] = A.cells / A.dc[c];         // 1 / <n>_c
+        for (int c = 0; c < A.F; c++)                                      // 1 / <n>_c
+            inv[c] = 1.0 / ((A.offset ? A.offset[c] : 0.0) + A.dc[c] / A.cells);
         int x = 0;
         for (int i = 0; i < A.F; i++) {
             s_auto[i] = inv[i] * inv[i];
@@ -924,7 +929,8 @@ int pyl_pk_take_dc(float *const *delta_k, int fields, int holds_dc, double *dc, 
     return PYL_OK;
 }
 
-int pyl_pk_density_scale(void *acc, int dims, int fields, const double *dc, pyl_stream_t stream) {
+int pyl_pk_density_scale(void *acc, int dims, int fields, const double *dc, const double *offset,
+                         pyl_stream_t stream) {
     PYL_REQUIRE(acc != nullptr && dc != nullptr, "pyl_pk_density_scale: NULL pointer");
     PYL_REQUIRE(dims > 0 && fields >= 1 && fields <= PYL_MAX_FIELDS, "pyl_pk_density_scale: bad dims/fields");
     pyl_pk_layout_t L;
@@ -932,6 +938,7 @@ int pyl_pk_density_scale(void *acc, int dims, int fields, const double *dc, pyl_
     DensityScaleArgs A;
     A.f = reinterpret_cast<double *>(acc);
     A.dc = dc;
+    A.offset = offset;
     A.cells = (double)dims * (double)dims * (double)dims;
     A.F = L.fields; A.X = L.xfields;
     const long long n3 = L.kmax + 1, n1 = L.kmax_par + 1;

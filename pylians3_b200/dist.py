@@ -444,6 +444,19 @@ class SlabContext:
         self.ops.overdensity_(slab, total, float(self.dims) ** 3)
         return slab
 
+    def prebias_(self, slab, particles, W=None):
+        """field.prebias_ for a slab: every rank fills its planes with the SAME -c (a rank-dependent constant
+        would be a step function along x), c = all-reduced particles * mean(sampled weights) / dims^3.  `particles`
+        and `W` are this rank's share before routing.  Returns c (CUDA float64[1]) for Pk(..., offset=c).
+        CPU stand-ins (tests) zero the slab and return 0."""
+        if self.device.type != "cuda":
+            slab.zero_()
+            return torch.zeros(1, dtype=torch.float64)
+        from . import field
+        scale = field.weight_estimate(particles, W, self.device)
+        dist.all_reduce(scale, group=self.group)
+        return field.prebias_(slab, None, cells=float(self.dims) ** 3, scale=scale)
+
     # ---- distributed r2c: (nx_local, N, N) real -> (N, nky_local, nz) complex ---------------------
     def fft(self, slab, slot=0, marks=None):
         """(nx_local, N, N) real -> (N, nky_local, nz) complex.  With the peer-memory transpose the result lives
@@ -547,7 +560,7 @@ class SlabContext:
             words[off:off + n] = np.rint(f64[off:off + n]).astype(np.int64)
         return PKL.unpack_raw(words, lay)
 
-    def _spectra(self, dk_list, mas_index, axis, want_phase, density=False):
+    def _spectra(self, dk_list, mas_index, axis, want_phase, density=False, offset=None):
         """bin -> all-reduce -> finalisation.  On GPUs the finalisation runs on the device (pyl_pk_finalize)
         and only the finished arrays cross PCIe; the CPU stand-ins of the tests finalise on the host.
         density=True: the slabs held densities n; the rank that holds k = 0 takes dims^3 <n> from the DC modes,
@@ -564,14 +577,16 @@ class SlabContext:
             out.view(torch.float64)[lay.total_words:lay.total_words + extra].copy_(dc)
         f64 = self._reduce(out, lay, extra)
         if density:
-            PKL.density_scale_(out, lay, self.dims, f64[lay.total_words:lay.total_words + extra].clone())
+            PKL.density_scale_(out, lay, self.dims, f64[lay.total_words:lay.total_words + extra].clone(),
+                               PKL._offsets(offset, extra, out.device))
         return PKL.finalize_device(f64.view(torch.int64), lay, self.BoxSize, self.dims, counts_are_f64=True)
 
-    def Pk(self, slab, axis=2, MAS="CIC", density=False):
+    def Pk(self, slab, axis=2, MAS="CIC", density=False, offset=None):
         """Pk_library.Pk of the slab-distributed field; every rank gets the full result.
-        density=True: the slab holds the density n, the spectrum is that of n/<n> - 1 (no overdensity_ pass)."""
+        density=True: the slab holds the density n, the spectrum is that of n/<n> - 1 (no overdensity_ pass);
+        offset=c: it holds n - c (c = prebias_(slab, ...) before the deposit)."""
         dk = self.fft(slab)
-        o = self._spectra([dk], [PKL.MAS_function(MAS)], axis, True, density)
+        o = self._spectra([dk], [PKL.MAS_function(MAS)], axis, True, density, offset)
         r = _Result()
         r.k1D, r.Pk1D, r.Nmodes1D = o["k1D"], o["Pk1D"][:, 0], o["Nmodes1D"]
         r.kpar, r.kper, r.Pk2D, r.Nmodes2D = o["kpar"], o["kper"], o["Pk2D"][:, 0], o["Nmodes2D"]
@@ -579,14 +594,14 @@ class SlabContext:
         r.Pk, r.Pkphase = np.ascontiguousarray(o["Pk"][:, :, 0]), o["Pkphase"]
         return r
 
-    def XPk(self, slabs, axis=2, MAS=None, density=False):
+    def XPk(self, slabs, axis=2, MAS=None, density=False, offset=None):
         """Pk_library.XPk of several slab-distributed fields (<= L.MAX_FIELDS per launch)."""
         if MAS is None or len(MAS) != len(slabs):
             raise TypeError("MAS must be a list with one scheme per field")
         if len(slabs) > L.MAX_FIELDS:
             raise ValueError("the distributed XPk bins at most %d fields per call" % L.MAX_FIELDS)
         dk = [self.fft(s, slot=i) for i, s in enumerate(slabs)]
-        o = self._spectra(dk, [PKL.MAS_function(m) for m in MAS], axis, False, density)
+        o = self._spectra(dk, [PKL.MAS_function(m) for m in MAS], axis, False, density, offset)
         r = _Result()
         r.k1D, r.Nmodes1D, r.Pk1D, r.PkX1D = o["k1D"], o["Nmodes1D"], o["Pk1D"], o["PkX1D"]
         r.kpar, r.kper, r.Nmodes2D, r.Pk2D, r.PkX2D = o["kpar"], o["kper"], o["Nmodes2D"], o["Pk2D"], o["PkX2D"]

@@ -32,3 +32,35 @@ def overdensity_(grid, total=None, cells=None):
         L.check(L.load().pyl_overdensity_inplace(D.ptr(grid), grid.numel(), D.ptr(total), float(cells),
                                                  D.stream_ptr(grid.device)), "pyl_overdensity_inplace")
     return grid
+
+
+def prebias_(grid, particles, W=None, cells=None, scale=None):
+    """Start value for a deposit whose spectrum is taken with Pk(..., density=True, offset=c): fills `grid` with
+    -c, c ~ the mean density the deposit will produce (particles/cells, times the mean of a strided sample of at
+    most 2^20 weights), and returns c -- the exact float32 fill value -- as a CUDA float64[1] tensor.
+
+    Why: a float32 FFT carries rounding noise proportional to its largest partial sums; a density grid has its
+    whole mass in the DC mode and the noise lands on the axes through k = 0.  With the constant taken out beforehand
+    the transform sees n - c, the DC mode is the (small) estimation error of c, and <n> = c + DC/cells exactly.
+    No host synchronisation: c stays on the device.  `scale` (CUDA float64[1]) replaces particles * mean(sample)
+    by an agreed numerator (multi-GPU: the all-reduced one, see SlabContext.prebias_)."""
+    if not D.is_cuda_tensor(grid) or grid.dtype != torch.float32:
+        raise ValueError("grid must be a float32 CUDA tensor")
+    cells = grid.numel() if cells is None else cells
+    if scale is None:
+        scale = weight_estimate(particles, W, grid.device)
+    c32 = (scale / float(cells)).to(torch.float32)
+    grid.fill_((-c32).reshape(()))
+    return c32.to(torch.float64)
+
+
+def weight_estimate(particles, W, device):
+    """particles * mean(W) from a strided sample of at most ~2^20 weights (particles if W is None), as a float64[1]
+    tensor on `device`; W may live on the host (torch tensor or ndarray) or on the device."""
+    if W is None:
+        return torch.full((1,), float(particles), dtype=torch.float64, device=device)
+    if not torch.is_tensor(W):
+        W = torch.from_numpy(W)
+    stride = max(1, W.numel() >> 20)
+    m = W.reshape(-1)[::stride].to(torch.float64).mean().reshape(1) * float(particles)
+    return m.to(device, non_blocking=True)

@@ -338,8 +338,15 @@ def test_full_size_512_against_the_compiled_reference(env):
     want = quiet(RP.Pk, ref, BOX, 0, "CIC", 8, False)
     have = PKL.Pk(torch.from_numpy(ref).cuda(), BOX, 0, "CIC", verbose=False)
     check_pk(have, want, phase_min_modes=64)
-    # and the fused form: OUR density grid, n/<n> - 1 folded into the scale of the binned sums
-    fused = PKL.Pk(grid, BOX, 0, "CIC", verbose=False, density=True)
+    # and the fused form of the bench step: the deposit starts from -c (prebias_), the transform sees n - c, and
+    # n/<n> - 1 is folded into the scale of the binned sums.  (Without the offset the float32 transform of a grid
+    # whose mass sits in the DC mode misses the 1e-4 bar in the single-mode Pk2D bins on the axis through k = 0.)
+    from pylians3_b200 import prebias_
+    pos_d = torch.from_numpy(np.random.default_rng(2).random((N ** 3, 3), dtype=np.float32) * np.float32(BOX)).cuda()
+    c = prebias_(grid, N ** 3)
+    assert float(c) == 1.0
+    MASL.MA(pos_d, grid, BOX, "CIC")
+    fused = PKL.Pk(grid, BOX, 0, "CIC", verbose=False, density=True, offset=c)
     check_pk(fused, want, phase_min_modes=64)
 
 
@@ -372,6 +379,34 @@ def test_pk_of_a_density_equals_pk_of_its_overdensity(env, oracle, N, axis):
         check_pk(got, ref)
         assert torch.equal(d.cpu(), torch.from_numpy(dens[fi]))            # the density is not modified
         assert got.Pk2D[0] == 0.0                                          # the DC mode is dropped, not binned
+        # the grid may hold n - c for any constant c (the deposit started from -c): <n> = c + DC/dims^3
+        c = float(np.float32(0.97 * dens[fi].mean()))
+        got = PKL.Pk(d - c, BOX, axis, mas[fi], verbose=False, density=True, offset=c)
+        check_pk(got, ref)
+
+
+def test_prebias_then_deposit_then_density_spectrum(env, oracle):
+    """The bench step's recipe end to end at a small size: prebias_ (fills -c, c from a sample of the weights,
+    no host sync) -> MA -> Pk(density=True, offset=c) against oracle MA -> delta -> Pk."""
+    torch, MASL, PKL, _ = env
+    from pylians3_b200 import prebias_
+    N = 96
+    pos, W = make_particles(41, 3 * N ** 3, True)
+    ref = np.zeros((N, N, N), np.float32)
+    oracle.MA(pos, ref, BOX, "PCS", W)
+    dens = ref.copy()
+    ref /= np.mean(ref, dtype=np.float64)
+    ref -= 1.0
+    want = oracle.Pk(ref, BOX, 0, "PCS", 1, False)
+    pos_d, W_d = torch.from_numpy(pos).cuda(), torch.from_numpy(W).cuda()
+    for w_arg in (W_d, W):                              # weights on the device, or still on the host
+        grid = torch.empty((N, N, N), dtype=torch.float32, device="cuda")
+        c = prebias_(grid, len(pos), w_arg)
+        assert abs(float(c) / float(dens.mean(dtype=np.float64)) - 1.0) < 0.02
+        assert torch.all(grid == -c.float())
+        MASL.MA(pos_d, grid, BOX, "PCS", W_d)
+        assert rel_err((grid.double() + c).float().cpu().numpy(), dens, floor=float(dens.mean())) < 1e-5
+        check_pk(PKL.Pk(grid, BOX, 0, "PCS", verbose=False, density=True, offset=c), want)
 
 
 @pytest.mark.parametrize("N,F", [(48, 2), (40, 3), (32, 4), (24, 6)])
@@ -380,4 +415,7 @@ def test_xpk_of_densities(env, oracle, N, F):
     dens, delta, mas = make_densities(oracle, N, F, 300 + N + F)
     ref = quiet(oracle.XPk, delta, BOX, 2, mas, 1)
     got = quiet(PKL.XPk, dens, BOX, 2, mas, 1, density=True)
+    check_pk(got, ref, cross=True)
+    cs = [float(np.float32(1.02 * d.mean())) for d in dens]
+    got = quiet(PKL.XPk, [d - np.float32(c) for d, c in zip(dens, cs)], BOX, 2, mas, 1, density=True, offset=cs)
     check_pk(got, ref, cross=True)
