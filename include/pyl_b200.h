@@ -131,6 +131,11 @@ int pyl_sum_f64(const float *x, int64_t n, double *out, pyl_stream_t stream);
  * callers compute it in NumPy (docs/source/construction.rst:50, Pk_snapshot.py:88).  `sum` is a
  * DEVICE double (e.g. from pyl_sum_f64, all-reduced across ranks), so no host sync is needed. */
 int pyl_overdensity_inplace(float *x, int64_t n, const double *sum, double count, pyl_stream_t stream);
+/* x[i] = -c with c = float32(numerator[0] / cells), numerator a DEVICE double; c_out[0] (DEVICE double) = c.
+ * The start value of a deposit whose spectrum is taken with pyl_pk_density_scale(offset = c_out): the grid then
+ * holds n - c and the float32 transform does not carry the whole mass in its DC mode. */
+int pyl_fill_negative(float *x, int64_t n, const double *numerator, double cells, double *c_out,
+                      pyl_stream_t stream);
 /* out[i] += in[i] (ghost-plane merge after the halo exchange) */
 int pyl_add_inplace(float *out, const float *in, int64_t n, pyl_stream_t stream);
 

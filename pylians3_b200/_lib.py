@@ -64,6 +64,7 @@ PROTOTYPES = {
     "pyl_affine_inplace": (_i, [_vp, _i64, _f, _f, _vp]),
     "pyl_sum_f64": (_i, [_vp, _i64, _vp, _vp]),
     "pyl_overdensity_inplace": (_i, [_vp, _i64, _vp, ctypes.c_double, _vp]),
+    "pyl_fill_negative": (_i, [_vp, _i64, _vp, ctypes.c_double, _vp, _vp]),
     "pyl_add_inplace": (_i, [_vp, _vp, _i64, _vp]),
     "pyl_fft_r2c_workspace_bytes": (_sz, [_i]),
     "pyl_fft_r2c": (_i, [_vp, _vp, _i, _vp, _sz, _vp]),

@@ -140,6 +140,26 @@ __global__ void __launch_bounds__(256) sum_f64_kernel(const float *__restrict__ 
     }
 }
 
+// x[i] = -c, c = float32(numerator/cells) read from DEVICE memory; c_out[0] = c as float64 (field.prebias_)
+__global__ void __launch_bounds__(256) fill_negative_kernel(float *__restrict__ x, int64_t n,
+                                                            const double *__restrict__ numerator, double cells,
+                                                            double *__restrict__ c_out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const float c = (float)(numerator[0] / cells);
+    if (tid == 0) c_out[0] = (double)c;
+    const float v = -c;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const int64_t n4 = n >> 2;
+        float4 *x4 = reinterpret_cast<float4 *>(x);
+        const float4 v4 = make_float4(v, v, v, v);
+        for (int64_t i = tid; i < n4; i += stride) x4[i] = v4;
+        for (int64_t i = (n4 << 2) + tid; i < n; i += stride) x[i] = v;
+    } else {
+        for (int64_t i = tid; i < n; i += stride) x[i] = v;
+    }
+}
+
 static int ew_grid(int64_t n) {
     int64_t blocks = (n / 4 + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -197,6 +217,15 @@ int pyl_overdensity_inplace(float *x, int64_t n, const double *sum, double count
     PYL_REQUIRE(sum != nullptr && count > 0.0, "pyl_overdensity_inplace: bad sum/count");
     if (n <= 0) return PYL_OK;
     overdensity_kernel<<<ew_grid(n), 256, 0, as_stream(stream)>>>(x, n, sum, count);
+    PYL_LAUNCH_CHECK();
+    return PYL_OK;
+}
+
+int pyl_fill_negative(float *x, int64_t n, const double *numerator, double cells, double *c_out,
+                      pyl_stream_t stream) {
+    PYL_REQUIRE(x != nullptr || n == 0, "pyl_fill_negative: x is NULL");
+    PYL_REQUIRE(numerator != nullptr && c_out != nullptr && cells > 0.0, "pyl_fill_negative: bad numerator/cells");
+    fill_negative_kernel<<<ew_grid(n > 0 ? n : 1), 256, 0, as_stream(stream)>>>(x, n > 0 ? n : 0, numerator, cells, c_out);
     PYL_LAUNCH_CHECK();
     return PYL_OK;
 }

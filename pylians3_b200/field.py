@@ -44,14 +44,16 @@ def prebias_(grid, particles, W=None, cells=None, scale=None):
     the transform sees n - c, the DC mode is the (small) estimation error of c, and <n> = c + DC/cells exactly.
     No host synchronisation: c stays on the device.  `scale` (CUDA float64[1]) replaces particles * mean(sample)
     by an agreed numerator (multi-GPU: the all-reduced one, see SlabContext.prebias_)."""
-    if not D.is_cuda_tensor(grid) or grid.dtype != torch.float32:
-        raise ValueError("grid must be a float32 CUDA tensor")
+    if not D.is_cuda_tensor(grid) or grid.dtype != torch.float32 or not grid.is_contiguous():
+        raise ValueError("grid must be a contiguous float32 CUDA tensor")
     cells = grid.numel() if cells is None else cells
     if scale is None:
         scale = weight_estimate(particles, W, grid.device)
-    c32 = (scale / float(cells)).to(torch.float32)
-    grid.fill_((-c32).reshape(()))
-    return c32.to(torch.float64)
+    c = torch.empty(1, dtype=torch.float64, device=grid.device)
+    with torch.cuda.device(grid.device):
+        L.check(L.load().pyl_fill_negative(D.ptr(grid), grid.numel(), D.ptr(scale), float(cells), D.ptr(c),
+                                           D.stream_ptr(grid.device)), "pyl_fill_negative")
+    return c
 
 
 def weight_estimate(particles, W, device):
