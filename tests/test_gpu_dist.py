@@ -81,14 +81,16 @@ def _worker(rank, world, port, N, q, transpose="peer"):
         wx = quiet(O.XPk, [refs["PCS"], refs["CIC"]], BOX, 0, ["PCS", "CIC"], 1)
         check_pk(gx, wx, cross=True)
         # density=True: the slabs keep n, the normalisation is the scale of the binned sums (DC mode all-reduced)
-        check_pk(ctx.Pk(dens["PCS"], 1, "PCS", density=True), O.Pk(refs["PCS"], BOX, 1, "PCS", 1, False))
+        check_pk(ctx.Pk(dens["PCS"], 1, "PCS", density=True), O.Pk(refs["PCS"], BOX, 1, "PCS", 1, False),
+                 phase_min_modes=64)
         check_pk(ctx.XPk([dens["PCS"], dens["CIC"]], 0, ["PCS", "CIC"], density=True), wx, cross=True)
         # the bench step's recipe: every rank fills its slab with the same -c, deposits, and passes c on
         slab = ctx.new_slab()
         w_mine = torch.from_numpy(W[mine].copy()).to(dev)
         c = ctx.prebias_(slab, len(w_mine), w_mine)
         ctx.MA(torch.from_numpy(pos[mine].copy()).to(dev), slab, "PCS", w_mine)
-        check_pk(ctx.Pk(slab, 1, "PCS", density=True, offset=c), O.Pk(refs["PCS"], BOX, 1, "PCS", 1, False))
+        check_pk(ctx.Pk(slab, 1, "PCS", density=True, offset=c), O.Pk(refs["PCS"], BOX, 1, "PCS", 1, False),
+                 phase_min_modes=64)
         q.put((rank, "ok", res))
         dist.destroy_process_group()
     except Exception:
