@@ -158,17 +158,19 @@ int pyl_fft_slab_x(float *cols_k, int dims, int nky, void *ws, size_t ws_bytes,
  * (ix, ky, :) of the local (nx, dims, dims/2+1) complex64 output of stage 1 is stored directly into the receive
  * buffer of the rank owning ky -- peer_recv[r] (HOST array of `nranks` DEVICE pointers, peer-mapped; shape
  * (dims, nky_of_rank[r], dims/2+1)) at [x0+ix][ky_row[ky]][:].  ky_owner / ky_row: DEVICE int32 [dims];
- * nky_of_rank: HOST int [nranks].  The caller synchronises the ranks before (buffers free) and after (rows
- * landed).  Replaces "pack + NCCL all-to-all". */
+ * nky_of_rank: HOST int [nranks].  ky_order: DEVICE int32 [dims] or NULL -- the order in which the rows are
+ * issued (a permutation of 0..dims-1); interleave the owners, starting with a different one on every rank, so
+ * that the ranks do not all write to the same receiver at the same time.  The caller synchronises the ranks
+ * before (buffers free) and after (rows landed).  Replaces "pack + NCCL all-to-all". */
 int pyl_transpose_scatter(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
-                          const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
-                          pyl_stream_t stream);
+                          const int *ky_owner, const int *ky_row, const int *ky_order, int dims, int nx, int x0,
+                          int nranks, pyl_stream_t stream);
 /* The same transpose into receive buffers laid out (nky[r], dims, dims/2+1), and the 1D transforms along x of such a
  * buffer (one strided cuFFT call per ky plane).  With x in the middle the x transforms stay inside one
  * (dims, dims/2+1) plane per ky; with x outermost they touch a different 2 MB page per element at 4096^3. */
 int pyl_transpose_scatter_kymajor(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
-                                  const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
-                                  pyl_stream_t stream);
+                                  const int *ky_owner, const int *ky_row, const int *ky_order, int dims, int nx,
+                                  int x0, int nranks, pyl_stream_t stream);
 size_t pyl_fft_slab_x_kymajor_workspace_bytes(int dims);
 int pyl_fft_slab_x_kymajor(float *cols_k, int dims, int nky, void *ws, size_t ws_bytes, pyl_stream_t stream);
 /* Unnormalised inverse c2r, (dims,dims,dims/2+1) complex64 -> (dims,dims,dims) float32, out of place; cuFFT may

@@ -71,8 +71,9 @@ PROTOTYPES = {
     "pyl_fft_slab_workspace_bytes": (_sz, [_i, _i, _i]),
     "pyl_fft_slab_yz": (_i, [_vp, _vp, _i, _i, _vp, _sz, _vp]),
     "pyl_fft_slab_x": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
-    "pyl_transpose_scatter": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i), _vp, _vp, _i, _i, _i, _i, _vp]),
-    "pyl_transpose_scatter_kymajor": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i), _vp, _vp, _i, _i, _i, _i, _vp]),
+    "pyl_transpose_scatter": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i), _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "pyl_transpose_scatter_kymajor": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_i), _vp, _vp, _vp, _i, _i, _i, _i,
+                                           _vp]),
     "pyl_fft_slab_x_kymajor_workspace_bytes": (_sz, [_i]),
     "pyl_fft_slab_x_kymajor": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
     "pyl_fft_clear_plans": (_i, []),

@@ -23,12 +23,17 @@ struct TransposeArgs {
     int nky[TR_MAX_RANKS];
     const int *ky_owner;               // [N] rank owning global row ky
     const int *ky_row;                 // [N] stored row index of ky on its owner
+    const int *ky_order;               // [N] or NULL: row handled by CTA column b (a permutation of 0..N-1)
     int N, nz, nx, x0;
     int ky_major;                      // receive buffers are (nky[r], N, nz) instead of (N, nky[r], nz)
 };
 
 __global__ void __launch_bounds__(TR_THREADS) transpose_scatter_kernel(const TransposeArgs A) {
-    const int ky = blockIdx.x, ix = blockIdx.y;
+    // CTAs are scheduled in blockIdx order.  With ky = blockIdx.x every rank would sweep the owners in the same
+    // order at the same time -- all senders on one or two receivers' NVLink ingress, the other links idle (the
+    // all-to-all incast: 0.44 of the link rate at 4096^3 on 8 GPUs).  ky_order interleaves the owners row by row,
+    // starting with a different owner on every rank, so every wave of CTAs writes to all ranks at once.
+    const int ky = A.ky_order != nullptr ? __ldg(A.ky_order + blockIdx.x) : (int)blockIdx.x, ix = blockIdx.y;
     const int r = __ldg(A.ky_owner + ky), j = __ldg(A.ky_row + ky);
     const float2 *src = A.src + ((int64_t)ix * A.N + ky) * A.nz;
     float2 *dst = A.ky_major ? A.peer[r] + ((int64_t)j * A.N + (A.x0 + ix)) * A.nz
@@ -55,8 +60,8 @@ __global__ void __launch_bounds__(TR_THREADS) transpose_scatter_kernel(const Tra
 using namespace pyl;
 
 static int transpose_scatter(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
-                             const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
-                             int ky_major, pyl_stream_t stream) {
+                             const int *ky_owner, const int *ky_row, const int *ky_order, int dims, int nx, int x0,
+                             int nranks, int ky_major, pyl_stream_t stream) {
     PYL_REQUIRE(nranks >= 1 && nranks <= TR_MAX_RANKS, "pyl_transpose_scatter: 1..16 ranks");
     PYL_REQUIRE(dims > 0 && nx >= 0 && x0 >= 0 && x0 + nx <= dims, "pyl_transpose_scatter: bad plane range");
     if (nx == 0) return PYL_OK;
@@ -70,7 +75,7 @@ static int transpose_scatter(const float *slab_k, void *const *peer_recv, const 
         A.peer[r] = reinterpret_cast<float2 *>(peer_recv[r]);
         A.nky[r] = nky_of_rank[r];
     }
-    A.ky_owner = ky_owner; A.ky_row = ky_row;
+    A.ky_owner = ky_owner; A.ky_row = ky_row; A.ky_order = ky_order;
     A.N = dims; A.nz = dims / 2 + 1; A.nx = nx; A.x0 = x0; A.ky_major = ky_major;
     transpose_scatter_kernel<<<dim3((unsigned)dims, (unsigned)nx), TR_THREADS, 0, as_stream(stream)>>>(A);
     PYL_LAUNCH_CHECK();
@@ -78,9 +83,10 @@ static int transpose_scatter(const float *slab_k, void *const *peer_recv, const 
 }
 
 extern "C" int pyl_transpose_scatter(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
-                                     const int *ky_owner, const int *ky_row, int dims, int nx, int x0, int nranks,
-                                     pyl_stream_t stream) {
-    return transpose_scatter(slab_k, peer_recv, nky_of_rank, ky_owner, ky_row, dims, nx, x0, nranks, 0, stream);
+                                     const int *ky_owner, const int *ky_row, const int *ky_order, int dims, int nx,
+                                     int x0, int nranks, pyl_stream_t stream) {
+    return transpose_scatter(slab_k, peer_recv, nky_of_rank, ky_owner, ky_row, ky_order, dims, nx, x0, nranks, 0,
+                             stream);
 }
 
 // Same, into receive buffers laid out (nky[r], N, nz): the x axis in the MIDDLE.  The 1D transforms along x then
@@ -88,7 +94,8 @@ extern "C" int pyl_transpose_scatter(const float *slab_k, void *const *peer_recv
 // buffer -- at 4096^3 over 8 ranks the latter touches a different 2 MB page for every x (TLB-bound: 83 ms for the
 // x transforms, profiles/r2_config5_pieces.md).
 extern "C" int pyl_transpose_scatter_kymajor(const float *slab_k, void *const *peer_recv, const int *nky_of_rank,
-                                             const int *ky_owner, const int *ky_row, int dims, int nx, int x0,
-                                             int nranks, pyl_stream_t stream) {
-    return transpose_scatter(slab_k, peer_recv, nky_of_rank, ky_owner, ky_row, dims, nx, x0, nranks, 1, stream);
+                                             const int *ky_owner, const int *ky_row, const int *ky_order, int dims,
+                                             int nx, int x0, int nranks, pyl_stream_t stream) {
+    return transpose_scatter(slab_k, peer_recv, nky_of_rank, ky_owner, ky_row, ky_order, dims, nx, x0, nranks, 1,
+                             stream);
 }

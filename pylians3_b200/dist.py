@@ -20,6 +20,7 @@ a kernel of libpyl_b200.so reached through `DeviceOps`.  The CPU tests inject nu
 those kernels to exercise the communication skeleton with world_size 2 and no GPU.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -51,6 +52,20 @@ def mirrored_rows(dims, ky_lo, ny_lo):
     lower = list(range(ky_lo, ky_lo + ny_lo))
     upper = sorted(dims - ky for ky in lower if ky != 0 and not (dims % 2 == 0 and ky == m))
     return lower + upper
+
+
+def interleaved_row_order(ky_rows, rank):
+    """Issue order of the ky rows in the peer-memory transpose of `rank`: row i of owner rank+1, row i of owner
+    rank+2, ..., row i of `rank` itself, then rows i+1.  Every wave of CTAs then writes to ALL ranks, and no two
+    senders start on the same receiver (an all-to-all in lock step puts every sender on one receiver's link)."""
+    P = len(ky_rows)
+    order = []
+    for i in range(max(len(r) for r in ky_rows)):
+        for d in range(1, P + 1):
+            rows = ky_rows[(rank + d) % P]
+            if i < len(rows):
+                order.append(rows[i])
+    return order
 
 
 def _row_runs(rows):
@@ -138,15 +153,16 @@ class DeviceOps:
         L.check(self.lib.pyl_fft_slab_x(D.ptr(cols), dims, nky, D.ptr(ws), need, self._s()), "pyl_fft_slab_x")
         return cols
 
-    def transpose_scatter(self, a, peer_ptrs, nky_of_rank, ky_owner, ky_row, dims, x0, ky_major=False):
+    def transpose_scatter(self, a, peer_ptrs, nky_of_rank, ky_owner, ky_row, dims, x0, ky_major=False, ky_order=None):
         """Rows of the local (nx, dims, nz) stage-1 output -> receive buffers of their owner ranks (peer stores).
-        ky_major: the receive buffers are (nky, dims, nz) instead of (dims, nky, nz)."""
+        ky_major: the receive buffers are (nky, dims, nz) instead of (dims, nky, nz).  ky_order (int32 CUDA tensor
+        [dims], a permutation): the order in which the rows are issued (see interleaved_row_order)."""
         P = len(peer_ptrs)
         ptrs = (ctypes.c_void_p * P)(*[int(p) for p in peer_ptrs])
         nky = (ctypes.c_int * P)(*[int(n) for n in nky_of_rank])
         fn = self.lib.pyl_transpose_scatter_kymajor if ky_major else self.lib.pyl_transpose_scatter
-        L.check(fn(D.ptr(a), ptrs, nky, D.ptr(ky_owner), D.ptr(ky_row), dims, a.shape[0], int(x0), P, self._s()),
-                "pyl_transpose_scatter")
+        L.check(fn(D.ptr(a), ptrs, nky, D.ptr(ky_owner), D.ptr(ky_row), D.ptr(ky_order) if ky_order is not None else None,
+                   dims, a.shape[0], int(x0), P, self._s()), "pyl_transpose_scatter")
 
     def fft_x_kymajor_(self, cols, dims):
         """In-place 1D transforms along x of a (nky, dims, nz) complex64 array (x is the MIDDLE axis)."""
@@ -208,7 +224,6 @@ class SlabContext:
         self._peer = None
         self._peer_slots = {}
         self._route = None
-        import os
         self._route_mode = os.environ.get("PYL_ROUTE", "peer")      # "nccl": argsort + all_to_all_single
         if self.device.type == "cuda" and self.world > 1 and os.environ.get("PYL_TRANSPOSE", "peer") == "peer":
             self._peer = self._setup_peer()
@@ -239,8 +254,9 @@ class SlabContext:
                 idx = torch.tensor(rows, dtype=torch.long)
                 owner[idx] = r
                 row[idx] = torch.arange(len(rows), dtype=torch.int32)
+            order = torch.tensor(interleaved_row_order(self.ky_rows, self.rank), dtype=torch.int32)
             state = {"symm": symm, "group": grp, "owner": owner.to(self.device), "row": row.to(self.device),
-                     "nky": [len(r) for r in self.ky_rows]}
+                     "order": order.to(self.device), "nky": [len(r) for r in self.ky_rows]}
         except Exception as e:                                   # symmetric memory unusable: NCCL all-to-all
             why = str(e)
         ok = torch.tensor([1 if state is not None else 0], dtype=torch.int32, device=self.device)
@@ -500,7 +516,9 @@ class SlabContext:
                     side.wait_event(ready)
                     ea = mark(stream=side)
                     self.ops.transpose_scatter(a, ptrs, self._peer["nky"], self._peer["owner"], self._peer["row"], N,
-                                               self.x_range[0] + b0, ky_major=ky_major)
+                                               self.x_range[0] + b0, ky_major=ky_major,
+                                               ky_order=None if os.environ.get("PYL_TRANSPOSE_ORDER") == "plain"
+                                               else self._peer["order"])
                     eb = mark(stream=side)
                     if ea is not None:
                         marks.setdefault("pairs", []).append((ea, eb))
