@@ -291,6 +291,14 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- which items -------------------------------------------------------------------------------------
+    // Pass 2 is persistent: 2 CTAs per SM walk the (super-tile, replica) sub-segments of buf1 and take the PP-record
+    // chunks of the non-empty ones.  (One CTA per possible chunk was ~380 000 CTAs at 1024^3, 1.8 ms of work
+    // lookups even when pass 1 had sent everything straight to the tiles.)  Segment order: PYL_P2_GROUP replicas of
+    // one super-tile, then the next super-tile -- CTAs running at the same time reserve runs on DIFFERENT bucket
+    // cursors (same-address atomics serialise) while the runs written at the same time still fall into a limited
+    // set of buckets (L2 write combining).  Warp 0 keeps the walk state; 32 candidate segments per look-up round.
+    unsigned seg_next = blockIdx.x, w_super = 0, w_at = 0, w_fill = 0;
+    for (;;) {
     int64_t first;              // index of this CTA's first item (particle index / slot of buf1)
     int n_in;                   // items of this CTA
     unsigned super = 0, repl = 0;
@@ -302,40 +310,43 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         repl = blockIdx.x % g.repl;
     } else {
         if (warp == 0) {
-            // CTAs that run at the same time (neighbouring blockIdx) take chunks of DIFFERENT super-tiles: the
-            // chunks of one super-tile all reserve runs on the same few hundred bucket cursors, and same-address
-            // atomics serialise (the straight order made this pass as slow as its atomics)
-            // ... in groups of PYL_P2_GROUP consecutive chunks per super-tile, so that the runs written at the same time
-            // still fall into a limited set of buckets (L2 write combining)
-            const unsigned rows = gridDim.x / g.nsuper;
-            const unsigned grp = blockIdx.x / PYL_P2_GROUP, in_grp = blockIdx.x % PYL_P2_GROUP;
-            const unsigned b = (grp % g.nsuper) * rows + (grp / g.nsuper) * PYL_P2_GROUP + in_grp;
-            // largest s with repl*spre[s] <= b: spre is non-decreasing, so it is (number of such s) - 1; the lanes
-            // count in parallel (a binary search by one thread was ~10 dependent L2 round trips per CTA)
-            unsigned below = 0;
-            for (unsigned s = lane; s < g.nsuper; s += 32) below += (__ldg(a.spre + s) * g.repl <= b) ? 1u : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-            const unsigned total = __ldg(a.spre + g.nsuper) * g.repl;
-            if (lane == 0) {
-                misc[18] = 0u;
-                if (b < total) {
-                    const unsigned lo = below - 1u;
-                    const unsigned nch = __ldg(a.spre + lo + 1) - __ldg(a.spre + lo);
-                    const unsigned rem = b - __ldg(a.spre + lo) * g.repl;
-                    const unsigned r = rem / nch, c = rem - r * nch;
-                    const Segment sg = super_segment(a.starts, g, lo, r);
-                    const unsigned fill = min(a.cur1[r * g.nsuper + lo], sg.begin + sg.cap);
-                    const unsigned b0 = sg.begin + c * PP;
-                    misc[16] = lo;
-                    misc[17] = b0;
-                    misc[18] = b0 < fill ? min((unsigned)PP, fill - b0) : 0u;
+            if (w_at >= w_fill) {
+                const unsigned G = min((unsigned)PYL_P2_GROUP, g.repl);
+                const unsigned nseg = (g.repl + G - 1) / G * G * g.nsuper;
+                while (seg_next < nseg) {
+                    const unsigned my = seg_next + lane * gridDim.x;
+                    unsigned mb = 0, mf = 0, ms = 0;
+                    if (my < nseg) {
+                        const unsigned s = (my / G) % g.nsuper, r = my / (G * g.nsuper) * G + my % G;
+                        if (r < g.repl) {
+                            const Segment sg = super_segment(a.starts, g, s, r);
+                            mf = min(a.cur1[r * g.nsuper + s], sg.begin + sg.cap);
+                            mb = sg.begin;
+                            ms = s;
+                        }
+                    }
+                    const unsigned hit = __ballot_sync(0xffffffffu, mf > mb);
+                    if (hit != 0u) {
+                        const int l = __ffs(hit) - 1;
+                        w_super = __shfl_sync(0xffffffffu, ms, l);
+                        w_at = __shfl_sync(0xffffffffu, mb, l);
+                        w_fill = __shfl_sync(0xffffffffu, mf, l);
+                        seg_next += (unsigned)(l + 1) * gridDim.x;
+                        break;
+                    }
+                    seg_next += 32u * gridDim.x;
                 }
             }
+            if (lane == 0) {
+                misc[16] = w_super;
+                misc[17] = w_at;
+                misc[18] = w_at < w_fill ? min((unsigned)PP, w_fill - w_at) : 0u;
+            }
+            if (w_at < w_fill) w_at += PP;
         }
         __syncthreads();
         n_in = (int)misc[18];
-        if (n_in == 0) return;
+        if (n_in == 0) return;                      // the walk is over
         super = misc[16];
         first = misc[17];
     }
@@ -500,9 +511,10 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
     __syncthreads();
 
     // ---- exclusive scan of the bin counts; one global reservation per non-empty bin -------------------------------
+    constexpr int EPT = MAX_BINS / PT;          // 4 bins per thread
+    unsigned c[EPT], got[EPT], end[EPT], run0;
     {
-        constexpr int EPT = MAX_BINS / PT;          // 4 bins per thread
-        unsigned c[EPT], sum = 0;
+        unsigned sum = 0;
 #pragma unroll
         for (int i = 0; i < EPT; i++) {
             const int b = tid * EPT + i;
@@ -520,9 +532,11 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         unsigned run = incl - sum;
 #pragma unroll
         for (int w = 0; w < PT / 32; w++) run += (w < warp) ? misc[w] : 0u;
-        // the reservations of this thread's bins are issued back to back (their results are consumed afterwards):
-        // returning global atomics take microseconds under load
-        unsigned got[EPT], end[EPT], btile[EPT];
+        run0 = run;
+        // the reservations of this thread's bins are issued back to back and consumed only AFTER the records have
+        // been staged: returning global atomics take microseconds under load, and the staging below needs nothing
+        // but the CTA-local bin starts
+        unsigned btile[EPT];
 #pragma unroll
         for (int i = 0; i < EPT; i++) {
             const int b = tid * EPT + i;
@@ -551,14 +565,8 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
 #pragma unroll
         for (int i = 0; i < EPT; i++) {
             const int b = tid * EPT + i;
-            if (b < nb) {
-                cnt[b] = run;
-                if (c[i] > 0) {
-                    goff[b] = got[i] - run;
-                    lim[b] = end[i];
-                }
-                run += c[i];
-            }
+            if (b < nb) cnt[b] = run;
+            run += c[i];
         }
         if (tid == PT - 1) misc[20] = run;         // items staged by this CTA
     }
@@ -582,6 +590,19 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         for (int o = 16; o > 0; o >>= 1) wabs += __shfl_xor_sync(0xffffffffu, wabs, o);
         if (lane == 0 && wabs != 0.0f) atomicAdd(a.wsum, (double)wabs);
     }
+    {
+        // now the reservations: global slot of sorted index 0 of every bin, and the end of its segment
+        unsigned run = run0;
+#pragma unroll
+        for (int i = 0; i < EPT; i++) {
+            const int b = tid * EPT + i;
+            if (b < nb && c[i] > 0) {
+                goff[b] = got[i] - run;
+                lim[b] = end[i];
+            }
+            run += c[i];
+        }
+    }
     __syncthreads();
 
     // ---- runs out: consecutive lanes write consecutive slots of a bin -------------------------------------------------
@@ -594,6 +615,9 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
         else overflow_deposit<MAS, WEIGHTED>(v.x, v.y, v.z, v.w, g, a.number, &dropped);
     }
     if (a.dropped != nullptr && dropped != 0) atomicAdd(a.dropped, dropped);
+    if (LEVEL == 1) return;
+    __syncthreads();                                // the next chunk reuses the staging area and the bin tables
+    }
 }
 
 // ---- 5. per-tile deposit ------------------------------------------------------------------------------------------
@@ -898,9 +922,7 @@ static int run_tiled_w(const float *pos, float *number, const float *W, int64_t 
     partition_kernel<MAS, WEIGHTED, 1><<<ctas1, PT, part_smem_bytes((int)g.nsuper), stream>>>(a, g);
     PYL_LAUNCH_CHECK();
     a.out = w.buf2;
-    // upper bound of the chunk count, rounded up to a multiple of nsuper (pass 2 walks it transposed)
-    const unsigned unit = g.nsuper * PYL_P2_GROUP;
-    const unsigned ctas2 = (unsigned)((w.slots / PP + (size_t)g.repl * g.nsuper + unit) / unit * unit);
+    const unsigned ctas2 = 2u * (unsigned)sm_count();          // persistent: two CTAs per SM walk the segments
     partition_kernel<MAS, WEIGHTED, 2><<<ctas2, PT, part_smem_bytes(1 << g.tps_shift), stream>>>(a, g);
     PYL_LAUNCH_CHECK();
     // bulk reductions need 16-byte aligned 128-byte rows: whole tiles along z and an aligned grid
