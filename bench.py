@@ -391,10 +391,14 @@ def run_extra(name, world, rank, dev, steps, grid_override=0):
         marks = {}
         dks = [ctx.fft(s_, slot=i, marks=marks if i == 0 else None) for i, s_ in enumerate(slabs)]
         e.append(ev())
-        o = ctx._spectra(dks, [PKL.MAS_function("CIC")] * nf, 0, nf == 1, density=True, offset=cs)
+        smarks = {}
+        o = ctx._spectra(dks, [PKL.MAS_function("CIC")] * nf, 0, nf == 1, density=True, offset=cs, marks=smarks)
         e.append(ev())
         if times is not None:
             torch.cuda.synchronize()
+            for k, (a, b) in (("bin_kernels", (e[-2], smarks["binned"])), ("allreduce(+wait for the slowest rank)",
+                              (smarks["binned"], smarks["reduced"])), ("finalise+d2h", (smarks["reduced"], e[-1]))):
+                times[k] = times.get(k, 0.0) + a.elapsed_time(b)
             for k, (a, b) in zip(("fill+deposit+halo", "slab_fft", "bin+allreduce+finalise+d2h"),
                                  zip(e[:-1], e[1:])):
                 times[k] = times.get(k, 0.0) + a.elapsed_time(b)

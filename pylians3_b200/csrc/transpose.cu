@@ -14,7 +14,13 @@
 
 namespace pyl {
 
-constexpr int TR_THREADS = 128;
+#ifndef PYL_TR_THREADS
+#define PYL_TR_THREADS 256
+#endif
+#ifndef PYL_TR_V
+#define PYL_TR_V 2           // 1: 8-byte stores; 2: 16-byte stores after aligning the destination row
+#endif
+constexpr int TR_THREADS = PYL_TR_THREADS;
 constexpr int TR_MAX_RANKS = 16;
 
 struct TransposeArgs {
@@ -38,6 +44,7 @@ __global__ void __launch_bounds__(TR_THREADS) transpose_scatter_kernel(const Tra
     const float2 *src = A.src + ((int64_t)ix * A.N + ky) * A.nz;
     float2 *dst = A.ky_major ? A.peer[r] + ((int64_t)j * A.N + (A.x0 + ix)) * A.nz
                              : A.peer[r] + ((int64_t)(A.x0 + ix) * A.nky[r] + j) * A.nz;
+#if PYL_TR_V == 1
     // four loads in flight per thread before the first peer store: a store over NVLink costs microseconds of latency,
     // and with one element per iteration the row (16 KB at 4096^3) was latency-bound
     for (int kz0 = threadIdx.x; kz0 < A.nz; kz0 += 4 * TR_THREADS) {
@@ -53,6 +60,39 @@ __global__ void __launch_bounds__(TR_THREADS) transpose_scatter_kernel(const Tra
             if (kz < A.nz) dst[kz] = v[u];
         }
     }
+#else
+    // 16-byte peer stores: rows are nz = dims/2+1 complex64 long (odd for even dims), so a row starts on an 8-byte
+    // boundary only; one leading element aligns the DESTINATION, the body moves pairs (a warp stores 512 contiguous
+    // bytes per instruction), one trailing element may remain.  Four pairs per thread are loaded before the first
+    // store leaves: a store over NVLink costs microseconds of latency.
+    const int head = (int)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1u);
+    if (head && threadIdx.x == 0) dst[0] = __ldg(src);
+    const int npair = (A.nz - head) >> 1;
+    const float2 *s2 = src + head;
+    float4 *d4 = reinterpret_cast<float4 *>(dst + head);
+    const bool src16 = (reinterpret_cast<uintptr_t>(s2) & 15u) == 0;
+    for (int p0 = threadIdx.x; p0 < npair; p0 += 4 * TR_THREADS) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int p = p0 + u * TR_THREADS;
+            if (p < npair) {
+                if (src16) {
+                    v[u] = __ldg(reinterpret_cast<const float4 *>(s2) + p);
+                } else {
+                    const float2 a = __ldg(s2 + 2 * p), b = __ldg(s2 + 2 * p + 1);
+                    v[u] = make_float4(a.x, a.y, b.x, b.y);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int p = p0 + u * TR_THREADS;
+            if (p < npair) d4[p] = v[u];
+        }
+    }
+    if (((A.nz - head) & 1) && threadIdx.x == 32) dst[A.nz - 1] = __ldg(src + A.nz - 1);
+#endif
 }
 
 }  // namespace pyl

@@ -279,8 +279,12 @@ class SlabContext:
         return s
 
     def _side_stream(self):
+        """Stream of the transposes.  HIGH priority: its CTAs take the SM slots the 2D-FFT kernels of the main
+        stream free up, so the NVLink traffic runs at its own pace instead of waiting behind the next FFT batch
+        (alone the kernel reaches 0.8 of the link rate; queued behind cuFFT at equal priority it got 0.45)."""
         if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            prio = int(os.environ.get("PYL_SIDE_PRIORITY", "-1"))
+            self._side = torch.cuda.Stream(device=self.device, priority=prio)
         return self._side
 
     def _buf(self, name, shape, dtype):
@@ -578,22 +582,30 @@ class SlabContext:
             words[off:off + n] = np.rint(f64[off:off + n]).astype(np.int64)
         return PKL.unpack_raw(words, lay)
 
-    def _spectra(self, dk_list, mas_index, axis, want_phase, density=False, offset=None):
+    def _spectra(self, dk_list, mas_index, axis, want_phase, density=False, offset=None, marks=None):
         """bin -> all-reduce -> finalisation.  On GPUs the finalisation runs on the device (pyl_pk_finalize)
         and only the finished arrays cross PCIe; the CPU stand-ins of the tests finalise on the host.
         density=True: the slabs held densities n; the rank that holds k = 0 takes dims^3 <n> from the DC modes,
-        the values ride the all-reduce behind the accumulators, and the sums are scaled to those of n/<n> - 1."""
+        the values ride the all-reduce behind the accumulators, and the sums are scaled to those of n/<n> - 1.
+        marks (a dict, bench.py): CUDA events "binned" (bin kernels done) and "reduced" (all-reduce done)."""
         if self.device.type != "cuda":
             if density:
                 raise NotImplementedError("density=True needs the CUDA path")
             return PKL._finalize(self._raw(dk_list, mas_index, axis, want_phase), self.BoxSize, self.dims)
+
+        def mark(key):
+            if marks is not None:
+                marks[key] = torch.cuda.Event(enable_timing=True)
+                marks[key].record()
         dc = PKL.take_dc(dk_list, holds_dc=(self.ky_lo == 0 and self.ny_lo > 0)) if density else None
         out, lay = self.ops.bin(dk_list, mas_index, self.dims, axis, want_phase, self.ky_lo, self.ny_lo)
         extra = 0
         if density:
             extra = len(dk_list)                   # (kpar/kper scratch: finalisation overwrites it afterwards)
             out.view(torch.float64)[lay.total_words:lay.total_words + extra].copy_(dc)
+        mark("binned")
         f64 = self._reduce(out, lay, extra)
+        mark("reduced")
         if density:
             PKL.density_scale_(out, lay, self.dims, f64[lay.total_words:lay.total_words + extra].clone(),
                                PKL._offsets(offset, extra, out.device))
