@@ -206,12 +206,21 @@ def bin_fields(dk_list, mas_index, dims, axis, want_phase=False, ky_lo=0, nky=No
     return res
 
 
-def finalize_device(out, lay, BoxSize, dims, counts_are_f64=False):
+class _Spectra(dict):
+    """Result dict of finalize_device: "kpar"/"kper" appear on first access (host index arithmetic from "kgrid")."""
+
+    def __missing__(self, key):
+        if key in ("kpar", "kper"):
+            self["kpar"], self["kper"] = _kpar_kper(*self["kgrid"])
+            return self[key]
+        raise KeyError(key)
+
+
+def finalize_device(out, lay, BoxSize, dims, counts_are_f64=False, k2d_on_device=False):
     """Finalise the accumulators on the device (pyl_pk_finalize) and return the reference's attribute arrays
     (same dict as `_finalize`).
 
-    `out` must have room for lay.total_words + 2*lay.n2d words (bin_device allocates that): kpar/kper are
-    written behind the accumulators.  The finished block crosses PCIe ONCE into a pinned host block
+    The finished block crosses PCIe ONCE into a pinned host block
     (_device.result_block) and the returned arrays are views of that block: they keep it out of circulation
     until the caller drops them.  No multi-MB NumPy temporaries: at 1024^3 their page faults alone
     cost several ms per call."""
@@ -219,10 +228,15 @@ def finalize_device(out, lay, BoxSize, dims, counts_are_f64=False):
     n2 = lay.n2d
     with torch.cuda.device(dev):
         f64 = out.view(torch.float64)
-        kp = f64[lay.total_words:lay.total_words + n2]
-        kq = f64[lay.total_words + n2:lay.total_words + 2 * n2]
+        kp = kq = None
+        if k2d_on_device:         # kpar/kper written behind the accumulators by the kernel and shipped with them
+            kp = f64[lay.total_words:lay.total_words + n2]
+            kq = f64[lay.total_words + n2:lay.total_words + 2 * n2]
+        else:
+            f64 = f64[:lay.total_words]
         L.check(L.load().pyl_pk_finalize(D.ptr(out), int(dims), int(lay.fields), float(BoxSize),
-                                         1 if counts_are_f64 else 0, D.ptr(kp), D.ptr(kq), D.stream_ptr(dev)),
+                                         1 if counts_are_f64 else 0, D.ptr(kp) if kp is not None else None,
+                                         D.ptr(kq) if kq is not None else None, D.stream_ptr(dev)),
                 "pyl_pk_finalize")
         block, f = D.result_block(f64.numel())
         block[:f64.numel()].copy_(f64, non_blocking=True)
@@ -234,13 +248,17 @@ def finalize_device(out, lay, BoxSize, dims, counts_are_f64=False):
     def arr(off, *shape, skip=0):
         return f[off:off + int(np.prod(shape))].reshape(shape)[skip:]
 
-    o = {}
+    o = _Spectra()
     Nm1 = arr(lay.Nm1D, n1, skip=1)
     with np.errstate(invalid="ignore", divide="ignore"):
         o["k1D"] = ((Nm1 * np.arange(1, n1, dtype=np.float64)) / Nm1) * kF
     o["Nmodes1D"] = Nm1
     o["Pk1D"], o["PkX1D"] = arr(lay.Pk1D, n1, F, skip=1), arr(lay.PkX1D, n1, X, skip=1)
-    o["kpar"], o["kper"] = arr(lay.total_words, n2), arr(lay.total_words + n2, n2)
+    # kpar/kper are pure index arithmetic (Pk_library.pyx:394-399): the result classes compute them on first access
+    # (K2D) instead of shipping 16 bytes per 2D bin across PCIe with every result (95 MB at 4096^3)
+    o["kgrid"] = (lay.kmax_par, lay.kmax_per, kF)
+    if k2d_on_device:
+        o["kpar"], o["kper"] = arr(lay.total_words, n2), arr(lay.total_words + n2, n2)
     o["Nmodes2D"], o["Pk2D"], o["PkX2D"] = arr(lay.Nm2D, n2), arr(lay.Pk2D, n2, F), arr(lay.PkX2D, n2, X)
     Nm3 = arr(lay.Nm3D, n3)
     check_number_modes(Nm3, dims)
@@ -349,6 +367,7 @@ def _finalize(raw, BoxSize, dims):
     o["k1D"], o["Nmodes1D"] = k1D, Nm1
     # 2D: DC bin kept
     o["kpar"], o["kper"] = _kpar_kper(kmax_par, kmax_per, kF)
+    o["kgrid"] = (kmax_par, kmax_per, kF)
     with np.errstate(invalid="ignore", divide="ignore"):
         o["Pk2D"] = raw["Pk2D"] * fact / raw["Nm2D"][:, None]
         o["PkX2D"] = raw["PkX2D"] * fact / raw["Nm2D"][:, None]
@@ -366,7 +385,27 @@ def _finalize(raw, BoxSize, dims):
     return o
 
 
-class Pk:
+class K2D:
+    """kpar / kper of the 2D arrays (bin-centre coordinates, Pk_library.pyx:394-399): pure index arithmetic, computed
+    on the host at first access from `_kgrid` = (kmax_par, kmax_per, kF) and kept."""
+    _kgrid = None
+
+    def _k2d(self):
+        v = self.__dict__.get("_k2d_v")
+        if v is None:
+            v = self.__dict__["_k2d_v"] = _kpar_kper(*self._kgrid)
+        return v
+
+    @property
+    def kpar(self):
+        return self._k2d()[0]
+
+    @property
+    def kper(self):
+        return self._k2d()[1]
+
+
+class Pk(K2D):
     """1D, 2D and 3D power spectrum of a density field (Pk_library.pyx:263-420).
 
     Attributes: k3D, Pk (kmax,3: l=0,2,4), Nmodes3D, Pkphase, k1D, Pk1D, Nmodes1D, kpar, kper,
@@ -397,7 +436,7 @@ class Pk:
         if verbose:
             print("Time to complete loop = %.2f" % (time.time() - start2))
         self.k1D, self.Pk1D, self.Nmodes1D = o["k1D"], o["Pk1D"][:, 0], o["Nmodes1D"]
-        self.kpar, self.kper = o["kpar"], o["kper"]
+        self._kgrid = o["kgrid"]
         self.Pk2D, self.Nmodes2D = o["Pk2D"][:, 0], o["Nmodes2D"]
         self.k3D, self.Nmodes3D = o["k3D"], o["Nmodes3D"]
         self.Pk, self.Pkphase = np.ascontiguousarray(o["Pk"][:, :, 0]), o["Pkphase"]
@@ -405,7 +444,7 @@ class Pk:
             print("Time taken = %.2f seconds" % (time.time() - start))
 
 
-class XPk:
+class XPk(K2D):
     """Auto- and cross-power spectra of several fields (Pk_library.pyx:529-793).
 
     Attributes: k3D, Nmodes3D, Pk (kmax,3,F), XPk (kmax,3,X), k1D, Nmodes1D, Pk1D (.,F),
@@ -436,7 +475,7 @@ class XPk:
         print("Time loop = %.2f" % (time.time() - start2))
         self.k1D, self.Nmodes1D = o["k1D"], o["Nmodes1D"]
         self.Pk1D, self.PkX1D = o["Pk1D"], o["PkX1D"]
-        self.kpar, self.kper, self.Nmodes2D = o["kpar"], o["kper"], o["Nmodes2D"]
+        self._kgrid, self.Nmodes2D = o["kgrid"], o["Nmodes2D"]
         self.Pk2D, self.PkX2D = o["Pk2D"], o["PkX2D"]
         self.k3D, self.Nmodes3D = o["k3D"], o["Nmodes3D"]
         self.Pk, self.XPk = o["Pk"], o["XPk"]

@@ -217,7 +217,7 @@ class XPk_plane:
 
 
 # ---- 3D: variants of XPk --------------------------------------------------------------------------------------
-class XPk_imag:
+class XPk_imag(_P.K2D):
     """XPk with the cross term imag_i*real_j - real_i*imag_j (Pk_library.pyx:811-1077); same attributes as XPk."""
 
     def __init__(self, delta, BoxSize, axis=2, MAS=None, threads=1):
@@ -241,7 +241,7 @@ class XPk_imag:
         del dk
         print("Time loop = %.2f" % (time.time() - start2))
         self.k1D, self.Nmodes1D, self.Pk1D, self.PkX1D = o["k1D"], o["Nmodes1D"], o["Pk1D"], o["PkX1D"]
-        self.kpar, self.kper, self.Nmodes2D = o["kpar"], o["kper"], o["Nmodes2D"]
+        self._kgrid, self.Nmodes2D = o["kgrid"], o["Nmodes2D"]
         self.Pk2D, self.PkX2D = o["Pk2D"], o["PkX2D"]
         self.k3D, self.Nmodes3D, self.Pk, self.XPk = o["k3D"], o["Nmodes3D"], o["Pk"], o["XPk"]
         print("Time taken = %.2f seconds" % (time.time() - start))
@@ -262,7 +262,8 @@ def XPk_2D(delta1, delta2, BoxSize, axis=2, MAS1="CIC", MAS2="CIC", threads=1):
     out, lay = _P.bin_device(dk, [_P.MAS_function(MAS1), _P.MAS_function(MAS2)], dims, axis)
     o = _P.finalize_device(out, lay, BoxSize, dims)          # Pk2D = sum*fact/Nmodes2D, the expression of :1860-1862
     print("Time compute modulus = %.2f" % (time.time() - start2))
-    res = [o["kpar"], o["kper"], np.ascontiguousarray(o["Pk2D"][:, 0]), np.ascontiguousarray(o["Pk2D"][:, 1]),
+    kpar, kper = _P._kpar_kper(*o["kgrid"])
+    res = [kpar, kper, np.ascontiguousarray(o["Pk2D"][:, 0]), np.ascontiguousarray(o["Pk2D"][:, 1]),
            np.ascontiguousarray(o["PkX2D"][:, 0]), o["Nmodes2D"]]
     print("Time taken = %.2f seconds" % (time.time() - start))
     return res

@@ -182,7 +182,7 @@ class DeviceOps:
                               flags=L.PK_KY_MAJOR if ky_major else 0)
 
 
-class _Result:
+class _Result(PKL.K2D):
     pass
 
 
@@ -619,7 +619,7 @@ class SlabContext:
         o = self._spectra([dk], [PKL.MAS_function(MAS)], axis, True, density, offset)
         r = _Result()
         r.k1D, r.Pk1D, r.Nmodes1D = o["k1D"], o["Pk1D"][:, 0], o["Nmodes1D"]
-        r.kpar, r.kper, r.Pk2D, r.Nmodes2D = o["kpar"], o["kper"], o["Pk2D"][:, 0], o["Nmodes2D"]
+        r._kgrid, r.Pk2D, r.Nmodes2D = o["kgrid"], o["Pk2D"][:, 0], o["Nmodes2D"]
         r.k3D, r.Nmodes3D = o["k3D"], o["Nmodes3D"]
         r.Pk, r.Pkphase = np.ascontiguousarray(o["Pk"][:, :, 0]), o["Pkphase"]
         return r
@@ -634,6 +634,6 @@ class SlabContext:
         o = self._spectra(dk, [PKL.MAS_function(m) for m in MAS], axis, False, density, offset)
         r = _Result()
         r.k1D, r.Nmodes1D, r.Pk1D, r.PkX1D = o["k1D"], o["Nmodes1D"], o["Pk1D"], o["PkX1D"]
-        r.kpar, r.kper, r.Nmodes2D, r.Pk2D, r.PkX2D = o["kpar"], o["kper"], o["Nmodes2D"], o["Pk2D"], o["PkX2D"]
+        r._kgrid, r.Nmodes2D, r.Pk2D, r.PkX2D = o["kgrid"], o["Nmodes2D"], o["Pk2D"], o["PkX2D"]
         r.k3D, r.Nmodes3D, r.Pk, r.XPk = o["k3D"], o["Nmodes3D"], o["Pk"], o["XPk"]
         return r

@@ -279,7 +279,7 @@ def test_device_finalisation_equals_host_finalisation(env, oracle, N, F):
         # ONE run of the bin kernel (its float64 reductions are not ordered), finalised both ways
         out, lay = PKL.bin_device(dk, mi, N, axis, F == 1)
         host = PKL._finalize(PKL.unpack_raw(out.cpu().numpy(), lay), BOX, N)
-        dev = PKL.finalize_device(out, lay, BOX, N)
+        dev = PKL.finalize_device(out, lay, BOX, N, k2d_on_device=True)
         assert set(host) == set(dev)
         for k in host:
             a, b = np.asarray(dev[k], dtype=np.float64), np.asarray(host[k], dtype=np.float64)
