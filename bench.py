@@ -474,7 +474,7 @@ def run_ours(args, wl, grid_n):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/pyl_b200_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
-    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, _device as D, _lib, prebias_, synth
+    from pylians3_b200 import MAS_library as MASL, Pk_library as PKL, _device as D, _lib, overdensity_, prebias_, synth
     lib = _lib.load()
     MAS, AXIS = wl["mas"], wl["axis"]
     npart = grid_n ** 3
@@ -494,6 +494,11 @@ def run_ours(args, wl, grid_n):
         slab = ctx.new_slab()
 
         def step(p, w):
+            if not p.is_cuda:                                # e2e, inputs on the host: the caller's classic recipe
+                slab.zero_()                                 # (an exact sum of GBs of host weights would cost more
+                ctx.MA(p, slab, MAS, W=w, routed=False)      # than the pass it saves; the PCIe copy bounds this path)
+                ctx.overdensity_(slab)
+                return ctx.Pk(slab, AXIS, MAS)
             c = ctx.prebias_(slab, p.shape[0], w)            # -c instead of 0: the transform sees n - c, not n
             ctx.MA(p, slab, MAS, W=w, routed=False)
             return ctx.Pk(slab, AXIS, MAS, density=True, offset=c)   # spectrum of n/<n> - 1: a scale of the sums
@@ -501,6 +506,11 @@ def run_ours(args, wl, grid_n):
         grid = torch.zeros((grid_n, grid_n, grid_n), dtype=torch.float32, device=dev)
 
         def step(p, w):
+            if not p.is_cuda:                                # e2e, inputs on the host: the caller's classic recipe
+                grid.zero_()                                 # (an exact sum of GBs of host weights would cost more
+                MASL.MA(p, grid, BOX, MAS, w)                # than the pass it saves; the PCIe copy bounds this path)
+                overdensity_(grid)
+                return PKL.Pk(grid, BOX, AXIS, MAS, verbose=False)
             c = prebias_(grid, p.shape[0], w)                # -c instead of 0: the transform sees n - c, not n
             MASL.MA(p, grid, BOX, MAS, w)
             return PKL.Pk(grid, BOX, AXIS, MAS, verbose=False, density=True, offset=c)   # n/<n> - 1 as a scale

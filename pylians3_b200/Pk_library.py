@@ -314,6 +314,10 @@ def spectra(dk_list, mas_index, dims, axis, BoxSize, want_phase=False, flags=0, 
     """bin + finalise: device finalisation for up to L.MAX_FIELDS fields, host assembly beyond.
     density=True: the fields are transforms of densities n (minus the constants `offset`); the spectra are those
     of n/<n> - 1."""
+    if density and offset is None:
+        raise ValueError("density=True needs offset=: the constant taken out of the grid before the deposit "
+                         "(c = prebias_(grid, particles, W)); offset=0.0 transforms the raw density, whose float32 "
+                         "FFT noise is ~1e-7 sqrt(cells)/sigma relative to the fluctuation modes")
     dc = take_dc(dk_list) if density else None
     off = _offsets(offset, len(dk_list), dk_list[0].device) if density else None
     if len(dk_list) <= L.MAX_FIELDS:
@@ -415,9 +419,11 @@ class Pk(K2D):
     spectrum of n/<n> - 1 -- the caller's `delta /= np.mean(delta); delta -= 1` (Pk_snapshot.py:88-89) folded into
     the scale of the binned sums, <n> read from the DC mode, which is then dropped (its Pk2D[0] slot reads 0
     where the reference leaves the squared rounding residue of sum(delta)).
-    offset=c: the grid holds n - c (the deposit started from -c: `c = prebias_(grid, particles, W)` instead of
-    zeroing it), <n> = c + DC/dims^3.  Recommended from 256^3 on: a float32 transform of a field whose mass sits in
-    the DC mode leaves rounding noise ~1e-7 dims/sigma (relative amplitude) on the axes through k = 0."""
+    offset=c (required with density=True): the grid holds n - c (the deposit started from -c:
+    `c = prebias_(grid, particles, W)` instead of zeroing it), <n> = c + DC/dims^3.  A float32 transform carries
+    rounding noise proportional to its largest amplitude; with the whole mass in the DC mode that is
+    ~1e-7 sqrt(cells)/sigma relative to the fluctuation modes (3e-4 in power at 64^3 with 8 particles per cell,
+    1e-2 at 1024^3), so the constant has to go before the transform.  offset=0.0 is accepted for small grids."""
 
     def __init__(self, delta, BoxSize, axis=2, MAS="CIC", threads=1, verbose=True, density=False, offset=None):
         start = time.time()

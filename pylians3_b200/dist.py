@@ -466,14 +466,14 @@ class SlabContext:
 
     def prebias_(self, slab, particles, W=None):
         """field.prebias_ for a slab: every rank fills its planes with the SAME -c (a rank-dependent constant
-        would be a step function along x), c = all-reduced particles * mean(sampled weights) / dims^3.  `particles`
+        would be a step function along x), c = all-reduced sum of the weights / dims^3.  `particles`
         and `W` are this rank's share before routing.  Returns c (CUDA float64[1]) for Pk(..., offset=c).
         CPU stand-ins (tests) zero the slab and return 0."""
         if self.device.type != "cuda":
             slab.zero_()
             return torch.zeros(1, dtype=torch.float64)
         from . import field
-        scale = field.weight_estimate(particles, W, self.device)
+        scale = field.weight_total(particles, W, self.device)
         dist.all_reduce(scale, group=self.group)
         return field.prebias_(slab, None, cells=float(self.dims) ** 3, scale=scale)
 
@@ -597,6 +597,8 @@ class SlabContext:
             if marks is not None:
                 marks[key] = torch.cuda.Event(enable_timing=True)
                 marks[key].record()
+        if density and offset is None:
+            raise ValueError("density=True needs offset= (c = prebias_(slab, particles, W) before the deposit)")
         dc = PKL.take_dc(dk_list, holds_dc=(self.ky_lo == 0 and self.ny_lo > 0)) if density else None
         out, lay = self.ops.bin(dk_list, mas_index, self.dims, axis, want_phase, self.ky_lo, self.ny_lo)
         extra = 0

@@ -36,19 +36,21 @@ def overdensity_(grid, total=None, cells=None):
 
 def prebias_(grid, particles, W=None, cells=None, scale=None):
     """Start value for a deposit whose spectrum is taken with Pk(..., density=True, offset=c): fills `grid` with
-    -c, c ~ the mean density the deposit will produce (particles/cells, times the mean of a strided sample of at
-    most 2^20 weights), and returns c -- the exact float32 fill value -- as a CUDA float64[1] tensor.
+    -c, c = the mean density the deposit will produce (sum of the weights / cells), and returns c -- the exact
+    float32 fill value -- as a CUDA float64[1] tensor.
 
-    Why: a float32 FFT carries rounding noise proportional to its largest partial sums; a density grid has its
-    whole mass in the DC mode and the noise lands on the axes through k = 0.  With the constant taken out beforehand
-    the transform sees n - c, the DC mode is the (small) estimation error of c, and <n> = c + DC/cells exactly.
-    No host synchronisation: c stays on the device.  `scale` (CUDA float64[1]) replaces particles * mean(sample)
-    by an agreed numerator (multi-GPU: the all-reduced one, see SlabContext.prebias_)."""
+    Why: a float32 FFT carries rounding noise proportional to its largest amplitudes; a density grid has its whole
+    mass in the DC mode.  With the constant taken out beforehand the transform sees n - c, the DC mode is what is
+    left of c's rounding, and <n> = c + DC/cells exactly.  The sum of the weights is exact (one pass over W on the
+    device, 4 bytes per particle; nothing for unweighted particles) because the residual DC must stay below the
+    fluctuation modes: |<n> - c|/<n> << sigma/sqrt(cells), 1e-5 at 1024^3.  No host synchronisation: c stays on
+    the device.  `scale` (CUDA float64[1]) replaces the sum by an agreed numerator (multi-GPU: the all-reduced
+    one, see SlabContext.prebias_)."""
     if not D.is_cuda_tensor(grid) or grid.dtype != torch.float32 or not grid.is_contiguous():
         raise ValueError("grid must be a contiguous float32 CUDA tensor")
     cells = grid.numel() if cells is None else cells
     if scale is None:
-        scale = weight_estimate(particles, W, grid.device)
+        scale = weight_total(particles, W, grid.device)
     c = torch.empty(1, dtype=torch.float64, device=grid.device)
     with torch.cuda.device(grid.device):
         L.check(L.load().pyl_fill_negative(D.ptr(grid), grid.numel(), D.ptr(scale), float(cells), D.ptr(c),
@@ -56,13 +58,27 @@ def prebias_(grid, particles, W=None, cells=None, scale=None):
     return c
 
 
-def weight_estimate(particles, W, device):
-    """particles * mean(W) from a strided sample of at most ~2^20 weights (particles if W is None), as a float64[1]
-    tensor on `device`; W may live on the host (torch tensor or ndarray) or on the device."""
+HOST_SUM_LIMIT = 1 << 24
+
+
+def weight_total(particles, W, device):
+    """Sum of the weights (the particle count if W is None) as a float64[1] tensor on `device`.  CUDA weights: exact
+    float64 sum (pyl_sum_f64).  Host weights: exact up to HOST_SUM_LIMIT elements; beyond that particles * mean of a
+    strided sample of 2^20 weights -- an ESTIMATE (a pass over GBs of host memory would cost more than the
+    overdensity_ pass prebias_ replaces), good to ~1e-3: use overdensity_ instead when weights of that size
+    live on the host."""
     if W is None:
         return torch.full((1,), float(particles), dtype=torch.float64, device=device)
+    if D.is_cuda_tensor(W):
+        if W.dtype != torch.float32 or not W.is_contiguous():
+            raise ValueError("W must be a contiguous float32 tensor")
+        return grid_sum(W)
     if not torch.is_tensor(W):
         W = torch.from_numpy(W)
-    stride = max(1, W.numel() >> 20)
-    m = W.reshape(-1)[::stride].to(torch.float64).mean().reshape(1) * float(particles)
+    W = W.reshape(-1)
+    if W.numel() <= HOST_SUM_LIMIT:
+        m = W.to(torch.float64).sum().reshape(1)
+    else:
+        stride = max(1, W.numel() >> 20)
+        m = W[::stride].to(torch.float64).mean().reshape(1) * float(particles)
     return m.to(device, non_blocking=True)

@@ -81,9 +81,9 @@ def _worker(rank, world, port, N, q, transpose="peer"):
         wx = quiet(O.XPk, [refs["PCS"], refs["CIC"]], BOX, 0, ["PCS", "CIC"], 1)
         check_pk(gx, wx, cross=True)
         # density=True: the slabs keep n, the normalisation is the scale of the binned sums (DC mode all-reduced)
-        check_pk(ctx.Pk(dens["PCS"], 1, "PCS", density=True), O.Pk(refs["PCS"], BOX, 1, "PCS", 1, False),
+        check_pk(ctx.Pk(dens["PCS"], 1, "PCS", density=True, offset=0.0), O.Pk(refs["PCS"], BOX, 1, "PCS", 1, False),
                  phase_min_modes=64)
-        check_pk(ctx.XPk([dens["PCS"], dens["CIC"]], 0, ["PCS", "CIC"], density=True), wx, cross=True)
+        check_pk(ctx.XPk([dens["PCS"], dens["CIC"]], 0, ["PCS", "CIC"], density=True, offset=0.0), wx, cross=True)
         # the bench step's recipe: every rank fills its slab with the same -c, deposits, and passes c on
         slab = ctx.new_slab()
         w_mine = torch.from_numpy(W[mine].copy()).to(dev)

@@ -375,7 +375,9 @@ def test_pk_of_a_density_equals_pk_of_its_overdensity(env, oracle, N, axis):
     for fi in (0, 1):
         ref = oracle.Pk(delta[fi], BOX, axis, mas[fi], 1, False)
         d = torch.from_numpy(dens[fi]).cuda()
-        got = PKL.Pk(d, BOX, axis, mas[fi], verbose=False, density=True)
+        with pytest.raises(ValueError):
+            PKL.Pk(d, BOX, axis, mas[fi], verbose=False, density=True)      # the offset has to be stated
+        got = PKL.Pk(d, BOX, axis, mas[fi], verbose=False, density=True, offset=0.0)
         check_pk(got, ref, phase_min_modes=64)       # (a different field goes through the float32 transform)
         assert torch.equal(d.cpu(), torch.from_numpy(dens[fi]))            # the density is not modified
         assert got.Pk2D[0] == 0.0                                          # the DC mode is dropped, not binned
@@ -402,19 +404,25 @@ def test_prebias_then_deposit_then_density_spectrum(env, oracle):
     for w_arg in (W_d, W):                              # weights on the device, or still on the host
         grid = torch.empty((N, N, N), dtype=torch.float32, device="cuda")
         c = prebias_(grid, len(pos), w_arg)
-        assert abs(float(c) / float(dens.mean(dtype=np.float64)) - 1.0) < 0.02
+        assert abs(float(c) / float(dens.mean(dtype=np.float64)) - 1.0) < 1e-6      # the exact sum of the weights
         assert torch.all(grid == -c.float())
         MASL.MA(pos_d, grid, BOX, "PCS", W_d)
-        assert rel_err((grid.double() + c).float().cpu().numpy(), dens, floor=float(dens.mean())) < 1e-5
-        check_pk(PKL.Pk(grid, BOX, 0, "PCS", verbose=False, density=True, offset=c), want, phase_min_modes=64)
-
+        got_dens = (grid.double() + c).float().cpu().numpy()
+        assert rel_err(got_dens, dens, floor=float(dens.mean())) < 1e-5
+        fused = PKL.Pk(grid, BOX, 0, "PCS", verbose=False, density=True, offset=c)
+        check_pk(fused, want, phase_min_modes=1 << 30)              # Pk, Pk1D, Pk2D, counts against the oracle's chain
+        # the phase statistic hangs on modes at the float32 noise floor: the two DEPOSITS (accumulation order) move
+        # it by 2e-4 in one shell whatever transforms them, so it is held to the oracle's Pk of THIS deposit
+        got_dens /= np.mean(got_dens, dtype=np.float64)
+        got_dens -= 1.0
+        check_pk(fused, oracle.Pk(got_dens, BOX, 0, "PCS", 1, False), phase_min_modes=64)
 
 @pytest.mark.parametrize("N,F", [(48, 2), (40, 3), (32, 4), (24, 6)])
 def test_xpk_of_densities(env, oracle, N, F):
     torch, MASL, PKL, _ = env
     dens, delta, mas = make_densities(oracle, N, F, 300 + N + F)
     ref = quiet(oracle.XPk, delta, BOX, 2, mas, 1)
-    got = quiet(PKL.XPk, dens, BOX, 2, mas, 1, density=True)
+    got = quiet(PKL.XPk, dens, BOX, 2, mas, 1, density=True, offset=0.0)
     check_pk(got, ref, cross=True)
     cs = [float(np.float32(1.02 * d.mean())) for d in dens]
     got = quiet(PKL.XPk, [d - np.float32(c) for d, c in zip(dens, cs)], BOX, 2, mas, 1, density=True, offset=cs)
