@@ -52,11 +52,11 @@ elif what == "step3":
     W = synth.weights_device(N ** 3, 3, dev)
     torch.cuda.empty_cache()
     grid = torch.zeros((N, N, N), dtype=torch.float32, device=dev)
+    from pylians3_b200 import prebias_
     for _ in range(reps):
-        grid.zero_()
+        c = prebias_(grid, pos.shape[0], W)
         MASL.MA(pos, grid, BOX, "PCS", W)
-        overdensity_(grid)
-        pk = PKL.Pk(grid, BOX, 0, "PCS", verbose=False)
+        pk = PKL.Pk(grid, BOX, 0, "PCS", verbose=False, density=True, offset=c)
     torch.cuda.synchronize()
     print("Pk0[:3] =", pk.Pk[:3, 0])
 elif what == "step":
