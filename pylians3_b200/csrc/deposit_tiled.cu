@@ -407,9 +407,11 @@ __global__ void __launch_bounds__(PT, 1024 / PT) partition_kernel(PartArgs a, Ti
     __syncthreads();
     bool ordered = false;
     if (LEVEL == 1 && g.ntx < 1024 && g.nty < 1024 && g.ntz < 1024) {
-        // cheap vote first: in half of the warps at least three lanes share lane 0's tile (random order: none does)
-        const unsigned lead = __shfl_sync(0xffffffffu, tl[0], 0);
-        const int agree = __popc(__ballot_sync(0xffffffffu, tl[0] == lead));
+        // cheap vote first: in half of the warps at least three lanes share a tile (random order: none does).  The
+        // largest group counts, not lane 0's: in lattice order lane 0 sits ON a tile boundary, and a coherent flow of
+        // a cell or two towards lower z leaves it alone in the previous tile (38 % of the CTAs of BASELINE config 3
+        // failed the lane-0 vote and took both passes)
+        const int agree = __reduce_max_sync(0xffffffffu, __popc(__match_any_sync(0xffffffffu, tl[0])));
         ordered = __syncthreads_count(lane == 0 && agree >= 3) >= PT / 32 / 2;
     }
     if (ordered) {
