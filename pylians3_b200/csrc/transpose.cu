@@ -20,6 +20,9 @@ namespace pyl {
 #ifndef PYL_TR_V
 #define PYL_TR_V 2           // 1: 8-byte stores; 2: 16-byte stores after aligning the destination row
 #endif
+#ifndef PYL_TR_CTAS_PER_SM
+#define PYL_TR_CTAS_PER_SM 2
+#endif
 constexpr int TR_THREADS = PYL_TR_THREADS;
 constexpr int TR_MAX_RANKS = 16;
 
@@ -35,11 +38,18 @@ struct TransposeArgs {
 };
 
 __global__ void __launch_bounds__(TR_THREADS) transpose_scatter_kernel(const TransposeArgs A) {
-    // CTAs are scheduled in blockIdx order.  With ky = blockIdx.x every rank would sweep the owners in the same
+    // A SMALL persistent grid (PYL_TR_CTAS_PER_SM CTAs per SM, grid-stride over the rows): the kernel is bound by the
+    // NVLink, which a quarter of the thread slots saturates, and it runs NEXT TO the 2D-FFT kernels of the following
+    // batch.  With one CTA per row (65 536 per batch at 4096^3) whichever kernel was scheduled first filled every SM
+    // and the two streams took turns: 2D FFTs + transposes cost their SUM (102 of 38 + 66 ms), not their maximum.
+    // Row order: CTAs are scheduled in blockIdx order.  With ky = column every rank would sweep the owners in the same
     // order at the same time -- all senders on one or two receivers' NVLink ingress, the other links idle (the
-    // all-to-all incast: 0.44 of the link rate at 4096^3 on 8 GPUs).  ky_order interleaves the owners row by row,
-    // starting with a different owner on every rank, so every wave of CTAs writes to all ranks at once.
-    const int ky = A.ky_order != nullptr ? __ldg(A.ky_order + blockIdx.x) : (int)blockIdx.x, ix = blockIdx.y;
+    // all-to-all incast).  ky_order interleaves the owners row by row, starting with a different owner on every
+    // rank, so the rows in flight at any time go to all ranks.
+    const int64_t rows = (int64_t)A.N * A.nx;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int col = (int)(row % A.N), ix = (int)(row / A.N);
+    const int ky = A.ky_order != nullptr ? __ldg(A.ky_order + col) : col;
     const int r = __ldg(A.ky_owner + ky), j = __ldg(A.ky_row + ky);
     const float2 *src = A.src + ((int64_t)ix * A.N + ky) * A.nz;
     float2 *dst = A.ky_major ? A.peer[r] + ((int64_t)j * A.N + (A.x0 + ix)) * A.nz
@@ -93,6 +103,7 @@ __global__ void __launch_bounds__(TR_THREADS) transpose_scatter_kernel(const Tra
     }
     if (((A.nz - head) & 1) && threadIdx.x == 32) dst[A.nz - 1] = __ldg(src + A.nz - 1);
 #endif
+    }
 }
 
 }  // namespace pyl
@@ -117,7 +128,9 @@ static int transpose_scatter(const float *slab_k, void *const *peer_recv, const 
     }
     A.ky_owner = ky_owner; A.ky_row = ky_row; A.ky_order = ky_order;
     A.N = dims; A.nz = dims / 2 + 1; A.nx = nx; A.x0 = x0; A.ky_major = ky_major;
-    transpose_scatter_kernel<<<dim3((unsigned)dims, (unsigned)nx), TR_THREADS, 0, as_stream(stream)>>>(A);
+    int64_t ctas = (int64_t)sm_count() * PYL_TR_CTAS_PER_SM;
+    if (ctas > (int64_t)dims * nx) ctas = (int64_t)dims * nx;
+    transpose_scatter_kernel<<<(unsigned)ctas, TR_THREADS, 0, as_stream(stream)>>>(A);
     PYL_LAUNCH_CHECK();
     return PYL_OK;
 }
