@@ -196,45 +196,15 @@ __device__ __forceinline__ Segment super_segment(const unsigned *__restrict__ st
     return sg;
 }
 
-// cur2[t] = bucket start of tile t; cur1[r][s] = start of sub-segment (s, r); spre = exclusive prefix over
-// super-tiles of the number of PP-particle chunks one replica sub-segment can hold (CTA -> work map of pass 2)
+// cur2[t] = bucket start of tile t; cur1[r][s] = start of sub-segment (s, r) of buf1
 __global__ void __launch_bounds__(1024) tile_setup_kernel(const unsigned *__restrict__ starts, TileGeom g,
-                                                          unsigned *__restrict__ cur1, unsigned *__restrict__ cur2,
-                                                          unsigned *__restrict__ spre) {
-    if (blockIdx.x > 0) {
-        const unsigned i = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
-        if (i < g.ntiles) cur2[i] = starts[i];
-        return;
+                                                          unsigned *__restrict__ cur1, unsigned *__restrict__ cur2) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < g.ntiles) cur2[i] = starts[i];
+    if (i < g.nsuper) {
+        const Segment sg = super_segment(starts, g, i, 0);
+        for (unsigned r = 0; r < g.repl; r++) cur1[r * g.nsuper + i] = sg.begin + r * sg.cap;
     }
-    __shared__ unsigned part[32];
-    __shared__ unsigned carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned s0 = 0; s0 < g.nsuper; s0 += 1024) {
-        const unsigned s = s0 + threadIdx.x;
-        unsigned nch = 0;
-        if (s < g.nsuper) {
-            const Segment sg = super_segment(starts, g, s, 0);
-            nch = (sg.cap + PP - 1) / PP;
-            for (unsigned r = 0; r < g.repl; r++) cur1[r * g.nsuper + s] = sg.begin + r * sg.cap;
-        }
-        unsigned incl = nch;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) part[warp] = incl;
-        __syncthreads();
-        unsigned base = carry;
-        for (int w = 0; w < warp; w++) base += part[w];
-        if (s < g.nsuper) spre[s] = base + incl - nch;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = base + incl;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) spre[g.nsuper] = carry;
 }
 
 // ---- 3./4. partition passes ---------------------------------------------------------------------------------
@@ -261,7 +231,6 @@ struct PartArgs {
     const unsigned *starts;      // ntiles + 1 bucket starts
     unsigned *cur1;              // [repl][nsuper]
     unsigned *cur2;              // [ntiles]
-    const unsigned *spre;        // nsuper + 1
     float *number;               // the grid (overflow path only)
     unsigned long long *dropped;
     double *wsum;                // sum of |W| over the particles of this call (pass 1, weighted only)
@@ -858,7 +827,6 @@ struct TiledWorkspace {
     unsigned *starts;             // ntiles + 1 : sampled counts -> capacities -> exclusive scan
     unsigned *cur2;               // ntiles : next free slot of a tile's bucket
     unsigned *cur1;               // MAX_REPL x nsuper : next free slot of a super-tile sub-segment
-    unsigned *spre;               // nsuper + 1
     void *scan_tmp;
     size_t scan_bytes;
     size_t total;
@@ -881,8 +849,6 @@ static TiledWorkspace carve(void *ws, int64_t particles, const TileGeom &g) {
     off += align_up((size_t)g.ntiles * 4, 256);
     w.cur1 = reinterpret_cast<unsigned *>(base + off);
     off += align_up((size_t)MAX_REPL * g.nsuper * 4, 256);
-    w.spre = reinterpret_cast<unsigned *>(base + off);
-    off += align_up(((size_t)g.nsuper + 1) * 4, 256);
     w.scan_tmp = base + off;
     w.scan_bytes = scan_temp_bytes(g.ntiles + 1);
     off += align_up(w.scan_bytes, 256);
@@ -916,7 +882,7 @@ static int run_tiled_w(const float *pos, float *number, const float *W, int64_t 
     }
     PartArgs a;
     a.pos = pos; a.W = W; a.particles = particles; a.in = w.buf1; a.out = w.buf1; a.out2 = w.buf2;
-    a.starts = w.starts; a.cur1 = w.cur1; a.cur2 = w.cur2; a.spre = w.spre; a.number = number; a.dropped = dropped;
+    a.starts = w.starts; a.cur1 = w.cur1; a.cur2 = w.cur2; a.number = number; a.dropped = dropped;
     a.wsum = w.wsum;
     a.n_dev = n_dev;
     if (WEIGHTED) PYL_CUDA_CHECK(cudaMemsetAsync(w.wsum, 0, 8, stream));
@@ -958,7 +924,7 @@ static int run_tiled(const float *pos, float *number, const float *W, int64_t pa
     PYL_LAUNCH_CHECK();
     PYL_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.scan_tmp, const_cast<size_t &>(w.scan_bytes), w.starts, w.starts,
                                                  (int)(g.ntiles + 1), stream));
-    tile_setup_kernel<<<1 + (g.ntiles + 1023) / 1024, 1024, 0, stream>>>(w.starts, g, w.cur1, w.cur2, w.spre);
+    tile_setup_kernel<<<(g.ntiles + 1023) / 1024, 1024, 0, stream>>>(w.starts, g, w.cur1, w.cur2);
     PYL_LAUNCH_CHECK();
     if (W) return run_tiled_w<MAS, true>(pos, number, W, particles, g, w, dropped, n_dev, stream);
     return run_tiled_w<MAS, false>(pos, number, W, particles, g, w, dropped, n_dev, stream);
