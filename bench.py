@@ -746,6 +746,9 @@ def run_ours(args, wl, grid_n):
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": e2e_steps,
                     "h2d_GBps_per_gpu": h2d / (ms_e2e * 1e-3) / 1e9,
                     "note": "upper bound per GPU = PCIe gen5 x16, ~55 GB/s: the copy, not the kernels, bounds e2e",
+                    "recipe": "inputs in pinned host memory: zero -> MA (host chunks streamed under the deposit) -> "
+                              "overdensity_ -> Pk; the device-resident step folds the normalisation into the spectrum "
+                              "(prebias_ + density=True), whose exact weight sum would be a pass over host memory here",
                     "host_cpus_rank0": (None if numa is None else "%d CPUs from %d (NVML ideal affinity)" % (len(numa), numa[0]))},
             "gpu_launches": int(gpu_launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
             "stages_ms": stages, "ma_particles_per_s": ma_rates, "check": check,
